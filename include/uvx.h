@@ -1,0 +1,169 @@
+/* libuvx - C ABI of the B200-native Ultravox audio->LLM hot path.
+ *
+ * The reference (fixie-ai/ultravox @ 648efe7f) has NO native / FFI boundary: its hot path is Python over
+ * transformers/torch.  This header is therefore the boundary a maintainer would bind from
+ * `ultravox/model/ultravox_model.py` / `ultravox_processing.py` with ctypes; every entry
+ * cites the reference (or third-party) function whose arithmetic it replaces.  `ref:` = /root/reference,
+ * `hf:` = transformers (4.51.3 pinned by the reference; same formulas in 5.5.0).
+ *
+ * Conventions
+ *   - plain pointers + sizes only; all pointers are DEVICE pointers unless named host_*;
+ *   - bf16 tensors are passed as `const void*` / `void*` (2-byte elements, row-major);
+ *   - every call is asynchronous on `stream` (a cudaStream_t), allocates nothing, performs no host
+ *     synchronisation and keeps no mutable global state (immutable per-device tables - twiddles, mel
+ *     filters - are built once on first use);
+ *   - returns 0 on success, a negative UVX_ERR_* otherwise; `uvx_last_error()` gives the message
+ *     (thread-local).  Argument validation that the reference does in Python stays in Python.
+ */
+#ifndef UVX_H_
+#define UVX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UVX_ABI_VERSION 1
+
+#define UVX_OK 0
+#define UVX_ERR_ARG (-1)   /* bad shape / alignment / null pointer */
+#define UVX_ERR_CUDA (-2)  /* CUDA runtime / driver error (launch failure, tensor-map encode, ...) */
+#define UVX_ERR_WS (-3)    /* workspace too small */
+
+typedef void* uvx_stream_t; /* cudaStream_t */
+
+int uvx_abi_version(void);
+const char* uvx_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's "gpu_launches") */
+int64_t uvx_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * a1 / K1-K3  log-mel front end.
+ * Replaces WhisperFeatureExtractor._torch_extract_fbank_features (hf:models/whisper/
+ * feature_extraction_whisper.py:135-164; call site ref:ultravox/model/ultravox_processing.py:295-303):
+ * reflect-pad 200, 400-point periodic-hann STFT with hop 160, last frame dropped, |.|^2, slaney mel
+ * filterbank (n_mels 80 or 128), log10(max(.,1e-10)), per-clip max-8 floor, (x+4)/4.
+ *   wave      [B, L] fp32, L % 160 == 0 (zero-padded by the host like the extractor does)
+ *   out_f32   [B, n_mels, T] fp32, T = L/160 (the reference's `audio_values` layout) or NULL
+ *   out_tm    [B, T + 2, n_mels] bf16 time-major with one zero row before and after each clip (the
+ *             layout the conv stem consumes, see uvx_gemm_bf16) or NULL
+ *   workspace >= uvx_logmel_workspace(B, L, n_mels) bytes                                            */
+size_t uvx_logmel_workspace(int64_t B, int64_t L, int n_mels);
+int uvx_logmel(const float* wave, int64_t B, int64_t L, int n_mels, float* out_f32, void* out_tm,
+               void* workspace, size_t workspace_bytes, uvx_stream_t stream);
+
+/* host-only helper: writes the dense [201, n_mels] fp32 slaney filterbank the library uses (no GPU needed) */
+int uvx_debug_mel_filters(int n_mels, float* host_dense);
+
+/* `audio_values` [N, n_mels, T] fp32 (as produced by the reference processor / collator, any padding
+ * content) -> bf16 time-major [N, T + 2, n_mels] with zero guard rows.  Replaces the
+ * `audio_values.to(dtype)` cast of ref:ultravox/model/ultravox_model.py:382-385.                      */
+int uvx_mel_to_timemajor(const float* mel, int64_t N, int n_mels, int64_t T, void* out_tm, uvx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense contraction on tcgen05 tensor cores (TMA -> smem -> tcgen05.mma -> TMEM -> epilogue).
+ *   C[row(b,m), n] = act( alpha * sum_k A[b,m,k] * W[n,k] + bias[n] ) + R[b,m,n]
+ * A is addressed as A + b*a_batch_stride + m*a_row_stride + k (elements), which lets the same kernel run
+ *   - every nn.Linear of the path (hf:models/whisper/modeling_whisper.py:279-335,403-408;
+ *     hf:models/llama/modeling_llama.py:171-184,262-288; ref:ultravox/model/ultravox_model.py:793-799),
+ *   - conv1 / conv2 of the Whisper stem as implicit GEMMs over the time-major padded activation
+ *     (ref:ultravox/model/ultravox_model.py:893-894): row m of clip b is the 3*C contiguous elements
+ *     starting at frame stride*m of the guard-padded buffer, W is the conv weight re-laid as [C_out, 3*C_in].
+ * Output rows: c_row_map ? c_row_map[b*a_rows+m] (negative = drop) : b*c_batch_rows + m + c_row_offset.
+ * R (optional) is addressed R + b*r_batch_stride + m*r_row_stride + n: residual stream (whisper/llama) or the
+ * positional embedding added after GELU (ref :896-899, r_batch_stride = 0).
+ * Requirements: K % 8 == 0, N % 64 == 0, strides % 8 == 0, 16-byte aligned bases.                       */
+enum { UVX_ACT_NONE = 0, UVX_ACT_GELU = 1 };
+enum { UVX_DT_BF16 = 0, UVX_DT_F32 = 1 };
+
+typedef struct uvx_gemm_args {
+  const void* A;            /* bf16 */
+  int64_t a_batch, a_rows, K;
+  int64_t a_row_stride, a_batch_stride;
+  const void* W;            /* bf16 [N, K] row-major (nn.Linear layout) */
+  int64_t N, w_row_stride;
+  void* C;                  /* bf16 or f32 */
+  int64_t c_row_stride, c_batch_rows, c_row_offset;
+  const int32_t* c_row_map; /* optional */
+  const void* bias;         /* bf16 [N] or NULL */
+  const void* R;            /* bf16 or NULL */
+  int64_t r_row_stride, r_batch_stride;
+  float alpha;
+  int32_t act;              /* UVX_ACT_* */
+  int32_t out_dtype;        /* UVX_DT_* */
+} uvx_gemm_args;
+
+int uvx_gemm_bf16(const uvx_gemm_args* args, uvx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row-wise normalisations (fp32 statistics, bf16 in/out).
+ * uvx_layernorm: nn.LayerNorm(eps 1e-5) of the Whisper encoder (hf:modeling_whisper.py:393,403;
+ *                ref:ultravox_model.py:980).
+ * uvx_rmsnorm:   LlamaRMSNorm (hf:models/llama/modeling_llama.py:53-67) and the projector RMSNorm
+ *                (ref:ultravox_model.py:733-736): y = w * bf16(x * rsqrt(mean(x^2) + eps)).
+ *                `valid_per_group`/`group_rows` implement StackAudioFrames (ref :722-730) without a copy:
+ *                rows are grouped `group_rows` per clip; row t of a clip only has
+ *                clamp(valid_elems - t*cols, 0, cols) real elements, the rest read as zero.
+ *                Pass group_rows = 0 for a plain matrix.                                               */
+int uvx_layernorm(const void* x, const void* w, const void* b, void* y, int64_t rows, int64_t cols,
+                  int64_t x_row_stride, float eps, uvx_stream_t stream);
+int uvx_rmsnorm(const void* x, const void* w, void* y, int64_t rows, int64_t cols, int64_t x_row_stride,
+                int64_t group_rows, int64_t group_stride, int64_t valid_elems, float eps, uvx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused softmax(QK^T*scale + mask)V, flash style, fp32 softmax, bf16 in/out.
+ *   Whisper encoder self-attention (hf:modeling_whisper.py:215-238,305-349): non-causal, keys >= kv_len[b]
+ *   masked (ref:ultravox_model.py:915-926), optional block-causal streaming mask (ref :834-863,928-936);
+ *   Llama attention (hf:modeling_llama.py:199-289): causal, grouped-query.
+ * q[b, i, h, :] = q + b*q_bs + i*q_rs + h*D  (same for k, v with h / (Hq/Hkv), and o).                  */
+typedef struct uvx_attn_args {
+  const void *q, *k, *v;
+  void* o;
+  int64_t B, Hq, Hkv, Sq, Skv, D;   /* D in {64, 128} */
+  int64_t q_rs, q_bs, k_rs, k_bs, v_rs, v_bs, o_rs, o_bs;
+  const int32_t* kv_len;            /* [B] or NULL (= Skv) */
+  int32_t causal;                   /* query i sees keys j <= i + (Skv - Sq) */
+  int32_t block;                    /* >0: block-causal, query i sees keys j with j/block <= i/block */
+  float scale;
+} uvx_attn_args;
+int uvx_attention(const uvx_attn_args* args, uvx_stream_t stream);
+
+/* RoPE on the q and k sections of a fused [rows, (Hq + 2*Hkv) * D] projection, in place
+ * (hf:modeling_llama.py:124-168; cos/sin tables [max_pos, D/2] fp32 built by the host exactly like
+ * LlamaRotaryEmbedding incl. llama3 scaling, hf:modeling_rope_utils.py:550-626).
+ * position of row r = positions ? positions[r] : pos_offset + (r % rows_per_seq).                      */
+int uvx_rope(void* qkv, int64_t rows, int64_t row_stride, int Hq, int Hkv, int D, const float* cos_tab,
+             const float* sin_tab, const int32_t* positions, int64_t rows_per_seq, int64_t pos_offset,
+             uvx_stream_t stream);
+
+/* out[r, j] = silu(gate) * lin where for x[r, 0:2H]:
+ *   gate_first = 0: lin = x[:, j], gate = x[:, H + j]   (ref SwiGLU, ultravox_model.py:739-742)
+ *   gate_first = 1: gate = x[:, j], lin = x[:, H + j]   (llama MLP act(gate)*up, hf:modeling_llama.py:183) */
+int uvx_swiglu(const void* x, void* out, int64_t rows, int64_t H, int64_t x_row_stride, int gate_first,
+               uvx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a11 + a5 (K14 + K15): token-embedding gather fused with the audio splice, sync-free and bit-exact.
+ * uvx_splice_plan builds src[b*S + s] = (row of audio_embeds) or -1 from the reference's index vectors
+ *   (ref:ultravox_model.py:259-275,390-394: chunks in batch order, later chunks overwrite earlier ones);
+ *   audio_embeds rows are a*tok_stride + j, j < audio_token_len[a].
+ * uvx_embed_splice writes out[b, s, :] = src >= 0 ? audio_embeds[src] : embed_tokens[input_ids[b, s]].  */
+int uvx_splice_plan(const int64_t* start_idx, const int32_t* tok_len, const int64_t* audio_batch_size,
+                    int64_t n_chunks, int64_t B, int64_t S, int64_t tok_stride, int32_t* src,
+                    uvx_stream_t stream);
+int uvx_embed_splice(const int64_t* input_ids, const void* embed_tokens, int64_t vocab, const void* audio_embeds,
+                     const int32_t* src, int64_t rows, int64_t d, void* out, uvx_stream_t stream);
+
+/* Last-position LM head: logits[b, v] = sum_k h[b, k] * W[v, k] (bf16 x bf16 -> f32), HBM-streaming GEMV
+ * (hf:modeling_llama.py:485-491 with logits_to_keep = 1), and greedy argmax (first maximal index, like
+ * torch.argmax; ref:ultravox/inference/infer.py:319-328 greedy path).                                  */
+int uvx_lm_head(const void* h, int64_t B, int64_t h_row_stride, const void* W, int64_t V, int64_t d,
+                float* logits, uvx_stream_t stream);
+int uvx_argmax(const float* logits, int64_t B, int64_t V, int64_t* out_idx, uvx_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UVX_H_ */

@@ -1,0 +1,10 @@
+"""ultravox_b200 - B200-native (sm_100a) implementation of the Ultravox audio->LLM hot path.
+
+Only what the path needs lives here: ``csrc/`` (hand-written CUDA + the C ABI ``libuvx.so``),
+``_lib`` (ctypes binding, fails loudly when the library is missing), ``ops`` (tensor-level wrappers and
+``torch.autograd.Function``s), and the host-side mirrors of the reference interface
+(``config``, ``processing``, ``model``).  There is no CPU fallback and nothing here imports ``oracle/``.
+"""
+from .config import LossConfig, LossFunction, LossMaskType, LoraConfigSimplified, UltravoxConfig, preset  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,378 @@
+// uvx_gemm_bf16: bf16 x bf16 -> fp32 GEMM on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+//
+//   C[row(b,m), n] = act(alpha * sum_k A[b,m,k] W[n,k] + bias[n]) + R[b,m,n]
+//
+// One CTA computes a 128 x BN output tile.  Warp roles (192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor of the A box {64 k, 128 rows, 1 batch} and the W box
+//               {64 k, BN rows} into a kStages-deep 128B-swizzled shared-memory ring, mbarrier expect_tx.
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32 accumulate in
+//               TMEM); tcgen05.commit releases ring slots / signals the epilogue.
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns per warp, fused bias / GELU / residual / row
+//               remap, 16-byte stores.
+// A is described by a 3-D tensor map (k, row, batch) with caller-chosen strides, so overlapping rows
+// (implicit-GEMM conv over a time-major activation) and batch-strided inputs need no im2col copy; rows or
+// k beyond the tensor bounds are zero-filled by TMA, which is how M / K tails are handled.
+#include "uvx_common.cuh"
+
+namespace uvx {
+
+static constexpr int kBM = 128;
+static constexpr int kBK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
+static constexpr int kThreads = 192;
+
+struct GemmParams {
+  int64_t a_rows, a_batch, K, N;
+  void* C;
+  int64_t c_row_stride, c_batch_rows, c_row_offset;
+  const int32_t* c_row_map;
+  const bf16* bias;
+  const bf16* R;
+  int64_t r_row_stride, r_batch_stride;
+  float alpha;
+  int act, out_f32;
+  int m_tiles;  // per batch
+};
+
+// ---------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile, 128-byte swizzle: rows are 128 B apart, 8-row groups 1024 B apart (SBO), LBO unused.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
+  d |= (uint64_t)(1024u >> 4) << 32;         // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int kABytes = kBM * kBK * 2;  // 16 KB
+  static constexpr int kWBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kWBytes;
+  static constexpr int kStages = (BN <= 64) ? 4 : 3;  // <= 96 KB so that two CTAs share an SM
+  static constexpr int kBarOff = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOff + 256 + 1024;  // barriers + slack for 1024-byte alignment
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+  using L = SmemLayout<BN>;
+  constexpr int kStages = L::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m_total = p.m_tiles * (int)p.a_batch;
+  const int tile = blockIdx.x;
+  const int tm_idx = tile % tiles_m_total;   // consecutive CTAs share the W tile
+  const int tn_idx = tile / tiles_m_total;
+  const int b = tm_idx / p.m_tiles;
+  const int m0 = (tm_idx % p.m_tiles) * kBM;
+  const int n0 = tn_idx * BN;
+  const int num_kb = (int)((p.K + kBK - 1) / kBK);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    constexpr uint32_t kCols = BN < 32 ? 32 : BN;
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        uint8_t* sa = smem + s * L::kStageBytes;
+        uint8_t* sw = sa + L::kABytes;
+        mbar_expect_tx(&full_bar[s], (uint32_t)L::kStageBytes);
+        tma_load_3d(sa, &tmA, kb * kBK, m0, b, &full_bar[s]);
+        tma_load_2d(sw, &tmW, kb * kBK, n0, &full_bar[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
+        const uint64_t da = make_smem_desc(sa);
+        const uint64_t dw = make_smem_desc(sa + L::kABytes);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+          umma_f16(tmem_base, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(tmem_full);  // accumulator complete
+    }
+  } else {
+    // ---- epilogue -------------------------------------------------------------------------
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int64_t m = (int64_t)m0 + row;
+    const bool row_ok = m < p.a_rows;
+    int64_t orow = -1;
+    if (row_ok) {
+      orow = p.c_row_map ? (int64_t)p.c_row_map[(int64_t)b * p.a_rows + m] : (int64_t)b * p.c_batch_rows + m + p.c_row_offset;
+    }
+    const bf16* rrow = (p.R && row_ok) ? p.R + (int64_t)b * p.r_batch_stride + m * p.r_row_stride : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
+      tmem_ld_wait();
+      if (orow >= 0) {
+        const int64_t n = (int64_t)n0 + c * 32;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
+        if (p.bias) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float t[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(p.bias + n + g * 8), t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[g * 8 + i] += t[i];
+          }
+        }
+        if (p.act == UVX_ACT_GELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        }
+        if (rrow) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float t[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(rrow + n + g * 8), t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[g * 8 + i] += t[i];
+          }
+        }
+        if (p.out_f32) {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + orow * p.c_row_stride + n);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        } else {
+          bf16x8* dst = reinterpret_cast<bf16x8*>(reinterpret_cast<bf16*>(p.C) + orow * p.c_row_stride + n);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) dst[g] = pack8(v + g * 8);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    constexpr uint32_t kCols = BN < 32 ? 32 : BN;
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, CUtensorMapL2promotion promo) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return UVX_ERR_CUDA;
+  }
+  cuuint64_t gd[3];
+  cuuint64_t gs[2];
+  cuuint32_t bx[3], es[3];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu stride %llu)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)strides_bytes[0]);
+    return UVX_ERR_CUDA;
+  }
+  return UVX_OK;
+}
+
+template <int BN>
+static int launch_gemm(const uvx_gemm_args* a, cudaStream_t stream) {
+  using L = SmemLayout<BN>;
+  CUtensorMap tmA, tmW;
+  {
+    uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->a_rows, (uint64_t)a->a_batch};
+    uint64_t st[2] = {(uint64_t)a->a_row_stride * 2, (uint64_t)(a->a_batch > 1 ? a->a_batch_stride : a->a_row_stride) * 2};
+    uint32_t box[3] = {kBK, kBM, 1};
+    int rc = encode_map(&tmA, a->A, 3, dims, st, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
+    uint64_t st[1] = {(uint64_t)a->w_row_stride * 2};
+    uint32_t box[2] = {kBK, (uint32_t)BN};
+    int rc = encode_map(&tmW, a->W, 2, dims, st, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (rc) return rc;
+  }
+  GemmParams p;
+  p.a_rows = a->a_rows;
+  p.a_batch = a->a_batch;
+  p.K = a->K;
+  p.N = a->N;
+  p.C = a->C;
+  p.c_row_stride = a->c_row_stride;
+  p.c_batch_rows = a->c_batch_rows;
+  p.c_row_offset = a->c_row_offset;
+  p.c_row_map = a->c_row_map;
+  p.bias = (const bf16*)a->bias;
+  p.R = (const bf16*)a->R;
+  p.r_row_stride = a->r_row_stride;
+  p.r_batch_stride = a->r_batch_stride;
+  p.alpha = a->alpha;
+  p.act = a->act;
+  p.out_f32 = a->out_dtype == UVX_DT_F32;
+  p.m_tiles = (int)((a->a_rows + kBM - 1) / kBM);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm_tc_kernel<%d>, smem %d): %s", BN, L::kTotal, cudaGetErrorString(e));
+      return UVX_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int64_t grid = (int64_t)p.m_tiles * a->a_batch * (a->N / BN);
+  gemm_tc_kernel<BN><<<(unsigned)grid, kThreads, L::kTotal, stream>>>(tmA, tmW, p);
+  return check_launch("gemm_tc_kernel");
+}
+
+}  // namespace uvx
+
+extern "C" int uvx_gemm_bf16(const uvx_gemm_args* a, uvx_stream_t stream_) {
+  using namespace uvx;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  UVX_REQUIRE(a && a->A && a->W && a->C, "uvx_gemm_bf16: null pointer");
+  UVX_REQUIRE(a->a_batch >= 1 && a->a_rows >= 1 && a->K >= 8 && a->N >= 64, "uvx_gemm_bf16: empty problem");
+  UVX_REQUIRE(a->K % 8 == 0 && a->N % 64 == 0, "uvx_gemm_bf16: K %% 8 and N %% 64 required (K=%lld N=%lld)",
+              (long long)a->K, (long long)a->N);
+  UVX_REQUIRE(a->a_row_stride % 8 == 0 && a->w_row_stride % 8 == 0 && (a->a_batch == 1 || a->a_batch_stride % 8 == 0),
+              "uvx_gemm_bf16: strides must be multiples of 8 elements");
+  UVX_REQUIRE(((uintptr_t)a->A % 16 == 0) && ((uintptr_t)a->W % 16 == 0) && ((uintptr_t)a->C % 16 == 0),
+              "uvx_gemm_bf16: 16-byte aligned bases required");
+  UVX_REQUIRE(a->c_row_stride % 8 == 0 && (!a->R || (a->r_row_stride % 8 == 0 && a->r_batch_stride % 8 == 0)),
+              "uvx_gemm_bf16: output / residual strides must be multiples of 8");
+  UVX_REQUIRE(a->a_rows < (1ll << 31) && a->K < (1ll << 31) && a->N < (1ll << 31), "uvx_gemm_bf16: dimension too large");
+  // Tile width: keep >= ~1 wave of CTAs on 148 SMs when M is small, otherwise the widest tile.
+  const int64_t m_tiles = (a->a_rows + kBM - 1) / kBM * a->a_batch;
+  if (a->N % 128 == 0 && m_tiles * (a->N / 128) >= 120) return launch_gemm<128>(a, stream);
+  return launch_gemm<64>(a, stream);
+}

@@ -1,0 +1,149 @@
+// Last-position LM head as an HBM-streaming GEMV (V x d bf16 weights read exactly once, 128-bit no-allocate
+// loads, fp32 accumulate, warp-shuffle reduction) + greedy argmax.
+#include "uvx_common.cuh"
+
+namespace uvx {
+
+static constexpr int kLmWarps = 8;
+static constexpr int kLmMaxB = 8;
+
+// each warp owns vocabulary rows v = warp_global, warp_global + total_warps, ...; h (B x d) sits in shared memory
+template <int B>
+__global__ void __launch_bounds__(kLmWarps * 32) lm_head_kernel(const bf16* __restrict__ h, int64_t h_row_stride,
+                                                                const bf16* __restrict__ W, int64_t V, int64_t d,
+                                                                float* __restrict__ logits) {
+  extern __shared__ uint8_t lm_smem[];
+  bf16* hs = reinterpret_cast<bf16*>(lm_smem);  // [B][d]
+  for (int64_t i = threadIdx.x; i < (int64_t)B * d / 8; i += blockDim.x) {
+    const int64_t b = i / (d / 8), j = i % (d / 8);
+    reinterpret_cast<uint4*>(hs)[i] = *reinterpret_cast<const uint4*>(h + b * h_row_stride + j * 8);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * kLmWarps + (threadIdx.x >> 5);
+  const int64_t total_warps = (int64_t)gridDim.x * kLmWarps;
+  const int nvec = (int)(d / 8);
+  for (int64_t v = warp_global; v < V; v += total_warps) {
+    const bf16* wr = W + v * d;
+    float acc[B];
+#pragma unroll
+    for (int b = 0; b < B; ++b) acc[b] = 0.f;
+#pragma unroll 4
+    for (int j = lane; j < nvec; j += 32) {
+      const uint4 raw = ld_nc_v4(wr + (int64_t)j * 8);
+      float wv[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(&raw), wv);
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        float hv[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(hs + (int64_t)b * d + (int64_t)j * 8), hv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[b] = fmaf(wv[e], hv[e], acc[b]);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      const float s = warp_sum(acc[b]);
+      if (lane == 0) logits[(int64_t)b * V + v] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int64_t V, int64_t* __restrict__ out) {
+  __shared__ float sv[32];
+  __shared__ int64_t si[32];
+  const float* row = logits + (int64_t)blockIdx.x * V;
+  float best = -INFINITY;
+  int64_t bi = INT64_MAX;
+  for (int64_t i = threadIdx.x; i < V; i += blockDim.x) {
+    const float x = row[i];
+    if (x > best || (x == best && i < bi)) {
+      best = x;
+      bi = i;
+    }
+  }
+  // NaN handling is out of contract (torch would return the NaN position); finite logits only.
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) {
+      best = ob;
+      bi = oi;
+    }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
+    sv[w] = best;
+    si[w] = bi;
+  }
+  __syncthreads();
+  if (w == 0) {
+    best = sv[lane];
+    bi = si[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) {
+        best = ob;
+        bi = oi;
+      }
+    }
+    if (lane == 0) out[blockIdx.x] = bi;
+  }
+}
+
+template <int B>
+static int launch_lm(const bf16* h, int64_t hs, const bf16* W, int64_t V, int64_t d, float* logits, cudaStream_t st) {
+  const size_t smem = (size_t)B * d * 2;
+  static bool attr = false;
+  if (!attr && smem > 48 * 1024) {
+    cudaFuncSetAttribute(lm_head_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  int64_t blocks = (V + kLmWarps - 1) / kLmWarps;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  lm_head_kernel<B><<<(unsigned)blocks, kLmWarps * 32, smem, st>>>(h, hs, W, V, d, logits);
+  return check_launch("lm_head_kernel");
+}
+
+}  // namespace uvx
+
+extern "C" int uvx_lm_head(const void* h, int64_t B, int64_t h_row_stride, const void* W, int64_t V, int64_t d,
+                           float* logits, uvx_stream_t stream) {
+  using namespace uvx;
+  UVX_REQUIRE(h && W && logits, "uvx_lm_head: null pointer");
+  UVX_REQUIRE(d % 8 == 0 && h_row_stride % 8 == 0 && B >= 1, "uvx_lm_head: d %% 8 == 0 required");
+  UVX_REQUIRE((size_t)kLmMaxB * d * 2 <= 200 * 1024, "uvx_lm_head: hidden size too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bf16* hp = (const bf16*)h;
+  float* lp = logits;
+  // batches larger than kLmMaxB are processed in slabs (weights re-read once per slab)
+  while (B > 0) {
+    const int64_t nb = B > kLmMaxB ? kLmMaxB : B;
+    int rc;
+    switch (nb) {
+      case 1: rc = launch_lm<1>(hp, h_row_stride, (const bf16*)W, V, d, lp, st); break;
+      case 2: rc = launch_lm<2>(hp, h_row_stride, (const bf16*)W, V, d, lp, st); break;
+      case 3: rc = launch_lm<3>(hp, h_row_stride, (const bf16*)W, V, d, lp, st); break;
+      case 4: rc = launch_lm<4>(hp, h_row_stride, (const bf16*)W, V, d, lp, st); break;
+      case 5: rc = launch_lm<5>(hp, h_row_stride, (const bf16*)W, V, d, lp, st); break;
+      case 6: rc = launch_lm<6>(hp, h_row_stride, (const bf16*)W, V, d, lp, st); break;
+      case 7: rc = launch_lm<7>(hp, h_row_stride, (const bf16*)W, V, d, lp, st); break;
+      default: rc = launch_lm<8>(hp, h_row_stride, (const bf16*)W, V, d, lp, st); break;
+    }
+    if (rc) return rc;
+    hp += nb * h_row_stride;
+    lp += nb * V;
+    B -= nb;
+  }
+  return UVX_OK;
+}
+
+extern "C" int uvx_argmax(const float* logits, int64_t B, int64_t V, int64_t* out_idx, uvx_stream_t stream) {
+  using namespace uvx;
+  UVX_REQUIRE(logits && out_idx && B >= 1 && V >= 1, "uvx_argmax: bad arguments");
+  argmax_kernel<<<(unsigned)B, 1024, 0, (cudaStream_t)stream>>>(logits, V, out_idx);
+  return check_launch("argmax_kernel");
+}

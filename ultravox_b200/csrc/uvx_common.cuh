@@ -1,0 +1,86 @@
+// Shared device/host helpers for libuvx (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/uvx.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libuvx is written for sm_100a (B200) only"
+#endif
+
+namespace uvx {
+
+// ---- error reporting -------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);  // cudaGetLastError -> UVX_ERR_CUDA + message
+
+#define UVX_REQUIRE(cond, ...)                 \
+  do {                                         \
+    if (!(cond)) {                             \
+      ::uvx::set_error(__VA_ARGS__);           \
+      return UVX_ERR_ARG;                      \
+    }                                          \
+  } while (0)
+
+typedef __nv_bfloat16 bf16;
+
+// ---- small device helpers --------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide sum for blockDim.x <= 1024 (multiple of 32); `red` is >= 32 floats of shared memory
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : 0.f;
+  return warp_sum(t);
+}
+
+struct __align__(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+
+// streaming 128-bit global load that does not allocate in L1 (weights are read once)
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+
+}  // namespace uvx
