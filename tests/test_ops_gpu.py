@@ -1,0 +1,230 @@
+"""Per-op parity of the CUDA kernels (through the C ABI) against fp32 math on identical bf16 inputs.
+
+Tolerance rule: each kernel's output, given bit-identical bf16 inputs, must be within
+1e-3 relative (Frobenius) of the fp32-math result rounded once to bf16 -- stated per test.  Index / copy paths
+are bit-exact.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def rnd(*shape, scale=1.0, seed=0, dtype=BF):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).cuda()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from ultravox_b200 import ops as o
+    return o
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (201, 256, 512), (1, 128, 256), (300, 192, 200), (1500, 1280, 1280),
+                                   (201, 4096, 4096), (129, 64, 64)])
+def test_gemm_plain(ops, M, N, K):
+    x, w = rnd(M, K, seed=1), rnd(N, K, scale=0.05, seed=2)
+    y = ops.linear(x, w)
+    ref = (x.float() @ w.float().T)
+    assert y.shape == (M, N) and y.dtype == BF
+    assert rel(y, ref.to(BF)) < 1e-3, rel(y, ref)
+
+
+def test_gemm_epilogues(ops):
+    M, N, K = 333, 384, 320
+    x, w, b, r = rnd(M, K, seed=1), rnd(N, K, scale=0.05, seed=2), rnd(N, seed=3), rnd(M, N, seed=4)
+    ref = F.gelu(x.float() @ w.float().T + b.float()) + r.float()
+    y = ops.linear(x, w, bias=b, act=ops.ACT_GELU, residual=r)
+    assert rel(y, ref) < 1e-3
+    # in-place residual (out aliases residual), fp32 output, alpha
+    y32 = ops.linear(x, w, out_dtype=torch.float32, alpha=0.5)
+    assert y32.dtype == torch.float32 and rel(y32, 0.5 * (x.float() @ w.float().T)) < 1e-5
+    r2 = r.clone()
+    ops.linear(x, w, bias=b, residual=r2, out=r2)
+    assert rel(r2, x.float() @ w.float().T + b.float() + r.float()) < 1e-3
+
+
+def test_gemm_row_map(ops):
+    M, N, K = 50, 128, 64
+    x, w = rnd(M, K, seed=1), rnd(N, K, seed=2)
+    out = torch.zeros(80, N, dtype=BF, device="cuda")
+    perm = torch.randperm(80)[:M].to(torch.int32)
+    perm[7] = -1
+    ops.linear(x, w, out=out, row_map=perm.cuda())
+    ref = (x.float() @ w.float().T).to(BF)
+    for m in range(M):
+        if perm[m] >= 0:
+            assert torch.equal(out[perm[m]], ref[m].to(out.dtype)) or rel(out[perm[m]], ref[m]) < 1e-3
+    untouched = sorted(set(range(80)) - set(int(v) for v in perm if v >= 0))
+    assert torch.count_nonzero(out[untouched]) == 0
+
+
+@pytest.mark.parametrize("stride,Cin,Cout,T,N", [(1, 80, 128, 100, 2), (2, 128, 128, 100, 2), (2, 128, 256, 37, 3),
+                                                 (1, 128, 1280, 3000, 1)])
+def test_conv_implicit_gemm(ops, stride, Cin, Cout, T, N):
+    x = rnd(N, Cin, T, seed=5).float()           # [N, C, T] "mel"
+    w = rnd(Cout, Cin, 3, scale=0.05, seed=6)
+    b = rnd(Cout, seed=7)
+    x_tm = torch.zeros(N, T + 2, Cin, dtype=BF, device="cuda")
+    x_tm[:, 1:T + 1] = x.transpose(1, 2).to(BF)
+    w_r = w.permute(0, 2, 1).reshape(Cout, 3 * Cin).contiguous()
+    Tout = (T + stride - 1) // stride if stride > 1 else T
+    ref = F.gelu(F.conv1d(x.to(BF).float(), w.float(), b.float(), stride=stride, padding=1)).transpose(1, 2)
+    assert ref.shape[1] == Tout
+    out = torch.zeros(N, Tout + 2, Cout, dtype=BF, device="cuda")
+    ops.conv1d_k3(x_tm, w_r, b, stride, out, out_guard=True)
+    assert rel(out[:, 1:Tout + 1], ref) < 1e-3
+    assert torch.count_nonzero(out[:, 0]) == 0 and torch.count_nonzero(out[:, Tout + 1]) == 0
+    pos = rnd(Tout, Cout, seed=8)
+    out2 = torch.empty(N, Tout, Cout, dtype=BF, device="cuda")
+    ops.conv1d_k3(x_tm, w_r, b, stride, out2, out_guard=False, pos=pos)
+    assert rel(out2, ref + pos.float()) < 1e-3
+
+
+@pytest.mark.parametrize("rows,cols", [(7, 128), (1500, 1280), (201, 4096), (33, 10240)])
+def test_norms(ops, rows, cols):
+    x, w, b = rnd(rows, cols, seed=1), rnd(cols, seed=2), rnd(cols, seed=3)
+    y = ops.layernorm(x, w, b, 1e-5)
+    assert rel(y, F.layer_norm(x.float(), (cols,), w.float(), b.float(), 1e-5)) < 1e-3
+    y = ops.rmsnorm(x, w, 1e-6)
+    xf = x.float()
+    ref = w.float() * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6))
+    assert rel(y, ref) < 2e-3  # two bf16 roundings by construction (LlamaRMSNorm order)
+
+
+@pytest.mark.parametrize("T,C", [(50, 384), (1500, 1280), (8, 128), (3, 128)])
+def test_stack_rmsnorm(ops, T, C):
+    enc, w = rnd(2, T, C, seed=1), rnd(8 * C, seed=2)
+    y = ops.stack_rmsnorm(enc, w, 8)
+    Tp = (T + 7) // 8 * 8
+    st = F.pad(enc.float(), (0, 0, 0, Tp - T)).reshape(2, Tp // 8, 8 * C)
+    ref = w.float() * (st * torch.rsqrt(st.pow(2).mean(-1, keepdim=True) + 1e-6))
+    assert y.shape == ref.shape and rel(y, ref) < 2e-3
+
+
+def _attn_ref(q, k, v, scale, causal=False, kv_len=None, block=0):
+    B, Hq, S, D = q.shape
+    Hkv = k.shape[1]
+    k = k.repeat_interleave(Hq // Hkv, 1)
+    v = v.repeat_interleave(Hq // Hkv, 1)
+    s = (q.float() @ k.float().transpose(-1, -2)) * scale
+    i = torch.arange(S, device=q.device)[:, None]
+    j = torch.arange(k.shape[2], device=q.device)[None, :]
+    ok = torch.ones(S, k.shape[2], dtype=torch.bool, device=q.device)
+    if causal:
+        ok &= j <= i
+    if block:
+        ok &= (j // block) <= (i // block)
+    ok = ok[None, None].expand(B, 1, -1, -1).clone()
+    if kv_len is not None:
+        ok &= (j[None, None] < kv_len.view(B, 1, 1, 1))
+    s = s.masked_fill(~ok, float("-inf"))
+    return torch.softmax(s, -1) @ v.float()
+
+
+@pytest.mark.parametrize("B,Hq,Hkv,S,D,causal,block,ragged", [
+    (2, 6, 6, 50, 64, False, 0, True), (1, 20, 20, 1500, 64, False, 0, False), (2, 4, 4, 300, 64, False, 100, True),
+    (1, 32, 8, 201, 128, True, 0, False), (2, 8, 2, 77, 64, True, 0, False), (3, 4, 2, 130, 128, True, 0, False)])
+def test_attention(ops, B, Hq, Hkv, S, D, causal, block, ragged):
+    W = (Hq + 2 * Hkv) * D
+    qkv = rnd(B * S, W, seed=3)
+    kv_len = torch.tensor([S, max(1, S // 3), S - 1][:B], dtype=torch.int32).cuda() if ragged else None
+    out = ops.attention_fused_qkv(qkv, B, S, Hq, Hkv, D, D ** -0.5, causal, kv_len, block)
+    t = qkv.view(B, S, Hq + 2 * Hkv, D).permute(0, 2, 1, 3)
+    ref = _attn_ref(t[:, :Hq], t[:, Hq:Hq + Hkv], t[:, Hq + Hkv:], D ** -0.5, causal, kv_len, block)
+    ref = ref.permute(0, 2, 1, 3).reshape(B * S, Hq * D)
+    assert rel(out, ref) < 3e-3  # P is rounded to bf16 before PV (as in every flash kernel)
+
+
+def test_rope(ops):
+    Hq, Hkv, D, S, B = 8, 2, 128, 40, 2
+    qkv = rnd(B * S, (Hq + 2 * Hkv) * D, seed=1)
+    inv = ops.llama3_inv_freq(D, 500000.0, dict(rope_type="llama3", factor=8.0, low_freq_factor=1.0,
+                                                high_freq_factor=4.0, original_max_position_embeddings=8192))
+    cos, sin = ops.rope_tables(inv, 64, "cuda")
+    ref = qkv.float().view(B, S, Hq + 2 * Hkv, D).clone()
+    pos = torch.arange(S, device="cuda").float()
+    fr = pos[:, None] * inv.cuda()[None]
+    c, s_ = torch.cat([fr, fr], -1).cos()[None, :, None], torch.cat([fr, fr], -1).sin()[None, :, None]
+    x = ref[:, :, :Hq + Hkv]
+    rot = torch.cat([-x[..., D // 2:], x[..., :D // 2]], -1)
+    ref[:, :, :Hq + Hkv] = x * c + rot * s_
+    got = ops.rope_(qkv.clone(), Hq, Hkv, D, cos, sin, rows_per_seq=S)
+    assert rel(got.view(B, S, -1, D), ref) < 1e-3
+    assert torch.equal(got.view(B, S, -1, D)[:, :, Hq + Hkv:], qkv.view(B, S, -1, D)[:, :, Hq + Hkv:])  # v untouched
+
+
+def test_swiglu(ops):
+    x = rnd(77, 512, seed=1)
+    a, g = x.float().chunk(2, -1)
+    assert rel(ops.swiglu(x, gate_first=False), F.silu(g) * a) < 2e-3
+    assert rel(ops.swiglu(x, gate_first=True), F.silu(a) * g) < 2e-3
+
+
+def test_embed_splice_bit_exact(ops):
+    B, S, d, V = 3, 40, 256, 1000
+    table, audio = rnd(V, d, seed=1), rnd(4, 12, d, seed=2)
+    ids = torch.randint(0, V, (B, S), generator=torch.Generator().manual_seed(3)).cuda()
+    start = torch.tensor([5, 20, 0, 28], dtype=torch.int64).cuda()
+    tlen = torch.tensor([7, 12, 3, 12], dtype=torch.int32).cuda()
+    abs_ = torch.tensor([2, 0, 2], dtype=torch.int64).cuda()
+    ref = table[ids].clone()
+    a = 0
+    for b, cnt in enumerate(abs_.tolist()):
+        for _ in range(cnt):
+            s, n = int(start[a]), int(tlen[a])
+            ref[b, s:s + n] = audio[a, :n]
+            a += 1
+    src = ops.splice_plan(start, tlen, abs_, B, S, audio.shape[1])
+    out = ops.embed_splice(ids, table, audio, src)
+    assert torch.equal(out, ref)
+    assert torch.equal(ops.embed_splice(ids, table, None, None), table[ids])
+
+
+def test_lm_head_argmax(ops):
+    V, d = 5000, 512
+    h, w = rnd(3, d, seed=1), rnd(V, d, scale=0.05, seed=2)
+    lg = ops.lm_head(h, w)
+    ref = h.float() @ w.float().T
+    assert rel(lg, ref) < 1e-5
+    assert torch.equal(ops.argmax(lg), lg.argmax(-1))
+    t = torch.zeros(2, 777, device="cuda")
+    t[0, 5] = t[0, 300] = 2.0
+    t[1, 776] = 1.0
+    assert ops.argmax(t).tolist() == [5, 776]
+
+
+@pytest.mark.parametrize("n_mels,secs,B", [(80, 1.0, 1), (128, 30.0, 1), (128, 2.5, 3)])
+def test_logmel(ops, n_mels, secs, B):
+    from oracle import logmel as om
+    n = int(16000 * secs)
+    waves = [np.random.default_rng(1000 + i).standard_normal(n - 137 * i).astype(np.float32) for i in range(B)]
+    t = np.arange(n) / 16000.0
+    if B > 1:
+        waves[1] = (0.1 * np.sin(2 * np.pi * 440 * t)).astype(np.float32)
+        waves[1][int(0.75 * n):] = 0
+    padded, _ = om.pad_batch(waves)
+    ref = om.log_mel(padded, n_mels)                       # float64 oracle
+    got, tm = ops.logmel(torch.from_numpy(padded).cuda(), n_mels, want_f32=True, want_tm=True)
+    got = got.cpu().numpy()
+    assert got.shape == ref.shape
+    # fp32 DFT vs float64: values live in [-1.5, 2]; 2e-3 abs covers near-floor bins of tonal input
+    assert np.abs(got - ref).max() < 2e-3, np.abs(got - ref).max()
+    assert np.sqrt(((got - ref) ** 2).mean()) < 1e-4
+    T = padded.shape[1] // 160
+    assert torch.equal(tm[:, 1:T + 1].float().cpu(), torch.from_numpy(got).transpose(1, 2).to(BF).float())
+    assert torch.count_nonzero(tm[:, 0]) == 0 and torch.count_nonzero(tm[:, T + 1]) == 0
+    av = ops.mel_to_timemajor(torch.from_numpy(got).cuda())
+    assert torch.equal(av, tm)

@@ -1,0 +1,284 @@
+"""Tensor-level wrappers over the C ABI (``libuvx``).  PyTorch is only the owner of device memory and of
+the current stream here; every op below is a hand-written sm_100a kernel.  CUDA tensors only - there is no
+CPU path (an exception is raised instead).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import AttnArgs, GemmArgs, check, lib
+
+ACT_NONE, ACT_GELU = 0, 1
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _cuda(t: torch.Tensor, dtype=None, name="tensor") -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.UvxError(f"{name} must be a CUDA tensor (ultravox_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------ log-mel
+def logmel(wave: torch.Tensor, n_mels: int, want_f32: bool = True, want_tm: bool = False,
+           out_f32: Optional[torch.Tensor] = None, out_tm: Optional[torch.Tensor] = None,
+           workspace: Optional[torch.Tensor] = None):
+    """wave [B, L] fp32 (L % 160 == 0) -> ``audio_values`` [B, n_mels, L/160] fp32 and/or the bf16 time-major
+    guard-padded layout [B, L/160 + 2, n_mels] (see include/uvx.h)."""
+    _cuda(wave, torch.float32, "wave")
+    wave = wave.contiguous()
+    B, L = wave.shape
+    T = L // 160
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty(B, n_mels, T, dtype=torch.float32, device=wave.device)
+    if want_tm and out_tm is None:
+        out_tm = torch.empty(B, T + 2, n_mels, dtype=BF16, device=wave.device)
+    need = lib().uvx_logmel_workspace(B, L, n_mels)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=wave.device)
+    check(lib().uvx_logmel(wave.data_ptr(), B, L, n_mels, _p(out_f32), _p(out_tm), workspace.data_ptr(),
+                           workspace.numel(), _stream()), "uvx_logmel")
+    if want_f32 and want_tm:
+        return out_f32, out_tm
+    return out_f32 if want_f32 else out_tm
+
+
+def mel_to_timemajor(audio_values: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(audio_values, torch.float32, "audio_values")
+    audio_values = audio_values.contiguous()
+    N, n_mels, T = audio_values.shape
+    if out is None:
+        out = torch.empty(N, T + 2, n_mels, dtype=BF16, device=audio_values.device)
+    check(lib().uvx_mel_to_timemajor(audio_values.data_ptr(), N, n_mels, T, out.data_ptr(), _stream()),
+          "uvx_mel_to_timemajor")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+def gemm_raw(A_ptr: int, a_batch: int, a_rows: int, K: int, a_row_stride: int, a_batch_stride: int,
+             W: torch.Tensor, C_t: torch.Tensor, c_row_stride: int, c_batch_rows: int, c_row_offset: int = 0,
+             c_row_map: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+             R: Optional[torch.Tensor] = None, r_row_stride: int = 0, r_batch_stride: int = 0,
+             alpha: float = 1.0, act: int = ACT_NONE) -> None:
+    a = GemmArgs()
+    a.A, a.a_batch, a.a_rows, a.K = A_ptr, a_batch, a_rows, K
+    a.a_row_stride, a.a_batch_stride = a_row_stride, a_batch_stride
+    a.W, a.N, a.w_row_stride = W.data_ptr(), W.shape[0], W.stride(0)
+    a.C, a.c_row_stride, a.c_batch_rows, a.c_row_offset = C_t.data_ptr(), c_row_stride, c_batch_rows, c_row_offset
+    a.c_row_map = _p(c_row_map)
+    a.bias, a.R = _p(bias), _p(R)
+    a.r_row_stride, a.r_batch_stride = r_row_stride, r_batch_stride
+    a.alpha, a.act = alpha, act
+    a.out_dtype = 1 if C_t.dtype == torch.float32 else 0
+    check(lib().uvx_gemm_bf16(C.byref(a), _stream()), "uvx_gemm_bf16")
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+           residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+           out_dtype=BF16, row_map: Optional[torch.Tensor] = None, alpha: float = 1.0) -> torch.Tensor:
+    """y = act(alpha * x @ w.T + bias) + residual for x [..., K] (last dim contiguous, uniform row stride)."""
+    _cuda(x, BF16, "x"), _cuda(w, BF16, "w")
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    M, N = x2.shape[0], w.shape[0]
+    if out is None:
+        out = torch.empty(*x.shape[:-1], N, dtype=out_dtype, device=x.device)
+    o2 = out.view(-1, out.shape[-1]) if row_map is None else out
+    r2 = None
+    if residual is not None:
+        r2 = residual.reshape(-1, N)
+    gemm_raw(x2.data_ptr(), 1, M, K, x2.stride(0), 0, w, o2, o2.stride(-2) if o2.dim() >= 2 else N, M, 0,
+             row_map, bias, r2, r2.stride(0) if r2 is not None else 0, 0, alpha, act)
+    return out
+
+
+def conv1d_k3(x_tm: torch.Tensor, w_r: torch.Tensor, bias: torch.Tensor, stride: int, out: torch.Tensor,
+              out_guard: bool, pos: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Conv1d(k=3, pad=1, stride) + GELU (+ pos) as an implicit GEMM over the guard-padded time-major input.
+
+    x_tm [N, T + 2, C_in] bf16 (rows 0 and T+1 zero), w_r [C_out, 3 * C_in] (= conv.weight.permute(0, 2, 1)
+    flattened).  Output rows t' = 0 .. ceil(T/stride)-1 are written to ``out`` [N, T' (+2), C_out]; with
+    ``out_guard`` they land at row t'+1 (guard rows must already be zero)."""
+    N, Tp, Cin = x_tm.shape
+    T = Tp - 2
+    Tout = (T + stride - 1) // stride if stride > 1 else T
+    Cout = w_r.shape[0]
+    rows_out = out.shape[1]
+    gemm_raw(x_tm.data_ptr(), N, Tout, 3 * Cin, stride * Cin, Tp * Cin, w_r, out, Cout, rows_out,
+             1 if out_guard else 0, None, bias, pos, Cout if pos is not None else 0, 0, 1.0, ACT_GELU)
+    return out
+
+
+# ------------------------------------------------------------------------------------------ norms
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e-5,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(x, BF16, "x")
+    cols = x.shape[-1]
+    x2 = x.reshape(-1, cols)
+    if out is None:
+        out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    check(lib().uvx_layernorm(x2.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), x2.shape[0], cols,
+                              x2.stride(0), eps, _stream()), "uvx_layernorm")
+    return out
+
+
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(x, BF16, "x")
+    cols = x.shape[-1]
+    x2 = x.reshape(-1, cols)
+    if out is None:
+        out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    check(lib().uvx_rmsnorm(x2.data_ptr(), w.data_ptr(), out.data_ptr(), x2.shape[0], cols, x2.stride(0), 0, 0, 0, eps,
+                            _stream()), "uvx_rmsnorm")
+    return out
+
+
+def stack_rmsnorm(enc: torch.Tensor, w: torch.Tensor, stack: int, eps: float = 1e-6,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """StackAudioFrames + ln_pre without materialising the padded/stacked tensor.
+    enc [N, T, C] contiguous -> [N, ceil(T/stack), stack*C]."""
+    _cuda(enc, BF16, "enc")
+    enc = enc.contiguous()
+    N, T, Cc = enc.shape
+    rows = (T + stack - 1) // stack
+    cols = Cc * stack
+    if out is None:
+        out = torch.empty(N, rows, cols, dtype=BF16, device=enc.device)
+    check(lib().uvx_rmsnorm(enc.data_ptr(), w.data_ptr(), out.data_ptr(), N * rows, cols, cols, rows, T * Cc, T * Cc, eps,
+                            _stream()), "uvx_rmsnorm(stack)")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ attention
+def attention(q_ptr: int, k_ptr: int, v_ptr: int, out: torch.Tensor, B: int, Hq: int, Hkv: int, Sq: int,
+              Skv: int, D: int, strides: tuple, scale: float, causal: bool = False,
+              kv_len: Optional[torch.Tensor] = None, block: int = 0) -> torch.Tensor:
+    """Raw strided interface: strides = (q_rs, q_bs, k_rs, k_bs, v_rs, v_bs, o_rs, o_bs) in elements; the three
+    pointers address element [b=0, i=0, h=0, 0] of q / k / v."""
+    a = AttnArgs()
+    a.q, a.k, a.v, a.o = q_ptr, k_ptr, v_ptr, out.data_ptr()
+    a.B, a.Hq, a.Hkv, a.Sq, a.Skv, a.D = B, Hq, Hkv, Sq, Skv, D
+    (a.q_rs, a.q_bs, a.k_rs, a.k_bs, a.v_rs, a.v_bs, a.o_rs, a.o_bs) = strides
+    a.kv_len = _p(kv_len)
+    a.causal, a.block, a.scale = int(causal), int(block), float(scale)
+    check(lib().uvx_attention(C.byref(a), _stream()), "uvx_attention")
+    return out
+
+
+def attention_fused_qkv(qkv: torch.Tensor, B: int, S: int, Hq: int, Hkv: int, D: int, scale: float, causal: bool,
+                        kv_len: Optional[torch.Tensor] = None, block: int = 0,
+                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qkv [B*S, (Hq + 2*Hkv) * D] (q | k | v sections) -> out [B*S, Hq*D]."""
+    _cuda(qkv, BF16, "qkv")
+    assert qkv.shape[-1] == (Hq + 2 * Hkv) * D and qkv.stride(-1) == 1
+    rs = qkv.stride(-2)
+    if out is None:
+        out = torch.empty(B * S, Hq * D, dtype=BF16, device=qkv.device)
+    base = qkv.data_ptr()
+    return attention(base, base + 2 * Hq * D, base + 2 * (Hq + Hkv) * D, out, B, Hq, Hkv, S, S, D,
+                     (rs, S * rs, rs, S * rs, rs, S * rs, Hq * D, S * Hq * D), scale, causal, kv_len, block)
+
+
+# ------------------------------------------------------------------------------------------ rope / swiglu
+def rope_tables(inv_freq: torch.Tensor, max_pos: int, device) -> tuple[torch.Tensor, torch.Tensor]:
+    """cos/sin [max_pos, D/2] fp32 exactly as LlamaRotaryEmbedding computes them (fp32 outer product)."""
+    pos = torch.arange(max_pos, dtype=torch.float32)
+    freqs = pos[:, None] * inv_freq.to(torch.float32)[None, :]
+    return freqs.cos().to(device).contiguous(), freqs.sin().to(device).contiguous()
+
+
+def rope_(qkv: torch.Tensor, Hq: int, Hkv: int, D: int, cos: torch.Tensor, sin: torch.Tensor, rows_per_seq: int,
+          pos_offset: int = 0, positions: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(qkv, BF16, "qkv")
+    rows = qkv.numel() // qkv.shape[-1]
+    check(lib().uvx_rope(qkv.data_ptr(), rows, qkv.stride(-2), Hq, Hkv, D, cos.data_ptr(), sin.data_ptr(), _p(positions),
+                         rows_per_seq, pos_offset, _stream()), "uvx_rope")
+    return qkv
+
+
+def swiglu(x: torch.Tensor, gate_first: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(x, BF16, "x")
+    H = x.shape[-1] // 2
+    x2 = x.reshape(-1, 2 * H)
+    if out is None:
+        out = torch.empty(*x.shape[:-1], H, dtype=BF16, device=x.device)
+    check(lib().uvx_swiglu(x2.data_ptr(), out.data_ptr(), x2.shape[0], H, x2.stride(0), int(gate_first), _stream()),
+          "uvx_swiglu")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ embed + splice
+def splice_plan(start_idx: torch.Tensor, tok_len: torch.Tensor, audio_batch_size: torch.Tensor, B: int, S: int,
+                tok_stride: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = start_idx.device
+    _cuda(start_idx, torch.int64, "audio_token_start_idx"), _cuda(tok_len, torch.int32, "audio_token_len")
+    _cuda(audio_batch_size, torch.int64, "audio_batch_size")
+    if out is None:
+        out = torch.empty(B * S, dtype=torch.int32, device=dev)
+    check(lib().uvx_splice_plan(start_idx.data_ptr(), tok_len.data_ptr(), audio_batch_size.data_ptr(), start_idx.numel(),
+                                B, S, tok_stride, out.data_ptr(), _stream()), "uvx_splice_plan")
+    return out
+
+
+def embed_splice(input_ids: torch.Tensor, embed_tokens: torch.Tensor, audio_embeds: Optional[torch.Tensor],
+                 src: Optional[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(input_ids, torch.int64, "input_ids"), _cuda(embed_tokens, BF16, "embed_tokens")
+    ids = input_ids.contiguous()
+    d = embed_tokens.shape[1]
+    if out is None:
+        out = torch.empty(*ids.shape, d, dtype=BF16, device=ids.device)
+    check(lib().uvx_embed_splice(ids.data_ptr(), embed_tokens.data_ptr(), embed_tokens.shape[0], _p(audio_embeds), _p(src),
+                                 ids.numel(), d, out.data_ptr(), _stream()), "uvx_embed_splice")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ lm head
+def lm_head(h: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """h [B, d] bf16 (row stride arbitrary) x w [V, d] -> fp32 logits [B, V]."""
+    _cuda(h, BF16, "h"), _cuda(w, BF16, "w")
+    B, d = h.shape
+    V = w.shape[0]
+    if out is None:
+        out = torch.empty(B, V, dtype=torch.float32, device=h.device)
+    check(lib().uvx_lm_head(h.data_ptr(), B, h.stride(0), w.data_ptr(), V, d, out.data_ptr(), _stream()), "uvx_lm_head")
+    return out
+
+
+def argmax(logits: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(logits, torch.float32, "logits")
+    B, V = logits.shape
+    if out is None:
+        out = torch.empty(B, dtype=torch.int64, device=logits.device)
+    check(lib().uvx_argmax(logits.data_ptr(), B, V, out.data_ptr(), _stream()), "uvx_argmax")
+    return out
+
+
+def llama3_inv_freq(head_dim: int, theta: float, scaling: Optional[dict]) -> torch.Tensor:
+    """inv_freq with the llama3 smoothing (hf:modeling_rope_utils.py:550-626); fp32 like the reference."""
+    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64).to(torch.float32) / head_dim))
+    if not scaling or scaling.get("rope_type", scaling.get("type")) != "llama3":
+        return inv
+    factor, lo, hi = scaling["factor"], scaling["low_freq_factor"], scaling["high_freq_factor"]
+    old = scaling["original_max_position_embeddings"]
+    wl = 2 * math.pi / inv
+    inv_l = torch.where(wl > old / lo, inv / factor, inv)
+    smooth = (old / wl - lo) / (hi - lo)
+    sm = (1 - smooth) * inv_l / factor + smooth * inv_l
+    mid = ~(wl < old / hi) * ~(wl > old / lo)
+    return torch.where(mid, sm, inv_l)
