@@ -163,6 +163,13 @@ int uvx_lm_head(const void* h, int64_t B, int64_t h_row_stride, const void* W, i
                 float* logits, uvx_stream_t stream);
 int uvx_argmax(const float* logits, int64_t B, int64_t V, int64_t* out_idx, uvx_stream_t stream);
 
+/* Shifted causal-LM cross entropy (hf:loss/loss_utils.py:28-67; called through LlamaForCausalLM.forward(labels=)
+ * from ref:ultravox/model/ultravox_model.py:328-334).  logits [B*S, V] fp32 (row_stride elements), labels [B, S]
+ * un-shifted (the shift and the ignore_index padding happen inside).  row_loss/row_lse [B*S] are kept for the
+ * backward; out_loss2[0] = mean loss over non-ignored positions, out_loss2[1] = their count.              */
+int uvx_ce_loss(const float* logits, int64_t row_stride, const int64_t* labels, int64_t B, int64_t S, int64_t V,
+                int64_t ignore_index, float* row_loss, float* row_lse, float* out_loss2, uvx_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,183 @@
+"""Host-side logic of the product package, no GPU: processor / collator integer path (bit-exact against fixtures made by
+the reference class), config surface, C-ABI symbol table, error behaviour."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from ultravox_b200 import _lib
+from ultravox_b200.config import LossConfig, LossFunction, UltravoxConfig, preset
+from ultravox_b200.processing import DataCollatorForSeq2SeqWithAudio, MelSpec, UltravoxProcessor
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+
+
+class StubTokenizer:
+    eos_token = "<|eot_id|>"
+    eos_token_id = 128009
+    pad_token_id = None
+    padding_side = "right"
+    model_input_names = ["input_ids", "attention_mask"]
+
+    def get_vocab(self):
+        return {self.eos_token: self.eos_token_id}
+
+    def __call__(self, parts, add_special_tokens=False, **kw):
+        return {"input_ids": [[(sum(map(ord, w)) * 31 + len(w)) % 100000 for w in p.split()] for p in parts]}
+
+    def pad(self, features, padding=True, max_length=None, pad_to_multiple_of=None, return_tensors=None, **kw):
+        import transformers
+        L = max(len(f["input_ids"]) for f in features)
+        out = {"input_ids": [], "attention_mask": []}
+        for f in features:
+            ids = list(map(int, f["input_ids"]))
+            n = L - len(ids)
+            left = self.padding_side == "left"
+            out["input_ids"].append([self.pad_token_id] * n + ids if left else ids + [self.pad_token_id] * n)
+            out["attention_mask"].append([0] * n + [1] * len(ids) if left else [1] * len(ids) + [0] * n)
+        out.update({k: [f[k] for f in features] for k in features[0] if k not in ("input_ids", "attention_mask")})
+        return transformers.BatchFeature(out, tensor_type=return_tensors)
+
+
+def wave(i, n):
+    return np.random.default_rng(1000 + i).standard_normal(n).astype(np.float32)
+
+
+@pytest.fixture(scope="module")
+def cases():
+    return json.load(open(os.path.join(G, "processor_cases.json")))
+
+
+@pytest.fixture()
+def proc():
+    return UltravoxProcessor(MelSpec(feature_size=80), StubTokenizer(), defer_mel=True)
+
+
+def test_processor_integer_path_bit_exact(proc, cases):
+    for c in cases["cases"]:
+        audios = [wave(i, n) for i, n in enumerate(c["sample_counts"])]
+        kw = dict(audios=audios, sampling_rate=16000, include_audio_num_chunks=True) if audios else {}
+        got = proc(c["text"], **kw)
+        exp = c["out"]
+        for key in ("input_ids", "attention_mask", "audio_lens", "audio_token_len", "audio_token_start_idx",
+                    "audio_batch_size", "audio_num_chunks"):
+            if key in exp:
+                assert got[key].tolist() == exp[key], (c["name"], key)
+                if key == "audio_token_len":
+                    assert got[key].dtype == torch.int32
+                if key in ("audio_lens", "audio_token_start_idx", "input_ids"):
+                    assert got[key].dtype == torch.int64
+            else:
+                assert key not in got
+        if audios:
+            L = got["audio_waveforms"].shape[1]
+            assert L % 160 == 0 and L >= 320 and got["audio_waveforms"].dtype == torch.float32
+
+
+def test_processor_errors(proc, cases):
+    for e in cases["errors"]:
+        audios = [wave(i, n) for i, n in enumerate(e["sample_counts"])]
+        if e["raises"]:
+            with pytest.raises(ValueError) as ei:
+                proc(e["text"], audios=audios, sampling_rate=16000) if audios else proc(e["text"])
+            assert str(ei.value) == e["msg"]
+    with pytest.raises(ValueError):
+        proc("x <|audio|>", audio=wave(0, 100), audios=[wave(0, 100)])
+    with pytest.raises(ValueError):
+        proc(["a", "b"])
+    tok = StubTokenizer()
+    tok.eos_token = None
+    with pytest.raises(AssertionError):
+        UltravoxProcessor(MelSpec(), tok)
+
+
+def test_chunk_and_pad_audio_matches_reference_semantics(proc):
+    """ref :153-215: continuation chunks are zero-padded to the context, first chunks keep the batch width."""
+    mel = torch.arange(2 * 3 * 3500, dtype=torch.float32).view(2, 3, 3500)
+    d = proc._chunk_and_pad_audio(mel, torch.tensor([3500, 1200]), include_audio_num_chunks=True)
+    assert d["audio_values"].shape == (3, 3, 3000)
+    assert d["audio_lens"].tolist() == [3000, 500, 1200] and d["audio_is_continuation"].tolist() == [False, True, False]
+    assert torch.equal(d["audio_values"][1, :, :500], mel[0, :, 3000:]) and float(d["audio_values"][1, :, 500:].abs().sum()) == 0
+    assert torch.equal(d["audio_values"][2], mel[1, :, :3000])
+    assert d["audio_batch_size"].tolist() == [3] and d["audio_num_chunks"].tolist() == [2, 1]
+
+
+def test_collator_left_padding_displacement(cases):
+    sr = 16000
+    for c in cases["collator"]:
+        tok = StubTokenizer()
+        tok.padding_side = c["padding_side"]
+        p = UltravoxProcessor(MelSpec(feature_size=80), tok, defer_mel=True)
+        samples = []
+        for text, n, i in (("Test with <|audio|>", sr, 0), ("Other longer text with <|audio|> more", 35 * sr, 1)):
+            s = dict(p(text, audio=wave(i, n), sampling_rate=sr))
+            s.pop("audio_waveforms"), s.pop("audio_num_frames")
+            # stand-in mel with the right frame width per chunk (the collator only pads / stacks it)
+            widths = [3000 if len(s["audio_lens"]) > 1 else int(s["audio_lens"][0])] * len(s["audio_lens"])
+            s["audio_values"] = torch.ones(len(widths), 80, widths[0])
+            s["input_ids"], s["attention_mask"] = s["input_ids"][0], s["attention_mask"][0]
+            samples.append(s)
+        got = DataCollatorForSeq2SeqWithAudio(tok)(samples)
+        exp = c["out"]
+        for key in ("input_ids", "attention_mask", "audio_lens", "audio_token_len", "audio_token_start_idx",
+                    "audio_batch_size"):
+            assert got[key].tolist() == exp[key], (c["padding_side"], key)
+        assert list(got["audio_values"].shape) == exp["audio_values_shape"]
+
+
+def test_config_surface_round_trip(tmp_path):
+    cfg = preset("micro", audio_latency_block_size=100)
+    assert cfg.model_type == "ultravox" and cfg.stack_factor == 8 and cfg.projector_ln_mid is True
+    assert cfg.vocab_size == cfg.text_config.vocab_size and cfg.initializer_range == cfg.text_config.initializer_range
+    cfg.save_pretrained(tmp_path)
+    back = UltravoxConfig.from_pretrained(tmp_path)
+    assert back.to_dict()["audio_latency_block_size"] == 100
+    assert back.audio_config.d_model == cfg.audio_config.d_model and back.text_config.hidden_size == cfg.text_config.hidden_size
+    assert back.text_model_lora_config["r"] == 0
+    d = UltravoxConfig().to_diff_dict()
+    assert "_attn_implementation_autoset" not in d.get("text_config", {})
+    assert LossConfig().loss_function == LossFunction.CrossEntropy and LossConfig(LossFunction.KL_Divergence).requires_alt_fields
+
+
+def test_library_exports_every_declared_symbol():
+    """include/uvx.h is the contract: every function it declares must be exported and bound."""
+    header = open(os.path.join(ROOT, "include", "uvx.h")).read()
+    declared = set(re.findall(r"\b(uvx_[a-z0-9_]+)\s*\(", header))
+    declared -= {"uvx_gemm_args", "uvx_attn_args"}
+    assert declared, "no declarations parsed"
+    lib = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/uvx.h but not exported by libuvx.so"
+        assert name in _lib.SIGNATURES, f"{name} not bound in ultravox_b200/_lib.py"
+    assert lib.uvx_abi_version() == 1
+    assert ctypes.sizeof(_lib.GemmArgs) == 8 * 18 + 4 * 3 + 4  # 18 pointers/int64 + float + 2 int32 (+pad)
+
+
+def test_host_only_mel_filter_table_is_bit_exact_with_hf():
+    transformers = pytest.importorskip("transformers")
+    lib = _lib.lib()
+    for n in (80, 128):
+        dense = np.zeros((201, n), np.float32)
+        assert lib.uvx_debug_mel_filters(n, dense.ctypes.data) == 0
+        hf = transformers.WhisperFeatureExtractor(feature_size=n).mel_filters.astype(np.float32)
+        assert np.array_equal(dense, hf)
+
+
+def test_no_cpu_fallback():
+    from ultravox_b200 import ops
+    with pytest.raises(_lib.UvxError):
+        ops.logmel(torch.zeros(1, 320), 80)
+    with pytest.raises(_lib.UvxError):
+        ops.linear(torch.zeros(4, 64, dtype=torch.bfloat16), torch.zeros(64, 64, dtype=torch.bfloat16))
+    assert lib_error_is_reported()
+
+
+def lib_error_is_reported():
+    lib = _lib.lib()
+    rc = lib.uvx_debug_mel_filters(77, None)
+    return rc == -1 and b"uvx_debug_mel_filters" in lib.uvx_last_error()

@@ -51,6 +51,7 @@ SIGNATURES = {
     "uvx_embed_splice": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "uvx_lm_head": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "uvx_argmax": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "uvx_ce_loss": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
 }
 
 _lib = None

@@ -1,0 +1,85 @@
+// Shifted causal-LM cross entropy over fp32 logits (hf:loss/loss_utils.py:28-67: labels padded with
+// ignore_index and shifted left by one, mean over the non-ignored positions, fp32 math).
+// One CTA per (b, s) row: online max / sum-exp with 128-bit loads, then one deterministic single-CTA mean.
+#include "uvx_common.cuh"
+
+namespace uvx {
+
+__global__ void __launch_bounds__(512) ce_rows_kernel(const float* __restrict__ logits, int64_t row_stride,
+                                                     const int64_t* __restrict__ labels, int64_t S, int64_t V,
+                                                     int64_t ignore_index, float* __restrict__ row_loss,
+                                                     float* __restrict__ row_lse) {
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const int64_t b = row / S, s = row % S;
+  const int64_t label = (s + 1 < S) ? labels[b * S + s + 1] : ignore_index;
+  const float* x = logits + row * row_stride;
+  // pass 1: max
+  float mx = -INFINITY;
+  for (int64_t i = threadIdx.x * 4; i < V; i += blockDim.x * 4) {
+    if (i + 3 < V) {
+      const float4 v = *reinterpret_cast<const float4*>(x + i);
+      mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    } else {
+      for (int64_t j = i; j < V; ++j) mx = fmaxf(mx, x[j]);
+    }
+  }
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  // pass 2: sum exp (row is L2-resident after pass 1)
+  float sum = 0.f;
+  for (int64_t i = threadIdx.x * 4; i < V; i += blockDim.x * 4) {
+    if (i + 3 < V) {
+      const float4 v = *reinterpret_cast<const float4*>(x + i);
+      sum += expf(v.x - mx) + expf(v.y - mx) + expf(v.z - mx) + expf(v.w - mx);
+    } else {
+      for (int64_t j = i; j < V; ++j) sum += expf(x[j] - mx);
+    }
+  }
+  sum = block_sum(sum, red);
+  if (threadIdx.x == 0) {
+    const float lse = mx + logf(sum);
+    row_lse[row] = lse;
+    const bool valid = label != ignore_index && label >= 0 && label < V;
+    row_loss[row] = valid ? lse - x[label] : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(1024) ce_mean_kernel(const float* __restrict__ row_loss, const int64_t* __restrict__ labels,
+                                                      int64_t B, int64_t S, int64_t V, int64_t ignore_index,
+                                                      float* __restrict__ out) {
+  __shared__ float red[32];
+  float sum = 0.f, cnt = 0.f;
+  for (int64_t r = threadIdx.x; r < B * S; r += blockDim.x) {
+    const int64_t s = r % S;
+    const int64_t label = (s + 1 < S) ? labels[r + 1] : ignore_index;
+    if (label != ignore_index && label >= 0 && label < V) {
+      sum += row_loss[r];
+      cnt += 1.f;
+    }
+  }
+  sum = block_sum(sum, red);
+  cnt = block_sum(cnt, red);
+  if (threadIdx.x == 0) {
+    out[0] = sum / cnt;  // 0/0 = NaN like torch when every label is ignored
+    out[1] = cnt;
+  }
+}
+
+}  // namespace uvx
+
+extern "C" int uvx_ce_loss(const float* logits, int64_t row_stride, const int64_t* labels, int64_t B, int64_t S, int64_t V,
+                           int64_t ignore_index, float* row_loss, float* row_lse, float* out_loss2, uvx_stream_t stream) {
+  using namespace uvx;
+  UVX_REQUIRE(logits && labels && row_loss && row_lse && out_loss2, "uvx_ce_loss: null pointer");
+  UVX_REQUIRE(B >= 1 && S >= 1 && V >= 1 && row_stride % 4 == 0 && (uintptr_t)logits % 16 == 0, "uvx_ce_loss: bad shape");
+  ce_rows_kernel<<<(unsigned)(B * S), 512, 0, (cudaStream_t)stream>>>(logits, row_stride, labels, S, V, ignore_index, row_loss,
+                                                                     row_lse);
+  int rc = check_launch("ce_rows_kernel");
+  if (rc) return rc;
+  ce_mean_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_loss, labels, B, S, V, ignore_index, out_loss2);
+  return check_launch("ce_mean_kernel");
+}

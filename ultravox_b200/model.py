@@ -1,0 +1,477 @@
+"""``UltravoxModel`` - drop-in model surface over the hand-written sm_100a kernels.
+
+Mirrors ``ref:ultravox/model/ultravox_model.py``: ``UltravoxModel.forward`` (:277-352), ``_prepare_audio_embeds``
+(:354-396), ``generate`` (:398-426), ``ModifiedWhisperEncoder.forward`` (:865-994), ``UltravoxProjector.forward``
+(:768-800), ``StackAudioFrames`` (:722-730); parameter names / state-dict keys are the reference's
+(``audio_tower.*``, ``multi_modal_projector.*``, ``language_model.*``), so checkpoints load unchanged.
+
+B200-first differences (none observable through the interface):
+* every op is a libuvx kernel (``ops``); q/k/v (and gate/up) projections run as ONE tcgen05 GEMM over a fused
+  weight - the per-projection ``nn.Parameter``s are views into that fused storage, so state-dict I/O is unchanged;
+* the conv stem runs as implicit GEMMs over a time-major guard-padded activation (no im2col, no permute);
+* StackAudioFrames is folded into the ln_pre kernel's addressing; the splice is one sync-free gather kernel driven
+  by a device index table (the reference does a host sync per chunk);
+* encoder attention masks are generated from ``audio_lens`` inside the attention kernel (no dense mask tensor);
+* log-mel can run on device from raw waveforms (``audio_waveforms``), fused with the bf16 time-major re-layout.
+There is no CPU fallback: tensors must be CUDA tensors and ``libuvx.so`` must be built.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Optional
+
+import torch
+import torch.nn as nn
+from transformers.modeling_outputs import CausalLMOutputWithPast
+
+from . import ops
+from .config import LossConfig, LossFunction, UltravoxConfig
+
+BF16 = torch.bfloat16
+
+
+# ------------------------------------------------------------------------------------------------ containers
+class _P(nn.Module):
+    """A leaf holding ``weight`` (and optionally ``bias``) - gives the reference's ``x.weight`` key names."""
+
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor] = None):
+        super().__init__()
+        self.weight = nn.Parameter(weight, requires_grad=False)
+        if bias is not None:
+            self.bias = nn.Parameter(bias, requires_grad=False)
+        else:
+            self.bias = None
+
+
+def _empty(*shape, device, dtype=BF16):
+    return torch.empty(*shape, device=device, dtype=dtype)
+
+
+class _WhisperAttn(nn.Module):
+    def __init__(self, d, device):
+        super().__init__()
+        self.qkv_w = _empty(3 * d, d, device=device)   # fused storage (not a parameter; views below are)
+        self.qkv_b = torch.zeros(3 * d, device=device, dtype=BF16)
+        self.q_proj = _P(self.qkv_w[0:d], self.qkv_b[0:d])
+        self.k_proj = _P(self.qkv_w[d:2 * d])           # no bias (hf:modeling_whisper.py:279)
+        self.v_proj = _P(self.qkv_w[2 * d:], self.qkv_b[2 * d:])
+        self.out_proj = _P(_empty(d, d, device=device), _empty(d, device=device))
+
+
+class _WhisperLayer(nn.Module):
+    def __init__(self, d, ffn, device):
+        super().__init__()
+        self.self_attn = _WhisperAttn(d, device)
+        self.self_attn_layer_norm = _P(_empty(d, device=device), _empty(d, device=device))
+        self.fc1 = _P(_empty(ffn, d, device=device), _empty(ffn, device=device))
+        self.fc2 = _P(_empty(d, ffn, device=device), _empty(d, device=device))
+        self.final_layer_norm = _P(_empty(d, device=device), _empty(d, device=device))
+
+
+class AudioTower(nn.Module):
+    """Whisper encoder weights (``ModifiedWhisperEncoder``, ref :803-994)."""
+
+    def __init__(self, ac, device):
+        super().__init__()
+        d = ac.d_model
+        self.d, self.heads, self.n_mels, self.max_pos = d, ac.encoder_attention_heads, ac.num_mel_bins, ac.max_source_positions
+        self.conv1 = _P(_empty(d, ac.num_mel_bins, 3, device=device), _empty(d, device=device))
+        self.conv2 = _P(_empty(d, d, 3, device=device), _empty(d, device=device))
+        self.embed_positions = _P(_empty(ac.max_source_positions, d, device=device))
+        self.layers = nn.ModuleList([_WhisperLayer(d, ac.encoder_ffn_dim, device) for _ in range(ac.encoder_layers)])
+        self.layer_norm = _P(_empty(d, device=device), _empty(d, device=device))
+
+    @property
+    def max_context_length(self) -> int:   # ref :826-832 (conv strides 1 and 2)
+        return self.max_pos * 2
+
+
+class Projector(nn.Module):
+    """``UltravoxProjector`` weights (ref :745-766)."""
+
+    def __init__(self, config: UltravoxConfig, device):
+        super().__init__()
+        dim_in = config.audio_config.d_model * config.stack_factor
+        hid = config.hidden_size
+        mid = hid // 2 if config.projector_act == "swiglu" else hid
+        out = config.text_config.hidden_size
+        self.ln_pre = _P(_empty(dim_in, device=device))
+        self.linear_1 = _P(_empty(hid, dim_in, device=device))
+        self.linear_2 = _P(_empty(out, mid, device=device))
+        if config.projector_ln_mid:
+            self.ln_mid = _P(_empty(mid, device=device))
+        else:
+            self.ln_post = _P(_empty(out, device=device))
+
+
+class _LlamaAttn(nn.Module):
+    def __init__(self, h, nq, nkv, hd, device):
+        super().__init__()
+        self.qkv_w = _empty((nq + 2 * nkv) * hd, h, device=device)
+        self.q_proj = _P(self.qkv_w[: nq * hd])
+        self.k_proj = _P(self.qkv_w[nq * hd: (nq + nkv) * hd])
+        self.v_proj = _P(self.qkv_w[(nq + nkv) * hd:])
+        self.o_proj = _P(_empty(h, nq * hd, device=device))
+
+
+class _LlamaMLP(nn.Module):
+    def __init__(self, h, ffn, device):
+        super().__init__()
+        self.gate_up_w = _empty(2 * ffn, h, device=device)
+        self.gate_proj = _P(self.gate_up_w[:ffn])
+        self.up_proj = _P(self.gate_up_w[ffn:])
+        self.down_proj = _P(_empty(h, ffn, device=device))
+
+
+class _LlamaLayer(nn.Module):
+    def __init__(self, tc, hd, device):
+        super().__init__()
+        self.self_attn = _LlamaAttn(tc.hidden_size, tc.num_attention_heads, tc.num_key_value_heads, hd, device)
+        self.mlp = _LlamaMLP(tc.hidden_size, tc.intermediate_size, device)
+        self.input_layernorm = _P(_empty(tc.hidden_size, device=device))
+        self.post_attention_layernorm = _P(_empty(tc.hidden_size, device=device))
+
+
+class _LlamaInner(nn.Module):
+    def __init__(self, tc, hd, device):
+        super().__init__()
+        self.embed_tokens = _P(_empty(tc.vocab_size, tc.hidden_size, device=device))
+        self.layers = nn.ModuleList([_LlamaLayer(tc, hd, device) for _ in range(tc.num_hidden_layers)])
+        self.norm = _P(_empty(tc.hidden_size, device=device))
+
+
+class LanguageModel(nn.Module):
+    def __init__(self, tc, device):
+        super().__init__()
+        self.head_dim = getattr(tc, "head_dim", None) or tc.hidden_size // tc.num_attention_heads
+        self.model = _LlamaInner(tc, self.head_dim, device)
+        self.tied = bool(getattr(tc, "tie_word_embeddings", False))
+        if self.tied:
+            self.lm_head = _P(self.model.embed_tokens.weight.data)
+        else:
+            self.lm_head = _P(_empty(tc.vocab_size, tc.hidden_size, device=device))
+
+    def get_input_embeddings(self):
+        return self.model.embed_tokens
+
+
+@dataclasses.dataclass
+class KVCache:
+    """Static per-layer K (post-RoPE) / V cache, [L, B, S_max, Hkv, D] bf16."""
+    k: torch.Tensor
+    v: torch.Tensor
+    length: int = 0
+
+    def get_seq_length(self) -> int:
+        return self.length
+
+
+# ------------------------------------------------------------------------------------------------ the model
+class UltravoxModel(nn.Module):
+    config_class = UltravoxConfig
+    _keys_to_ignore_on_load_missing = ["audio_tower.*", "language_model.*"]
+    accepts_loss_kwargs = False
+
+    def __init__(self, config: UltravoxConfig, device="cuda"):
+        super().__init__()
+        self.config = config
+        self.vocab_size = config.vocab_size
+        self.keep_params: set[str] = set()
+        dev = torch.device(device)
+        if not config.llm_only_training:
+            self.audio_tower = AudioTower(config.audio_config, dev)
+            self.multi_modal_projector = Projector(config, dev)
+            self.audio_tower_context_length = self.audio_tower.max_context_length
+        self.language_model = LanguageModel(config.text_config, dev)
+        self.loss_config = LossConfig()
+        self._derived: dict = {}
+        self._rope: Optional[tuple] = None
+        # projector params are the trainable ones in the adapter-only recipe (ref apply_lora r=0 freezes the rest)
+        if not config.llm_only_training:
+            for p in self.multi_modal_projector.parameters():
+                p.requires_grad_(True)
+
+    # -- reference surface ---------------------------------------------------------------------------
+    def get_input_embeddings(self):
+        return self.language_model.get_input_embeddings()
+
+    def set_loss_config(self, loss_config: LossConfig):
+        self.loss_config = loss_config
+
+    @property
+    def device(self):
+        return self.language_model.model.norm.weight.device
+
+    @property
+    def dtype(self):
+        return BF16
+
+    def diff_state_dict(self, state_dict=None):
+        """ref :565-584 - only trainable (+ explicitly kept) parameters."""
+        sd = state_dict if state_dict is not None else self.state_dict()
+        trainable = {k for k, v in self.named_parameters() if v.requires_grad}
+        return {k: v for k, v in sd.items() if k in self.keep_params or k in trainable}
+
+    # -- weights -------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def init_random_(self, seed: int = 42):
+        """Seeded synthetic weights: Linear/Conv/Embedding ~ N(0, initializer_range), biases 0,
+        Layer/RMS-norm weight 1, projector RMSNorm weights = norm_init, sinusoidal ``embed_positions``."""
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        std = self.config.initializer_range
+        for name, p in self.named_parameters():
+            if name.endswith("embed_positions.weight"):
+                p.copy_(_sinusoids(p.shape[0], p.shape[1]).to(p.device, p.dtype))
+            elif "multi_modal_projector.ln_" in name:
+                p.fill_(self.config.norm_init)
+            elif "layer_norm" in name or "layernorm" in name or name.endswith("model.norm.weight"):
+                p.fill_(1.0) if name.endswith("weight") else p.zero_()
+            elif name.endswith("bias"):
+                p.zero_()
+            else:
+                # chunked fill keeps the fp32 staging buffer small for 8B / 70B
+                flat = p.view(-1)
+                step = 1 << 26
+                for i in range(0, flat.numel(), step):
+                    n = min(step, flat.numel() - i)
+                    flat[i:i + n] = (torch.randn(n, generator=g, device=p.device, dtype=torch.float32) * std).to(p.dtype)
+        self.prepare()
+        return self
+
+    @torch.no_grad()
+    def prepare(self):
+        """(Re)build derived device buffers: conv weights re-laid for the implicit GEMM, rope tables.  Call after
+        loading / changing encoder conv weights."""
+        if hasattr(self, "audio_tower"):
+            at = self.audio_tower
+            self._derived["conv1_w"] = at.conv1.weight.permute(0, 2, 1).reshape(at.d, -1).contiguous()
+            self._derived["conv2_w"] = at.conv2.weight.permute(0, 2, 1).reshape(at.d, -1).contiguous()
+        tc = self.config.text_config
+        rp = getattr(tc, "rope_parameters", None) or {}
+        scaling = getattr(tc, "rope_scaling", None) or (rp if rp.get("rope_type", "default") != "default" else None)
+        theta = rp.get("rope_theta", None) or getattr(tc, "rope_theta", 10000.0)
+        inv = ops.llama3_inv_freq(self.language_model.head_dim, float(theta), scaling)
+        self._inv_freq = inv
+        self._rope = None
+        return self
+
+    def _rope_tables(self, need: int):
+        if self._rope is None or self._rope[0].shape[0] < need:
+            n = max(need, 4096)
+            self._rope = ops.rope_tables(self._inv_freq, n, self.device)
+        return self._rope
+
+    # -- audio tower ---------------------------------------------------------------------------------
+    def encode_audio(self, x_tm: torch.Tensor, audio_lens: Optional[torch.Tensor]) -> torch.Tensor:
+        """x_tm [N, T+2, n_mels] bf16 guard-padded time-major mel -> encoder output [N, ceil(T/2), d]
+        (``ModifiedWhisperEncoder.forward``, ref :865-994)."""
+        at = self.audio_tower
+        N, Tp, _ = x_tm.shape
+        T = Tp - 2
+        if T > at.max_context_length:
+            raise ValueError(f"Whisper expects the mel input features to be of length {at.max_context_length} or less, "
+                             f"but found {T}. Make sure to pad the input mel features to {at.max_context_length}.")
+        d, H = at.d, at.heads
+        T2 = (T + 1) // 2
+        dev = x_tm.device
+        h1 = torch.zeros(N, T + 2, d, dtype=BF16, device=dev)
+        ops.conv1d_k3(x_tm, self._derived["conv1_w"], at.conv1.bias, 1, h1, out_guard=True)
+        h = torch.empty(N, T2, d, dtype=BF16, device=dev)
+        ops.conv1d_k3(h1, self._derived["conv2_w"], at.conv2.bias, 2, h, out_guard=False,
+                      pos=at.embed_positions.weight[:T2])
+        kv_len = None
+        if audio_lens is not None:
+            kv_len = ((audio_lens.to(dev, torch.int64) - 1) // 2 + 1).to(torch.int32)
+        block = int(self.config.audio_latency_block_size or 0)
+        hd = d // H
+        x = torch.empty_like(h)
+        qkv = torch.empty(N * T2, 3 * d, dtype=BF16, device=dev)
+        att = torch.empty(N * T2, d, dtype=BF16, device=dev)
+        ff = torch.empty(N * T2, at.layers[0].fc1.weight.shape[0], dtype=BF16, device=dev)
+        for layer in at.layers:
+            sa = layer.self_attn
+            ops.layernorm(h, layer.self_attn_layer_norm.weight, layer.self_attn_layer_norm.bias, 1e-5, out=x)
+            ops.linear(x, sa.qkv_w, sa.qkv_b, out=qkv)
+            ops.attention_fused_qkv(qkv, N, T2, H, H, hd, hd ** -0.5, False, kv_len, block, out=att)
+            ops.linear(att, sa.out_proj.weight, sa.out_proj.bias, residual=h, out=h)
+            ops.layernorm(h, layer.final_layer_norm.weight, layer.final_layer_norm.bias, 1e-5, out=x)
+            ops.linear(x, layer.fc1.weight, layer.fc1.bias, act=ops.ACT_GELU, out=ff)
+            ops.linear(ff, layer.fc2.weight, layer.fc2.bias, residual=h, out=h)
+        return ops.layernorm(h, at.layer_norm.weight, at.layer_norm.bias, 1e-5, out=x)
+
+    def project_audio(self, enc: torch.Tensor) -> torch.Tensor:
+        """``UltravoxProjector.forward`` (ref :768-800): [N, T2, d] -> [N, ceil(T2/stack), D_text]."""
+        pj, cfg = self.multi_modal_projector, self.config
+        x = ops.stack_rmsnorm(enc, pj.ln_pre.weight, cfg.stack_factor, 1e-6)
+        y = ops.linear(x, pj.linear_1.weight)
+        if cfg.projector_act != "swiglu":
+            raise NotImplementedError(f"projector_act={cfg.projector_act!r}: only 'swiglu' (all released configs) is built")
+        z = ops.swiglu(y, gate_first=False)
+        if cfg.projector_ln_mid:
+            z = ops.rmsnorm(z, pj.ln_mid.weight, 1e-6)
+        a = ops.linear(z, pj.linear_2.weight)
+        if not cfg.projector_ln_mid:
+            a = ops.rmsnorm(a, pj.ln_post.weight, 1e-6)
+        return a
+
+    def _prepare_audio_embeds(self, input_ids, audio_values=None, audio_token_start_idx=None, audio_lens=None,
+                              audio_token_len=None, audio_batch_size=None, audio_tm=None) -> torch.Tensor:
+        """Embedding gather + audio splice (ref :354-396).  Returns the spliced ``inputs_embeds`` [B, S, D]."""
+        assert (audio_token_start_idx is not None and audio_token_len is not None and audio_lens is not None
+                and audio_batch_size is not None), \
+            "inputs_embeds/audio_values/audio_token_start_idx/audio_token_len/audio_lens/audio_batch_size must be provided."
+        n = audio_values.shape[0] if audio_values is not None else audio_tm.shape[0]
+        assert len(audio_token_start_idx) == len(audio_token_len) == len(audio_lens) == n, \
+            "audio_token_start_idx/audio_token_len/audio_lens/audio_values must have the same batch size."
+        assert len(audio_batch_size) == len(input_ids), "audio_batch_size and inputs_embeds must have the same batch size."
+        dev = self.device
+        if audio_tm is None:
+            audio_tm = ops.mel_to_timemajor(audio_values.to(dev, torch.float32))
+        enc = self.encode_audio(audio_tm, audio_lens)
+        aud = self.project_audio(enc)
+        B, S = input_ids.shape
+        src = ops.splice_plan(audio_token_start_idx.to(dev, torch.int64).contiguous(),
+                              audio_token_len.to(dev, torch.int32).contiguous(),
+                              audio_batch_size.to(dev, torch.int64).reshape(-1).contiguous(), B, S, aud.shape[1])
+        return ops.embed_splice(input_ids, self.language_model.model.embed_tokens.weight, aud, src)
+
+    # -- llama ---------------------------------------------------------------------------------------
+    def llama_hidden(self, inputs_embeds: torch.Tensor, cache: Optional[KVCache] = None,
+                     kv_len: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """All decoder layers + final RMSNorm (hf:models/llama/modeling_llama.py:355-426).  ``inputs_embeds`` [B,S,D]
+        is consumed in place (it becomes the residual stream).  ``kv_len`` [B] int32 masks right padding."""
+        lm, tc = self.language_model, self.config.text_config
+        B, S, Dm = inputs_embeds.shape
+        nq, nkv, hd = tc.num_attention_heads, tc.num_key_value_heads, lm.head_dim
+        eps = tc.rms_norm_eps
+        dev = inputs_embeds.device
+        past = cache.length if cache is not None else 0
+        cos, sin = self._rope_tables(past + S)
+        h = inputs_embeds.view(B * S, Dm)
+        x = torch.empty_like(h)
+        qkv = torch.empty(B * S, (nq + 2 * nkv) * hd, dtype=BF16, device=dev)
+        att = torch.empty(B * S, nq * hd, dtype=BF16, device=dev)
+        ffn = tc.intermediate_size
+        gu = torch.empty(B * S, 2 * ffn, dtype=BF16, device=dev)
+        act = torch.empty(B * S, ffn, dtype=BF16, device=dev)
+        rs = qkv.stride(0)
+        for li, layer in enumerate(lm.model.layers):
+            sa, mlp = layer.self_attn, layer.mlp
+            ops.rmsnorm(h, layer.input_layernorm.weight, eps, out=x)
+            ops.linear(x, sa.qkv_w, out=qkv)
+            ops.rope_(qkv, nq, nkv, hd, cos, sin, rows_per_seq=S, pos_offset=past)
+            if cache is None:
+                ops.attention_fused_qkv(qkv, B, S, nq, nkv, hd, hd ** -0.5, True, kv_len, 0, out=att)
+            else:
+                kc, vc = cache.k[li], cache.v[li]            # [B, S_max, Hkv, D]
+                kc[:, past:past + S].copy_(qkv.view(B, S, -1)[:, :, nq * hd:(nq + nkv) * hd].view(B, S, nkv, hd))
+                vc[:, past:past + S].copy_(qkv.view(B, S, -1)[:, :, (nq + nkv) * hd:].view(B, S, nkv, hd))
+                smax = kc.shape[1]
+                ops.attention(qkv.data_ptr(), kc.data_ptr(), vc.data_ptr(), att, B, nq, nkv, S, past + S, hd,
+                              (rs, S * rs, nkv * hd, smax * nkv * hd, nkv * hd, smax * nkv * hd, nq * hd, S * nq * hd),
+                              hd ** -0.5, True, kv_len, 0)
+            ops.linear(att, sa.o_proj.weight, residual=h, out=h)
+            ops.rmsnorm(h, layer.post_attention_layernorm.weight, eps, out=x)
+            ops.linear(x, mlp.gate_up_w, out=gu)
+            ops.swiglu(gu, gate_first=True, out=act)
+            ops.linear(act, mlp.down_proj.weight, residual=h, out=h)
+        if cache is not None:
+            cache.length = past + S
+        return ops.rmsnorm(h, lm.model.norm.weight, eps, out=x).view(B, S, Dm)
+
+    def new_cache(self, batch: int, max_len: int) -> KVCache:
+        tc, lm = self.config.text_config, self.language_model
+        shape = (tc.num_hidden_layers, batch, max_len, tc.num_key_value_heads, lm.head_dim)
+        return KVCache(torch.empty(shape, dtype=BF16, device=self.device), torch.empty(shape, dtype=BF16, device=self.device))
+
+    @staticmethod
+    def _right_pad_lengths(attention_mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        """attention_mask [B,S] of 1s then 0s -> kv_len int32; None if all ones; left padding is not built yet."""
+        if attention_mask is None:
+            return None
+        m = attention_mask.to(torch.bool)
+        if bool(m.all()):
+            return None
+        lens = m.sum(-1)
+        ar = torch.arange(m.shape[1], device=m.device)[None, :]
+        if not torch.equal(m, ar < lens[:, None]):
+            raise NotImplementedError("left / interior padding in attention_mask (SURVEY.md 8f rank 2) is not built yet; "
+                                      "use right padding or unpadded batches")
+        return lens.to(torch.int32)
+
+    # -- forward / generate --------------------------------------------------------------------------
+    def forward(self, input_ids: torch.Tensor, audio_values: Optional[torch.Tensor] = None,
+                inputs_embeds: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
+                attention_mask: Optional[torch.Tensor] = None, audio_token_start_idx: Optional[torch.Tensor] = None,
+                audio_lens: Optional[torch.Tensor] = None, audio_token_len: Optional[torch.Tensor] = None,
+                audio_batch_size: Optional[torch.Tensor] = None, past_key_values: Optional[KVCache] = None,
+                alt_input_ids=None, alt_attention_mask=None, alt_labels=None, logits_to_keep: int = 0,
+                **kwargs) -> CausalLMOutputWithPast:
+        """Same signature and semantics as the reference ``forward`` (ref :277-352).  ``logits_to_keep=1`` computes
+        only the last position's logits (the TTFT path, hf:modeling_llama.py:485-491)."""
+        dev = self.device
+        input_ids = input_ids.to(dev)
+        if inputs_embeds is None:
+            if audio_values is not None and len(audio_values) > 0:
+                inputs_embeds = self._prepare_audio_embeds(input_ids, audio_values, audio_token_start_idx, audio_lens,
+                                                           audio_token_len, audio_batch_size)
+            else:
+                inputs_embeds = ops.embed_splice(input_ids, self.language_model.model.embed_tokens.weight, None, None)
+        else:
+            inputs_embeds = inputs_embeds.clone()
+        if self.training and self.loss_config.loss_function not in (LossFunction.CrossEntropy, LossFunction.KL_Divergence):
+            raise ValueError(f"Unsupported loss function: {self.loss_config.loss_function}")
+        kv_len = self._right_pad_lengths(attention_mask.to(dev) if attention_mask is not None else None)
+        hidden = self.llama_hidden(inputs_embeds, past_key_values, kv_len)
+        B, S, Dm = hidden.shape
+        lm_w = self.language_model.lm_head.weight
+        if logits_to_keep == 1:
+            logits = ops.lm_head(hidden[:, -1, :], lm_w).view(B, 1, -1)
+        else:
+            logits = ops.linear(hidden.view(B * S, Dm), lm_w, out_dtype=torch.float32).view(B, S, -1)
+        loss = None
+        if labels is not None:
+            from .losses import causal_lm_loss
+            loss = causal_lm_loss(logits, labels.to(dev), self.config.ignore_index)
+        return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=past_key_values)
+
+    @torch.no_grad()
+    def generate(self, input_ids: torch.Tensor, audio_values: Optional[torch.Tensor] = None,
+                 inputs_embeds: Optional[torch.Tensor] = None, audio_token_start_idx=None, audio_lens=None,
+                 audio_token_len=None, audio_batch_size=None, max_new_tokens: int = 20, eos_token_id=None,
+                 attention_mask: Optional[torch.Tensor] = None, **kwargs) -> torch.Tensor:
+        """Greedy decoding (the reference's default: temperature None/0, ref infer.py:319-328).  Returns prompt ids
+        followed by the new tokens, like ``GenerationMixin.generate`` (ref :398-426)."""
+        dev = self.device
+        input_ids = input_ids.to(dev)
+        B, S = input_ids.shape
+        if attention_mask is not None and not bool(attention_mask.to(torch.bool).all()):
+            raise NotImplementedError("padded batches in generate() are not built yet (SURVEY.md 8f rank 2)")
+        cache = self.new_cache(B, S + max_new_tokens)
+        out = self.forward(input_ids, audio_values, inputs_embeds, None, None, audio_token_start_idx, audio_lens,
+                           audio_token_len, audio_batch_size, cache, logits_to_keep=1)
+        eos = set([eos_token_id] if isinstance(eos_token_id, int) else (eos_token_id or []))
+        seq = [input_ids]
+        done = torch.zeros(B, dtype=torch.bool, device=dev)
+        tok = ops.argmax(out.logits.view(B, -1))
+        for step in range(max_new_tokens):
+            seq.append(tok.view(B, 1))
+            if eos:
+                done |= torch.isin(tok, torch.tensor(sorted(eos), device=dev))
+                if bool(done.all()):
+                    break
+            if step == max_new_tokens - 1:
+                break
+            emb = ops.embed_splice(tok.view(B, 1), self.language_model.model.embed_tokens.weight, None, None)
+            hidden = self.llama_hidden(emb, cache)
+            tok = ops.argmax(ops.lm_head(hidden[:, -1, :], self.language_model.lm_head.weight))
+        return torch.cat(seq, dim=1)
+
+
+def _sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> torch.Tensor:
+    """Whisper's fixed positional table (hf:models/whisper/modeling_whisper.py:55-65)."""
+    import math
+    inc = math.log(max_timescale) / (channels // 2 - 1)
+    inv = torch.exp(-inc * torch.arange(channels // 2))
+    t = torch.arange(length).view(-1, 1) * inv.view(1, -1)
+    return torch.cat([t.sin(), t.cos()], dim=1)
