@@ -1,0 +1,355 @@
+"""Headline benchmark: audio-seconds/s of prefill (and TTFT p50) for Ultravox-v0.5-shaped random-init weights
+(Whisper-large-v3 encoder + Llama-3.1-8B), synthetic 30 s / 16 kHz clips, batch 1 per GPU, data-parallel replicas.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--preset v0_5_8b] [--secs 30]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one full pass of the hot path over one clip: waveform -> log-mel -> encoder -> projector -> splice -> Llama
+prefill -> last-position logits -> argmax (one CUDA-graph replay of libuvx kernels).  `value` is measured with the
+waveform already resident in HBM; `e2e` goes through PrefillEngine.run_e2e with a pinned HOST waveform (H2D inside the
+timed region, token D2H + sync per step).  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "audio-sec/s prefill (Llama-3.1-8B, 30s clip) at 1/2/4/8 B200; TTFT p50"
+UNIT = "audio-sec/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--preset", default="v0_5_8b")
+    ap.add_argument("--secs", type=float, default=30.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--cpu-layers", type=int, default=2, help="encoder / LLM layers timed by the CPU baseline sample")
+    return ap.parse_args()
+
+
+def workload(cfg, secs):
+    """Synthetic request of SURVEY.md 8d: 8 text ids + audio placeholders + 5 text ids, start idx 8."""
+    import torch
+    n = int(round(16000 * secs))
+    frames = -(-n // 160)
+    n_tok = -(-frames // 16)
+    g = torch.Generator().manual_seed(7)
+    ids = torch.cat([torch.randint(0, min(cfg.vocab_size, 128000), (8,), generator=g), torch.full((n_tok,), 128009 % cfg.vocab_size),
+                     torch.randint(0, min(cfg.vocab_size, 128000), (5,), generator=g)])[None]
+    return dict(n=n, frames=frames, n_tok=n_tok, input_ids=ids, start=torch.tensor([8]),
+                tok_len=torch.tensor([n_tok], dtype=torch.int32), abs=torch.tensor([1]))
+
+
+def config_block(args, cfg, wl, n_gpus):
+    return {"workload": f"cfg2: Ultravox-v0.5 shapes ({args.preset}: Whisper-large-v3 encoder + Llama-3.1-8B, random-init), "
+                        f"{args.secs:g} s 16 kHz synthetic clip prefill, batch 1 per GPU",
+            "clip_seconds": args.secs, "llm_tokens": int(wl["input_ids"].shape[1]), "audio_tokens": wl["n_tok"],
+            "batch_per_gpu": 1, "parallelism": f"replicas x{n_gpus} (no collective)",
+            "l2": "weights streamed per step (17.6 GB) >> 126 MB L2, so every step re-reads HBM; no explicit flush"}
+
+
+# ----------------------------------------------------------------------------------------------- CPU baseline (oracle)
+def cpu_baseline(cfg, wl, n_layers_sample: int):
+    """Times the fp32 CPU oracle (the reference's algorithm) on this box's host cores on a bounded sample of the same
+    workload: full log-mel + conv stem + `n_layers_sample` encoder layers + projector + splice + `n_layers_sample` LLM
+    layers + final norm + last-row lm_head; the two layer loops are extrapolated to the full depth."""
+    import numpy as np
+    import torch
+    from oracle import logmel as ol, model as om
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sh = om.shapes_from_config(cfg)
+    g = torch.Generator().manual_seed(42)
+
+    def r(*s, std=0.02):
+        return torch.randn(*s, generator=g) * std
+
+    wave = np.random.default_rng(1000).standard_normal(wl["n"]).astype(np.float32)
+    t = {}
+    t0 = time.perf_counter()
+    padded, frames = ol.pad_batch([wave])
+    mel = torch.from_numpy(ol.log_mel(padded, sh.n_mels, dtype=np.float32))
+    t["mel"] = time.perf_counter() - t0
+    d, f = sh.enc_d, sh.enc_ffn
+    sd = {"conv1.weight": r(d, sh.n_mels, 3), "conv1.bias": torch.zeros(d), "conv2.weight": r(d, d, 3),
+          "conv2.bias": torch.zeros(d)}
+    lay = {}
+    for nm, shp in (("self_attn.q_proj.weight", (d, d)), ("self_attn.k_proj.weight", (d, d)), ("self_attn.v_proj.weight", (d, d)),
+                    ("self_attn.out_proj.weight", (d, d)), ("fc1.weight", (f, d)), ("fc2.weight", (d, f))):
+        lay["L." + nm] = r(*shp)
+    for nm, n_ in (("self_attn.q_proj.bias", d), ("self_attn.v_proj.bias", d), ("self_attn.out_proj.bias", d), ("fc1.bias", f),
+                   ("fc2.bias", d), ("self_attn_layer_norm.bias", d), ("final_layer_norm.bias", d)):
+        lay["L." + nm] = torch.zeros(n_)
+    lay["L.self_attn_layer_norm.weight"] = torch.ones(d)
+    lay["L.final_layer_norm.weight"] = torch.ones(d)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        h = torch.nn.functional.gelu(torch.nn.functional.conv1d(mel, sd["conv1.weight"], sd["conv1.bias"], padding=1))
+        h = torch.nn.functional.gelu(torch.nn.functional.conv1d(h, sd["conv2.weight"], sd["conv2.bias"], stride=2, padding=1))
+        h = h.permute(0, 2, 1).contiguous()
+        mask = om.encoder_masks(torch.tensor([int(frames[0])]), h.shape[1], h.dtype, None)
+        t["conv_stem"] = time.perf_counter() - t0
+        om.whisper_layer(lay, "L.", h, mask, sh.enc_heads)  # warm-up
+        t0 = time.perf_counter()
+        for _ in range(n_layers_sample):
+            h2 = om.whisper_layer(lay, "L.", h, mask, sh.enc_heads)
+        t["enc_layer"] = (time.perf_counter() - t0) / n_layers_sample
+        pj = {"P.ln_pre.weight": torch.full((d * sh.stack,), 0.4), "P.linear_1.weight": r(sh.proj_hidden, d * sh.stack),
+              "P.ln_mid.weight": torch.full((sh.proj_hidden // 2,), 0.4), "P.linear_2.weight": r(sh.d, sh.proj_hidden // 2)}
+        t0 = time.perf_counter()
+        aud = om.projector(pj, sh, h2, prefix="P.")
+        S = int(wl["input_ids"].shape[1])
+        emb = r(1, S, sh.d)
+        om.splice(emb, aud, wl["start"], wl["tok_len"], wl["abs"])
+        t["projector_splice"] = time.perf_counter() - t0
+        D, F_ = sh.d, sh.ffn
+        ll = {"M.input_layernorm.weight": torch.ones(D), "M.post_attention_layernorm.weight": torch.ones(D),
+              "M.self_attn.q_proj.weight": r(sh.heads * sh.head_dim, D), "M.self_attn.k_proj.weight": r(sh.kv_heads * sh.head_dim, D),
+              "M.self_attn.v_proj.weight": r(sh.kv_heads * sh.head_dim, D), "M.self_attn.o_proj.weight": r(D, sh.heads * sh.head_dim),
+              "M.mlp.gate_proj.weight": r(F_, D), "M.mlp.up_proj.weight": r(F_, D), "M.mlp.down_proj.weight": r(D, F_)}
+        cos, sin = om.rope_cos_sin(sh, torch.arange(S)[None])
+        neg = torch.finfo(torch.float32).min
+        causal = torch.triu(torch.full((S, S), neg), diagonal=1)[None, None]
+        om.llama_layer(ll, "M.", sh, emb, cos, sin, causal)
+        t0 = time.perf_counter()
+        for _ in range(n_layers_sample):
+            hh = om.llama_layer(ll, "M.", sh, emb, cos, sin, causal)
+        t["llm_layer"] = (time.perf_counter() - t0) / n_layers_sample
+        head = r(sh.vocab, D)
+        t0 = time.perf_counter()
+        x = om.rms_norm(hh, torch.ones(D), sh.rms_eps)[:, -1:, :]
+        int(torch.nn.functional.linear(x, head).argmax(-1))
+        t["final_norm_lm_head"] = time.perf_counter() - t0
+    total = (t["mel"] + t["conv_stem"] + t["enc_layer"] * sh.enc_layers + t["projector_splice"] + t["llm_layer"] * sh.layers
+             + t["final_norm_lm_head"])
+    secs = wl["n"] / 16000.0
+    return {"value": secs / total, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"fp32 CPU oracle, 1 clip: full log-mel + conv stem + {n_layers_sample}/{sh.enc_layers} encoder layers + "
+                      f"projector + splice + {n_layers_sample}/{sh.layers} LLM layers + final norm + last-row lm_head; layer "
+                      f"loops extrapolated to full depth (ttft_s {total:.2f})",
+            "stage_seconds": {k: round(v, 4) for k, v in t.items()}, "ttft_s": total}
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- roofline pass
+def roofline_pass(model, eng, peaks):
+    """Per-launch CUDA-event timing of the dominant kernel (gemm_tc_kernel in the Llama prefill, HBM-bound: M = S = 201
+    tokens against 15 GB of weights) on the launching stream, eager (non-graph) replay of the same step, right after the
+    timed region.  Algorithmic bytes per launch = W (N*K*2) + A (M*K*2) + C (M*N*2) (+ residual read)."""
+    import torch
+    from ultravox_b200 import ops
+    rec = []
+    orig = ops.gemm_raw
+
+    def timed(A_ptr, a_batch, a_rows, K, a_rs, a_bs, W, C_t, *a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig(A_ptr, a_batch, a_rows, K, a_rs, a_bs, W, C_t, *a, **k)
+        e1.record()
+        M, N = a_batch * a_rows, W.shape[0]
+        R = k.get("R", a[5] if len(a) > 5 else None)
+        byt = N * K * 2 + M * K * 2 + M * N * C_t.element_size() + (M * N * 2 if R is not None else 0)
+        rec.append((e0, e1, M, N, K, byt, 2.0 * M * N * K))
+
+    ops.gemm_raw = timed
+    try:
+        for _ in range(3):
+            rec.clear()
+            eng._step()
+            torch.cuda.synchronize()
+    finally:
+        ops.gemm_raw = orig
+    S = eng.input_ids.shape[1]
+    llm = [(e0.elapsed_time(e1) * 1e-3, byt, fl) for e0, e1, M, N, K, byt, fl in rec if M == S * eng.input_ids.shape[0] and K >= 2048]
+    enc = [(e0.elapsed_time(e1) * 1e-3, byt, fl) for e0, e1, M, N, K, byt, fl in rec if M > S * eng.input_ids.shape[0]]
+    out = {}
+    if llm:
+        tt, bb = sum(x[0] for x in llm), sum(x[1] for x in llm)
+        peak = peaks.get("hbm_gbs", 6650.0)
+        out = {"bound": "hbm", "kernel": "gemm_tc_kernel (Llama prefill GEMMs, M=%d)" % S, "achieved": bb / tt / 1e9,
+               "peak": peak, "unit": "GB/s", "frac": bb / tt / 1e9 / peak, "traffic": None, "launches": len(llm),
+               "avg_launch_us": tt / len(llm) * 1e6, "bytes_per_launch_avg": bb / len(llm),
+               "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+               "how": "CUDA events around each launch on the launching stream, eager replay of the step after the timed region"}
+    if enc:
+        tt, ff = sum(x[0] for x in enc), sum(x[2] for x in enc)
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        out["encoder_gemms"] = {"bound": "tensor", "achieved": ff / tt / 1e12, "peak": peak, "unit": "TFLOP/s",
+                                "frac": ff / tt / 1e12 / peak, "launches": len(enc), "avg_launch_us": tt / len(enc) * 1e6}
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- main
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from ultravox_b200.config import preset
+    cfg = preset(args.preset)
+    import torch
+    wl = workload(cfg, args.secs)
+
+    if args.impl == "reference":
+        # the reference's own path is CPU PyTorch (pure Python repo); it cannot be pip-installed/imported here verbatim
+        # (accelerate/peft/librosa absent, transformers 4->5 drift), so the arm times the oracle port.
+        if rank != 0:
+            return
+        t0 = time.perf_counter()
+        vals = []
+        for _ in range(max(1, min(args.steps, 2))):
+            cb = cpu_baseline(cfg, wl, args.cpu_layers)
+            vals.append(cb)
+        cb = max(vals, key=lambda c: c["value"])
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": cb["ttft_s"] * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_block(args, cfg, wl, args.gpus),
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "ttft_ms_p50": cb["ttft_s"] * 1e3, "wall_s": time.perf_counter() - t0}
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch.distributed as dist
+    from ultravox_b200 import _lib
+    from ultravox_b200.engine import PrefillEngine
+    from ultravox_b200.model import UltravoxModel
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    model = UltravoxModel(cfg, device=dev).init_random_(seed=42)
+    eng = PrefillEngine(model, wl["n"], wl["input_ids"], wl["start"], wl["tok_len"], wl["abs"])
+    K, W = args.steps, max(args.warmup, 3)
+    n_wave = min(K, 8)
+    host = [torch.from_numpy(np.random.default_rng(1000 + rank * 100 + i).standard_normal(wl["n"]).astype(np.float32))[None]
+            for i in range(n_wave)]
+    host = [torch.nn.functional.pad(h, (0, eng.L - h.shape[1])).pin_memory() for h in host]
+    devw = [h.to(dev) for h in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value")
+    for i in range(W):
+        eng.wave.copy_(devw[i % n_wave])
+        eng.run()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        eng.wave.copy_(devw[i % n_wave])      # D2D stage of the resident waveform into the graph's input buffer
+        eng.run()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+    # ---- end to end through the public engine call with HOST buffers
+    for i in range(3):
+        eng.run_e2e(host[i % n_wave])
+    barrier()
+    per = []
+    t0 = time.perf_counter()
+    for i in range(K):
+        s0 = time.perf_counter()
+        eng.run_e2e(host[i % n_wave])
+        per.append(time.perf_counter() - s0)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    tokens_ok = int(eng.token[0]) >= 0
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        secs = wl["n"] / 16000.0
+        line = {"metric": METRIC, "value": world * K * secs / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic", "config": config_block(args, cfg, wl, world),
+                "e2e": {"value": world * K * secs / float(e2e_s), "unit": UNIT, "h2d_bytes_per_step": int(host[0].numel() * 4),
+                        "d2h_bytes_per_step": 8, "timer": "host perf_counter around K engine.run_e2e calls, max over ranks"},
+                "ttft_ms_p50": statistics.median(per) * 1e3, "ttft_ms_p90": sorted(per)[int(0.9 * (len(per) - 1))] * 1e3,
+                "gpu_launches": eng.launches_per_step * K, "launches_per_step": eng.launches_per_step,
+                "clocks": clocks, "token_check": tokens_ok}
+        if not args.no_roofline:
+            try:
+                line["roofline"] = roofline_pass(model, eng, peaks)
+            except Exception as e:  # never lose the headline number to the diagnostic pass
+                line["roofline"] = {"error": repr(e)}
+        if not args.no_cpu_baseline:
+            cb = cpu_baseline(cfg, wl, args.cpu_layers)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "stage_seconds")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

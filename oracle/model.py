@@ -276,3 +276,31 @@ def forward(sd, sh: Shapes, input_ids, audio_values=None, audio_token_start_idx=
     logits = llama_forward(sd, sh, emb, attention_mask, last_only=last_only)
     loss = causal_lm_loss(logits, labels) if labels is not None else None
     return logits, loss
+
+
+# --------------------------------------------------------------------------- adapters (duck-typed; no product import)
+def shapes_from_config(cfg) -> Shapes:
+    """Build ``Shapes`` from an UltravoxConfig-like object (reference or ultravox_b200 - same field names)."""
+    ac, tc = cfg.audio_config, cfg.text_config
+    rp = getattr(tc, "rope_parameters", None) or {}
+    sc = getattr(tc, "rope_scaling", None) or rp
+    llama3 = bool(sc) and sc.get("rope_type", sc.get("type", "default")) == "llama3"
+    theta = rp.get("rope_theta", None) or getattr(tc, "rope_theta", 10000.0)
+    return Shapes(
+        n_mels=ac.num_mel_bins, enc_d=ac.d_model, enc_layers=ac.encoder_layers, enc_heads=ac.encoder_attention_heads,
+        enc_ffn=ac.encoder_ffn_dim, enc_max_pos=ac.max_source_positions, stack=cfg.stack_factor,
+        proj_hidden=cfg.hidden_size, proj_ln_mid=cfg.projector_ln_mid, proj_act=cfg.projector_act, d=tc.hidden_size,
+        layers=tc.num_hidden_layers, heads=tc.num_attention_heads, kv_heads=tc.num_key_value_heads,
+        head_dim=getattr(tc, "head_dim", None) or tc.hidden_size // tc.num_attention_heads, ffn=tc.intermediate_size,
+        vocab=tc.vocab_size, rms_eps=tc.rms_norm_eps, rope_theta=float(theta), rope_llama3=llama3,
+        rope_factor=float(sc.get("factor", 8.0)) if llama3 else 8.0,
+        rope_low=float(sc.get("low_freq_factor", 1.0)) if llama3 else 1.0,
+        rope_high=float(sc.get("high_freq_factor", 4.0)) if llama3 else 4.0,
+        rope_orig_ctx=int(sc.get("original_max_position_embeddings", 8192)) if llama3 else 8192,
+        tie_embeddings=bool(getattr(tc, "tie_word_embeddings", False)),
+        latency_block=getattr(cfg, "audio_latency_block_size", None))
+
+
+def state_dict_fp32(module) -> dict:
+    """fp32 CPU copy of a torch module's state dict (bit-identical values: bf16 -> fp32 is exact)."""
+    return {k: v.detach().to("cpu", torch.float32) for k, v in module.state_dict().items()}

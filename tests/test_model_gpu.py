@@ -1,0 +1,188 @@
+"""End-to-end parity of the CUDA path (through the C ABI) against the fp32 CPU oracle on shared seeded weights.
+
+Stage tolerances follow SURVEY.md section 7: bf16 storage between kernels means the end-to-end error against an fp32
+oracle is a few 1e-3 .. 1e-2 relative (HF's own bf16 forward shows 7e-3 after one layer, 1.3e-2 after 32); index / splice
+paths are bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def wave(i, n):
+    return np.random.default_rng(1000 + i).standard_normal(n).astype(np.float32)
+
+
+def build(name="micro", **kw):
+    from ultravox_b200.config import preset
+    from ultravox_b200.model import UltravoxModel
+    from oracle import model as om
+    cfg = preset(name, **kw)
+    model = UltravoxModel(cfg, device="cuda").init_random_(seed=42)
+    return cfg, model, om.state_dict_fp32(model), om.shapes_from_config(cfg)
+
+
+def make_batch(cfg, lens_samples, text_pre=8, text_post=5, seed=7):
+    """One sequence per clip (B = len(lens)), layout of ref infer_test.py:97-109: 8 ids, placeholders, 5 ids."""
+    from oracle import logmel as ol
+    waves = [wave(i, n) for i, n in enumerate(lens_samples)]
+    padded, frames = ol.pad_batch(waves)
+    g = torch.Generator().manual_seed(seed)
+    tok = [int(-(-int(f) // 16)) for f in frames]
+    S = text_pre + max(tok) + text_post
+    ids = torch.randint(0, cfg.vocab_size, (len(waves), S), generator=g)
+    batch = dict(input_ids=ids, audio_token_start_idx=torch.tensor([text_pre] * len(waves)),
+                 audio_lens=torch.tensor([int(f) for f in frames]), audio_token_len=torch.tensor(tok, dtype=torch.int32),
+                 audio_batch_size=torch.ones(len(waves), dtype=torch.int64))
+    return padded, batch
+
+
+def test_state_dict_keys_match_reference_names():
+    cfg, model, sd, sh = build()
+    keys = set(sd)
+    for k in ("audio_tower.conv1.weight", "audio_tower.conv2.bias", "audio_tower.embed_positions.weight",
+              "audio_tower.layers.0.self_attn.q_proj.weight", "audio_tower.layers.0.self_attn.q_proj.bias",
+              "audio_tower.layers.1.self_attn.k_proj.weight", "audio_tower.layers.0.self_attn.out_proj.bias",
+              "audio_tower.layers.0.self_attn_layer_norm.weight", "audio_tower.layers.0.fc1.weight",
+              "audio_tower.layers.0.final_layer_norm.bias", "audio_tower.layer_norm.weight",
+              "multi_modal_projector.ln_pre.weight", "multi_modal_projector.linear_1.weight",
+              "multi_modal_projector.ln_mid.weight", "multi_modal_projector.linear_2.weight",
+              "language_model.model.embed_tokens.weight", "language_model.model.layers.0.self_attn.q_proj.weight",
+              "language_model.model.layers.1.self_attn.o_proj.weight", "language_model.model.layers.0.mlp.gate_proj.weight",
+              "language_model.model.layers.0.mlp.down_proj.weight", "language_model.model.layers.0.input_layernorm.weight",
+              "language_model.model.layers.0.post_attention_layernorm.weight", "language_model.model.norm.weight",
+              "language_model.lm_head.weight"):
+        assert k in keys, k
+    assert "audio_tower.layers.0.self_attn.k_proj.bias" not in keys
+    assert not any("qkv" in k or "gate_up" in k for k in keys)
+    # fused storage really is shared: writing through the named parameter changes the fused weight
+    l0 = model.language_model.model.layers[0].self_attn
+    l0.k_proj.weight.data.fill_(0.5)
+    nq = cfg.text_config.num_attention_heads * model.language_model.head_dim
+    assert float(l0.qkv_w[nq:nq + 4].float().mean()) == 0.5
+    assert set(model.diff_state_dict().keys()) == {k for k in keys if k.startswith("multi_modal_projector.")}
+
+
+@pytest.mark.parametrize("lens", [[16000], [16000 * 3, 16000 + 77, 5000]])
+def test_encoder_projector_stages(lens):
+    from oracle import logmel as ol, model as om
+    from ultravox_b200 import ops
+    cfg, model, sd, sh = build()
+    padded, batch = make_batch(cfg, lens)
+    mel_ref = torch.from_numpy(ol.log_mel(padded, sh.n_mels))
+    mel = ops.logmel(torch.from_numpy(padded).cuda(), sh.n_mels)
+    assert float((mel.cpu() - mel_ref).abs().max()) < 2e-3
+    # feed the oracle the bf16-rounded mel the GPU path actually consumes -> isolates encoder/projector error
+    mel_b = mel.cpu().to(torch.bfloat16).float()
+    enc_ref = om.whisper_encoder(sd, sh, mel_b, batch["audio_lens"])
+    tm = ops.mel_to_timemajor(mel)
+    enc = model.encode_audio(tm, batch["audio_lens"])
+    for i, n in enumerate(batch["audio_lens"].tolist()):
+        valid = (n - 1) // 2 + 1
+        assert rel(enc[i, :valid], enc_ref[i, :valid]) < 1.5e-2, i
+    aud_ref = om.projector(sd, sh, enc_ref)
+    aud = model.project_audio(enc)
+    for i, n in enumerate(batch["audio_token_len"].tolist()):
+        assert rel(aud[i, :n], aud_ref[i, :n]) < 2e-2, i
+
+
+def test_forward_matches_oracle_ragged_batch():
+    from oracle import logmel as ol, model as om
+    from ultravox_b200 import ops
+    cfg, model, sd, sh = build()
+    padded, batch = make_batch(cfg, [16000 * 2, 16000 + 77, 9000])
+    mel = ops.logmel(torch.from_numpy(padded).cuda(), sh.n_mels)
+    labels = batch["input_ids"].clone()
+    labels[:, :-5] = -100
+    out = model(audio_values=mel, labels=labels.cuda(), **{k: v.cuda() for k, v in batch.items()})
+    st = {}
+    ref_logits, ref_loss = om.forward(sd, sh, batch["input_ids"], mel.cpu().to(torch.bfloat16).float(),
+                                      batch["audio_token_start_idx"], batch["audio_lens"], batch["audio_token_len"],
+                                      batch["audio_batch_size"], labels=labels, stages=st)
+    assert out.logits.shape == ref_logits.shape and out.logits.dtype == torch.float32
+    r = rel(out.logits, ref_logits)
+    agree = float((out.logits.cpu().argmax(-1) == ref_logits.argmax(-1)).float().mean())
+    assert r < 3e-2 and agree > 0.9, (r, agree)
+    assert abs(float(out.loss) - float(ref_loss)) < 3e-2 * max(1.0, abs(float(ref_loss)))
+
+
+def test_splice_rows_bit_exact_and_text_rows_are_table_rows():
+    from oracle import logmel as ol
+    from ultravox_b200 import ops
+    cfg, model, sd, sh = build()
+    padded, batch = make_batch(cfg, [16000, 16000 * 2])
+    mel = ops.logmel(torch.from_numpy(padded).cuda(), sh.n_mels)
+    emb = model._prepare_audio_embeds(batch["input_ids"].cuda(), mel, batch["audio_token_start_idx"], batch["audio_lens"],
+                                      batch["audio_token_len"], batch["audio_batch_size"])
+    aud = model.project_audio(model.encode_audio(ops.mel_to_timemajor(mel), batch["audio_lens"]))
+    table = model.language_model.model.embed_tokens.weight
+    for b in range(2):
+        s, n = int(batch["audio_token_start_idx"][b]), int(batch["audio_token_len"][b])
+        assert torch.equal(emb[b, s:s + n], aud[b, :n])
+        ids = batch["input_ids"][b].cuda()
+        assert torch.equal(emb[b, :s], table[ids[:s]]) and torch.equal(emb[b, s + n:], table[ids[s + n:]])
+
+
+def test_text_only_and_right_padding_and_errors():
+    from oracle import model as om
+    cfg, model, sd, sh = build()
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(0, cfg.vocab_size, (2, 19), generator=g)
+    am = torch.ones(2, 19, dtype=torch.long)
+    am[1, 13:] = 0
+    out = model(ids.cuda(), attention_mask=am.cuda())
+    ref = om.llama_forward(sd, sh, sd["language_model.model.embed_tokens.weight"][ids], attention_mask=am)
+    assert rel(out.logits[0], ref[0]) < 2e-2 and rel(out.logits[1, :13], ref[1, :13]) < 2e-2
+    with pytest.raises(NotImplementedError):
+        model(ids.cuda(), attention_mask=am.flip(1).cuda())
+    with pytest.raises(AssertionError):
+        model(ids.cuda(), audio_values=torch.zeros(1, 80, 100).cuda())
+    with pytest.raises(ValueError):
+        model.encode_audio(torch.zeros(1, 3003, 80, dtype=torch.bfloat16, device="cuda"), None)
+
+
+def test_generate_greedy_matches_stepwise_oracle():
+    from oracle import logmel as ol, model as om
+    from ultravox_b200 import ops
+    cfg, model, sd, sh = build()
+    padded, batch = make_batch(cfg, [16000])
+    mel = ops.logmel(torch.from_numpy(padded).cuda(), sh.n_mels)
+    seq = model.generate(audio_values=mel, max_new_tokens=4, **{k: v.cuda() for k, v in batch.items()})
+    S = batch["input_ids"].shape[1]
+    assert seq.shape == (1, S + 4) and torch.equal(seq[:, :S].cpu(), batch["input_ids"])
+    # KV-cache decode must agree with a full re-forward of the CUDA path itself (same kernels, no cache)
+    emb = model._prepare_audio_embeds(batch["input_ids"].cuda(), mel, batch["audio_token_start_idx"], batch["audio_lens"],
+                                      batch["audio_token_len"], batch["audio_batch_size"])
+    table = model.language_model.model.embed_tokens.weight
+    cur = emb
+    for t in range(4):
+        hidden = model.llama_hidden(cur.clone())
+        tok = ops.argmax(ops.lm_head(hidden[:, -1, :], model.language_model.lm_head.weight))
+        assert int(tok) == int(seq[0, S + t]), t
+        cur = torch.cat([cur, table[tok][None]], dim=1)
+
+
+def test_prefill_engine_graph_matches_eager():
+    from ultravox_b200.engine import PrefillEngine
+    cfg, model, sd, sh = build()
+    padded, batch = make_batch(cfg, [16000])
+    eng = PrefillEngine(model, 16000, batch["input_ids"], batch["audio_token_start_idx"], batch["audio_token_len"],
+                        batch["audio_batch_size"])
+    assert eng.launches_per_step > 20
+    host = torch.from_numpy(padded).pin_memory()
+    tok = eng.run_e2e(host).clone()
+    from ultravox_b200 import ops
+    mel = ops.logmel(torch.from_numpy(padded).cuda(), sh.n_mels)
+    out = model(audio_values=mel, logits_to_keep=1, **{k: v.cuda() for k, v in batch.items()})
+    assert int(tok[0]) == int(out.logits.view(1, -1).argmax(-1))
+    assert torch.allclose(eng.logits, out.logits.view(1, -1), rtol=1e-5, atol=1e-5)
+    host2 = torch.from_numpy(wave(5, 16000)[None]).pin_memory()
+    t2 = eng.run_e2e(host2).clone()
+    eng.wave.copy_(host2)
+    assert int(eng.run()[0]) == int(t2[0])

@@ -262,7 +262,8 @@ class UltravoxModel(nn.Module):
         return self._rope
 
     # -- audio tower ---------------------------------------------------------------------------------
-    def encode_audio(self, x_tm: torch.Tensor, audio_lens: Optional[torch.Tensor]) -> torch.Tensor:
+    def encode_audio(self, x_tm: torch.Tensor, audio_lens: Optional[torch.Tensor],
+                     kv_len: Optional[torch.Tensor] = None) -> torch.Tensor:
         """x_tm [N, T+2, n_mels] bf16 guard-padded time-major mel -> encoder output [N, ceil(T/2), d]
         (``ModifiedWhisperEncoder.forward``, ref :865-994)."""
         at = self.audio_tower
@@ -279,9 +280,9 @@ class UltravoxModel(nn.Module):
         h = torch.empty(N, T2, d, dtype=BF16, device=dev)
         ops.conv1d_k3(h1, self._derived["conv2_w"], at.conv2.bias, 2, h, out_guard=False,
                       pos=at.embed_positions.weight[:T2])
-        kv_len = None
-        if audio_lens is not None:
-            kv_len = ((audio_lens.to(dev, torch.int64) - 1) // 2 + 1).to(torch.int32)
+        if kv_len is None and audio_lens is not None:
+            # hf _get_feat_extract_output_lengths (ref :915-917); computed where the tensor lives, then moved
+            kv_len = ((audio_lens.to(torch.int64) - 1) // 2 + 1).to(torch.int32).to(dev)
         block = int(self.config.audio_latency_block_size or 0)
         hd = d // H
         x = torch.empty_like(h)
