@@ -74,7 +74,8 @@ int uvx_mel_to_timemajor(const float* mel, int64_t N, int n_mels, int64_t T, voi
  * Output rows: c_row_map ? c_row_map[b*a_rows+m] (negative = drop) : b*c_batch_rows + m + c_row_offset.
  * R (optional) is addressed R + b*r_batch_stride + m*r_row_stride + n: residual stream (whisper/llama) or the
  * positional embedding added after GELU (ref :896-899, r_batch_stride = 0).
- * Requirements: K % 8 == 0, N % 64 == 0, strides % 8 == 0, 16-byte aligned bases.                       */
+ * Requirements: K % 8 == 0, N % 64 == 0, strides % 8 == 0, 16-byte aligned bases.
+ * Split-K partial sums are reduced in a fixed order by the last CTA to finish a tile: results are deterministic.  */
 enum { UVX_ACT_NONE = 0, UVX_ACT_GELU = 1 };
 enum { UVX_DT_BF16 = 0, UVX_DT_F32 = 1 };
 
@@ -93,9 +94,14 @@ typedef struct uvx_gemm_args {
   float alpha;
   int32_t act;              /* UVX_ACT_* */
   int32_t out_dtype;        /* UVX_DT_* */
+  void* workspace;          /* optional, 256-byte aligned: enables split-K when the tile count cannot fill the SMs.   */
+  int64_t workspace_bytes;  /* First ceil(4*tiles/256)*256 bytes are per-tile counters and must be ZERO on entry (the */
+                            /* kernel leaves them zero); the rest holds fp32 partial tiles (contents don't matter).   */
 } uvx_gemm_args;
 
 int uvx_gemm_bf16(const uvx_gemm_args* args, uvx_stream_t stream);
+/* tuning hook: force tile config MT*1000+BN (0 = heuristic) and split-K count (0 = heuristic) for later calls */
+int uvx_debug_gemm_override(int cfg, int splits);
 
 /* ---------------------------------------------------------------------------------------------
  * Row-wise normalisations (fp32 statistics, bf16 in/out).

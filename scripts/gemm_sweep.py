@@ -1,0 +1,64 @@
+"""GPU tuning sweep for uvx_gemm_bf16 (run under gpurun): every cfg2 GEMM shape x tile config x split-K, timed with CUDA
+events over rotating weight copies (> L2), with a correctness check per configuration."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from ultravox_b200 import ops, _lib
+
+lib = _lib.lib()
+SHAPES = [  # name, M, N, K
+    ("llm_qkv", 201, 6144, 4096), ("llm_o", 201, 4096, 4096), ("llm_gate_up", 201, 28672, 4096), ("llm_down", 201, 4096, 14336),
+    ("proj_l1", 188, 4096, 10240), ("proj_l2", 188, 4096, 2048),
+    ("enc_qkv", 1500, 3840, 1280), ("enc_out", 1500, 1280, 1280), ("enc_fc1", 1500, 5120, 1280), ("enc_fc2", 1500, 1280, 5120),
+    ("enc_conv2", 1500, 1280, 3840), ("dec_gate_up", 1, 28672, 4096), ("dec_down", 1, 4096, 14336), ("dec_qkv", 1, 6144, 4096),
+]
+only = sys.argv[1:] or None
+res = []
+for name, M, N, K in SHAPES:
+    if only and not any(o in name for o in only):
+        continue
+    wbytes = N * K * 2
+    copies = max(2, min(8, int(400e6 // wbytes) + 1))
+    Ws = [(torch.randn(N, K, device="cuda") * 0.05).bfloat16() for _ in range(copies)]
+    x = torch.randn(M, K, device="cuda").bfloat16()
+    ref = (x.float() @ Ws[0].float().T)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    cfgs = [(1064, 0), (1128, 0), (1256, 0)] if M > 256 or M <= 128 else [(2064, 0), (2128, 0), (2256, 0), (1128, 0), (1064, 0)]
+    cands = [(0, 0)]
+    for c, _ in cfgs:
+        for sp in (1, 2, 3, 4, 6, 8, 12, 16):
+            cands.append((c, sp))
+    best = None
+    for cfg, sp in cands:
+        lib.uvx_debug_gemm_override(cfg, sp)
+        try:
+            ops.linear(x, Ws[0], out=out)
+            torch.cuda.synchronize()
+        except Exception as e:
+            print(name, cfg, sp, "EXC", str(e)[:80]); continue
+        err = ((out.float() - ref).norm() / ref.norm()).item()
+        if err > 5e-3 or err != err:
+            print(f"{name} cfg={cfg} sp={sp} WRONG rel={err:.3e}"); continue
+        for i in range(3):
+            ops.linear(x, Ws[i % copies], out=out)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 20
+        e0.record()
+        for i in range(iters):
+            ops.linear(x, Ws[i % copies], out=out)
+        e1.record(); torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / iters
+        gbs = (wbytes + M * K * 2 + M * N * 2) / us / 1e3
+        tf = 2.0 * M * N * K / us / 1e6
+        r = dict(shape=name, M=M, N=N, K=K, cfg=cfg, splits=sp, us=round(us, 2), GBs=round(gbs, 1), TFs=round(tf, 1))
+        res.append(r)
+        if best is None or us < best["us"]:
+            best = r
+        if cfg == 0:
+            print("HEUR ", r)
+    print("BEST ", best, flush=True)
+    del Ws
+    torch.cuda.empty_cache()
+lib.uvx_debug_gemm_override(0, 0)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(res, open("gpurun_out/gemm_sweep.json", "w"))

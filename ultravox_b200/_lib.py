@@ -21,7 +21,7 @@ class GemmArgs(C.Structure):
                 ("a_batch_stride", c_i64), ("W", c_vp), ("N", c_i64), ("w_row_stride", c_i64), ("C", c_vp),
                 ("c_row_stride", c_i64), ("c_batch_rows", c_i64), ("c_row_offset", c_i64), ("c_row_map", c_vp),
                 ("bias", c_vp), ("R", c_vp), ("r_row_stride", c_i64), ("r_batch_stride", c_i64), ("alpha", c_f32),
-                ("act", c_i32), ("out_dtype", c_i32)]
+                ("act", c_i32), ("out_dtype", c_i32), ("workspace", c_vp), ("workspace_bytes", c_i64)]
 
 
 class AttnArgs(C.Structure):
@@ -42,6 +42,7 @@ SIGNATURES = {
     "uvx_debug_mel_filters": (C.c_int, [C.c_int, c_vp]),
     "uvx_mel_to_timemajor": (C.c_int, [c_vp, c_i64, C.c_int, c_i64, c_vp, c_vp]),
     "uvx_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), c_vp]),
+    "uvx_debug_gemm_override": (C.c_int, [C.c_int, C.c_int]),
     "uvx_layernorm": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_vp]),
     "uvx_rmsnorm": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_vp]),
     "uvx_attention": (C.c_int, [C.POINTER(AttnArgs), c_vp]),

@@ -2,16 +2,21 @@
 //
 //   C[row(b,m), n] = act(alpha * sum_k A[b,m,k] W[n,k] + bias[n]) + R[b,m,n]
 //
-// One CTA computes a 128 x BN output tile.  Warp roles (192 threads):
-//   warp 0      TMA producer: cp.async.bulk.tensor of the A box {64 k, 128 rows, 1 batch} and the W box
-//               {64 k, BN rows} into a kStages-deep 128B-swizzled shared-memory ring, mbarrier expect_tx.
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32 accumulate in
-//               TMEM); tcgen05.commit releases ring slots / signals the epilogue.
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns per warp, fused bias / GELU / residual / row
-//               remap, 16-byte stores.
-// A is described by a 3-D tensor map (k, row, batch) with caller-chosen strides, so overlapping rows
-// (implicit-GEMM conv over a time-major activation) and batch-strided inputs need no im2col copy; rows or
-// k beyond the tensor bounds are zero-filled by TMA, which is how M / K tails are handled.
+// Persistent, warp-specialised kernel: grid = min(#tiles, #SMs), each CTA walks tiles t = blockIdx.x + i*gridDim.x.
+// A CTA tile is (MT*128) x BN: MT in {1,2} row sub-tiles share one W tile (so at M <= 256 - the LLM prefill - every
+// weight byte is fetched from L2/HBM exactly once), BN in {64,128,256}.
+//   warp 0      TMA producer: cp.async.bulk.tensor of the A box {64 k, MT*128 rows, 1 batch} and the W box {64 k, BN
+//               rows} into a kStages-deep 128B-swizzled shared-memory ring (mbarrier expect_tx); runs ahead across tiles.
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32 accumulators in TMEM, MT
+//               accumulators per tile); tcgen05.commit releases ring slots and publishes finished accumulators.
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns per warp, fused bias / GELU / residual / row remap, 16-byte
+//               stores.  When MT*BN <= 256 the accumulators are double-buffered in TMEM, so the epilogue of tile i
+//               overlaps the main loop of tile i+1.
+// A is described by a 3-D tensor map (k, row, batch) with caller-chosen strides, so overlapping rows (implicit-GEMM
+// conv over a time-major activation) and batch-strided inputs need no im2col copy; rows or k beyond the tensor bounds
+// are zero-filled by TMA, which is how M / K tails are handled.
+#include <stdlib.h>
+
 #include "uvx_common.cuh"
 
 namespace uvx {
@@ -30,7 +35,11 @@ struct GemmParams {
   int64_t r_row_stride, r_batch_stride;
   float alpha;
   int act, out_f32;
-  int m_tiles;  // per batch
+  int m_tiles;  // per batch (of MT*128 rows)
+  int n_tiles, num_tiles;
+  int splits, kb_per_split;  // split-K: units = num_tiles * splits
+  float* ws_partial;         // [num_tiles * splits][MT*128][BN] fp32
+  int* ws_counter;           // [num_tiles], zero between launches (self-cleaning)
 };
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -110,50 +119,59 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-template <int BN>
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int MT, int BN>
 struct SmemLayout {
-  static constexpr int kABytes = kBM * kBK * 2;  // 16 KB
+  static constexpr int kABytes = MT * kBM * kBK * 2;  // 16 KB per row sub-tile
   static constexpr int kWBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kWBytes;
-  static constexpr int kStages = (BN <= 64) ? 4 : 3;  // <= 96 KB so that two CTAs share an SM
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kAcc = (MT * BN * 2 <= 512) ? 2 : 1;  // TMEM accumulator stages
+  static constexpr int kTmemCols = kAcc * MT * BN < 32 ? 32 : kAcc * MT * BN;
   static constexpr int kBarOff = kStages * kStageBytes;
   static constexpr int kTotal = kBarOff + 256 + 1024;  // barriers + slack for 1024-byte alignment
+  static_assert(kStages >= 2, "ring too shallow");
+  static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns must be a power of two <= 512");
 };
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int MT, int BN>
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<MT, BN>;
   constexpr int kStages = L::kStages;
+  constexpr int kAcc = L::kAcc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + L::kBarOff);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  uint64_t* tmem_empty = tmem_full + kAcc;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + kAcc);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m_total = p.m_tiles * (int)p.a_batch;
-  const int tile = blockIdx.x;
-  const int tm_idx = tile % tiles_m_total;   // consecutive CTAs share the W tile
-  const int tn_idx = tile / tiles_m_total;
-  const int b = tm_idx / p.m_tiles;
-  const int m0 = (tm_idx % p.m_tiles) * kBM;
-  const int n0 = tn_idx * BN;
   const int num_kb = (int)((p.K + kBK - 1) / kBK);
+  const int num_units = p.num_tiles * p.splits;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int a = 0; a < kAcc; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    constexpr uint32_t kCols = BN < 32 ? 32 : BN;
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kCols)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)L::kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -166,99 +184,204 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        uint8_t* sa = smem + s * L::kStageBytes;
-        uint8_t* sw = sa + L::kABytes;
-        mbar_expect_tx(&full_bar[s], (uint32_t)L::kStageBytes);
-        tma_load_3d(sa, &tmA, kb * kBK, m0, b, &full_bar[s]);
-        tma_load_2d(sw, &tmW, kb * kBK, n0, &full_bar[s]);
+      uint32_t it = 0;  // global k-block counter: the ring runs ahead across tile boundaries
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int tile = unit / p.splits, split = unit % p.splits;
+        const int tm_idx = tile % tiles_m_total;  // consecutive tiles share the W tile
+        const int tn_idx = tile / tiles_m_total;
+        const int b = tm_idx / p.m_tiles;
+        const int m0 = (tm_idx % p.m_tiles) * (MT * kBM);
+        const int n0 = tn_idx * BN;
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(num_kb, kb_begin + p.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* sa = smem + s * L::kStageBytes;
+          mbar_expect_tx(&full_bar[s], (uint32_t)L::kStageBytes);
+          tma_load_3d(sa, &tmA, kb * kBK, m0, b, &full_bar[s]);
+          tma_load_2d(sa + L::kABytes, &tmW, kb * kBK, n0, &full_bar[s]);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, tcount = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++tcount) {
+        const int split = unit % p.splits;
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(num_kb, kb_begin + p.kb_per_split);
+        const uint32_t acc = tcount % kAcc;
+        const uint32_t aph = (tcount / kAcc) & 1u;
+        mbar_wait(&tmem_empty[acc], aph ^ 1u);  // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
-        const uint64_t da = make_smem_desc(sa);
-        const uint64_t dw = make_smem_desc(sa + L::kABytes);
+        const uint32_t d_tmem = tmem_base + acc * (MT * BN);
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
+          const uint64_t dw = make_smem_desc(sa + L::kABytes);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-          umma_f16(tmem_base, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t da = make_smem_desc(sa + mt * (kBM * kBK * 2));
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+              umma_f16(d_tmem + mt * BN, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+        umma_commit(&tmem_full[acc]);  // accumulators of this tile complete
       }
-      umma_commit(tmem_full);  // accumulator complete
     }
   } else {
     // ---- epilogue -------------------------------------------------------------------------
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    const int64_t m = (int64_t)m0 + row;
-    const bool row_ok = m < p.a_rows;
-    int64_t orow = -1;
-    if (row_ok) {
-      orow = p.c_row_map ? (int64_t)p.c_row_map[(int64_t)b * p.a_rows + m] : (int64_t)b * p.c_batch_rows + m + p.c_row_offset;
-    }
-    const bf16* rrow = (p.R && row_ok) ? p.R + (int64_t)b * p.r_batch_stride + m * p.r_row_stride : nullptr;
+    uint32_t* flag = tmem_slot + 1;
+    uint32_t tcount = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++tcount) {
+      const int tile = unit / p.splits, split = unit % p.splits;
+      const int tm_idx = tile % tiles_m_total;
+      const int tn_idx = tile / tiles_m_total;
+      const int b = tm_idx / p.m_tiles;
+      const int m0 = (tm_idx % p.m_tiles) * (MT * kBM);
+      const int n0 = tn_idx * BN;
+      const uint32_t acc = tcount % kAcc;
+      const uint32_t aph = (tcount / kAcc) & 1u;
+      mbar_wait(&tmem_full[acc], aph);
+      tc_fence_after();
+      const bool direct = p.splits == 1;
+      if (!direct) {
+        // split-K: park the raw fp32 partial tile in the workspace (rows past the matrix are skipped)
+        float* part = p.ws_partial + (size_t)unit * (MT * kBM) * BN;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t raw[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
-      tmem_ld_wait();
-      if (orow >= 0) {
-        const int64_t n = (int64_t)n0 + c * 32;
-        float v[32];
+        for (int mt = 0; mt < MT; ++mt) {
+          if ((int64_t)m0 + mt * kBM + q * 32 >= p.a_rows) continue;
+          const int r = mt * kBM + q * 32 + lane;
+          const bool row_ok = (int64_t)m0 + r < p.a_rows;
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) {
+            uint32_t raw[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * BN) + (uint32_t)(mt * BN + c * 32), raw);
+            tmem_ld_wait();
+            if (row_ok) {
+              uint4* dst = reinterpret_cast<uint4*>(part + (size_t)r * BN + c * 32);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
-        if (p.bias) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float t[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(p.bias + n + g * 8), t);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[g * 8 + i] += t[i];
+              for (int g = 0; g < 8; ++g) dst[g] = make_uint4(raw[4 * g], raw[4 * g + 1], raw[4 * g + 2], raw[4 * g + 3]);
+            }
           }
         }
-        if (p.act == UVX_ACT_GELU) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);  // accumulator stage is free again
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) *flag = (atomicAdd(p.ws_counter + tile, 1) == p.splits - 1) ? 1u : 0u;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const bool last = *flag != 0u;
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // flag may be rewritten by the next unit only after everyone read it
+        if (!last) continue;
+        __threadfence();
+      }
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        const int row = q * 32 + lane;
+        const int64_t m = (int64_t)m0 + mt * kBM + row;
+        const bool row_ok = m < p.a_rows;
+        int64_t orow = -1;
+        if (row_ok) {
+          orow = p.c_row_map ? (int64_t)p.c_row_map[(int64_t)b * p.a_rows + m]
+                             : (int64_t)b * p.c_batch_rows + m + p.c_row_offset;
         }
-        if (rrow) {
+        const bf16* rrow = (p.R && row_ok) ? p.R + (int64_t)b * p.r_batch_stride + m * p.r_row_stride : nullptr;
+        // skip sub-tiles that are entirely out of range (warp-uniform)
+        if ((int64_t)m0 + mt * kBM + q * 32 >= p.a_rows) continue;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          float v[32];
+          if (direct) {
+            uint32_t raw[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * BN) + (uint32_t)(mt * BN + c * 32), raw);
+            tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float t[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(rrow + n + g * 8), t);
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+          } else {
+            // last-arriving CTA of this tile: sum the partials in split order (deterministic)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[g * 8 + i] += t[i];
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            if (row_ok) {
+              for (int sidx = 0; sidx < p.splits; ++sidx) {
+                const float4* src = reinterpret_cast<const float4*>(
+                    p.ws_partial + ((size_t)(tile * p.splits + sidx) * (MT * kBM) + mt * kBM + row) * BN + c * 32);
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                  const float4 t = __ldcg(src + g);
+                  v[4 * g] += t.x;
+                  v[4 * g + 1] += t.y;
+                  v[4 * g + 2] += t.z;
+                  v[4 * g + 3] += t.w;
+                }
+              }
+            }
+          }
+          if (orow >= 0) {
+            const int64_t n = (int64_t)n0 + c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+            if (p.bias) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float t[8];
+                unpack8(*reinterpret_cast<const bf16x8*>(p.bias + n + g * 8), t);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[g * 8 + i] += t[i];
+              }
+            }
+            if (p.act == UVX_ACT_GELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+            }
+            if (rrow) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float t[8];
+                unpack8(*reinterpret_cast<const bf16x8*>(rrow + n + g * 8), t);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[g * 8 + i] += t[i];
+              }
+            }
+            if (p.out_f32) {
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + orow * p.c_row_stride + n);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+            } else {
+              bf16x8* dst = reinterpret_cast<bf16x8*>(reinterpret_cast<bf16*>(p.C) + orow * p.c_row_stride + n);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) dst[g] = pack8(v + g * 8);
+            }
           }
         }
-        if (p.out_f32) {
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + orow * p.c_row_stride + n);
-#pragma unroll
-          for (int g = 0; g < 8; ++g) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-        } else {
-          bf16x8* dst = reinterpret_cast<bf16x8*>(reinterpret_cast<bf16*>(p.C) + orow * p.c_row_stride + n);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) dst[g] = pack8(v + g * 8);
-        }
+      }
+      if (direct) {
+        // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator stage back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      } else if (threadIdx.x == 64) {
+        p.ws_counter[tile] = 0;  // self-cleaning: the next launch finds zeros
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    constexpr uint32_t kCols = BN < 32 ? 32 : BN;
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L::kTmemCols)
+                 : "memory");
   }
 }
 
@@ -305,14 +428,25 @@ static int encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_
   return UVX_OK;
 }
 
-template <int BN>
-static int launch_gemm(const uvx_gemm_args* a, cudaStream_t stream) {
-  using L = SmemLayout<BN>;
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int MT, int BN>
+static int launch_gemm(const uvx_gemm_args* a, int splits, cudaStream_t stream) {
+  using L = SmemLayout<MT, BN>;
   CUtensorMap tmA, tmW;
   {
     uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->a_rows, (uint64_t)a->a_batch};
     uint64_t st[2] = {(uint64_t)a->a_row_stride * 2, (uint64_t)(a->a_batch > 1 ? a->a_batch_stride : a->a_row_stride) * 2};
-    uint32_t box[3] = {kBK, kBM, 1};
+    uint32_t box[3] = {kBK, (uint32_t)(MT * kBM), 1};
     int rc = encode_map(&tmA, a->A, 3, dims, st, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (rc) return rc;
   }
@@ -340,22 +474,82 @@ static int launch_gemm(const uvx_gemm_args* a, cudaStream_t stream) {
   p.alpha = a->alpha;
   p.act = a->act;
   p.out_f32 = a->out_dtype == UVX_DT_F32;
-  p.m_tiles = (int)((a->a_rows + kBM - 1) / kBM);
+  p.m_tiles = (int)((a->a_rows + MT * kBM - 1) / (MT * kBM));
+  p.n_tiles = (int)(a->N / BN);
+  p.num_tiles = p.m_tiles * (int)a->a_batch * p.n_tiles;
+  const int num_kb = (int)((a->K + kBK - 1) / kBK);
+  // split-K needs the caller's workspace: counters first (4 B per tile, 256-byte aligned), then fp32 partial tiles
+  const size_t counter_bytes = (((size_t)p.num_tiles * 4) + 255) / 256 * 256;
+  while (splits > 1 && (!a->workspace || counter_bytes + (size_t)p.num_tiles * splits * MT * kBM * BN * 4 > (size_t)a->workspace_bytes))
+    --splits;
+  if (splits > num_kb) splits = num_kb;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = (num_kb + splits - 1) / splits;
+  p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
+  p.ws_counter = (int*)a->workspace;
+  p.ws_partial = (float*)((uint8_t*)a->workspace + counter_bytes);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(gemm_tc_kernel<%d>, smem %d): %s", BN, L::kTotal, cudaGetErrorString(e));
+      set_error("cudaFuncSetAttribute(gemm_tc_kernel<%d,%d>, smem %d): %s", MT, BN, L::kTotal, cudaGetErrorString(e));
       return UVX_ERR_CUDA;
     }
     attr_set = true;
   }
-  const int64_t grid = (int64_t)p.m_tiles * a->a_batch * (a->N / BN);
-  gemm_tc_kernel<BN><<<(unsigned)grid, kThreads, L::kTotal, stream>>>(tmA, tmW, p);
+  const int units = p.num_tiles * p.splits;
+  const int grid = units < num_sms() ? units : num_sms();
+  gemm_tc_kernel<MT, BN><<<(unsigned)grid, kThreads, L::kTotal, stream>>>(tmA, tmW, p);
   return check_launch("gemm_tc_kernel");
 }
 
 }  // namespace uvx
+
+// Tile / split selection.  cfg = MT*1000 + BN; UVX_GEMM_CFG / UVX_GEMM_SPLITS (env, tuning only) override the heuristic.
+static int forced = -1, forced_splits = -1;
+
+// tuning hook (scripts/gemm_sweep.py): force a tile config (MT*1000+BN, 0 = heuristic) and a split count (0 = heuristic)
+extern "C" int uvx_debug_gemm_override(int cfg, int splits) {
+  forced = cfg;
+  forced_splits = splits;
+  return UVX_OK;
+}
+
+static void pick_cfg(int64_t rows, int64_t batch, int64_t N, int64_t K, int* cfg, int* splits) {
+  if (forced < 0) {
+    const char* e = getenv("UVX_GEMM_CFG");
+    forced = e ? atoi(e) : 0;
+    const char* s = getenv("UVX_GEMM_SPLITS");
+    forced_splits = s ? atoi(s) : 0;
+  }
+  const int sms = 148;
+  const int num_kb = (int)((K + 63) / 64);
+  int mt, bn;
+  if (rows > 128 && rows <= 256 && batch == 1) {
+    // weight-streaming regime (LLM prefill at B=1, projector): one CTA tile spans every row, W is read once
+    mt = 2;
+    bn = (N % 256 == 0 && N / 256 >= sms / 2) ? 256 : (N % 128 == 0 ? 128 : 64);
+  } else {
+    mt = 1;
+    const int64_t m_tiles = (rows + 127) / 128 * batch;
+    bn = (N % 128 == 0 && m_tiles * (N / 128) >= sms / 2) ? 128 : 64;
+  }
+  if (forced > 0 && N % (forced % 1000) == 0) {
+    mt = forced / 1000;
+    bn = forced % 1000;
+  }
+  const int64_t tiles = ((rows + mt * 128 - 1) / (mt * 128)) * batch * (N / bn);
+  int sp = 1;
+  if (tiles * 2 <= sms && num_kb >= 16) {  // too few tiles to occupy the SMs: split K (>= 8 k-blocks per split)
+    sp = (int)(sms / tiles);
+    if (sp > num_kb / 8) sp = num_kb / 8;
+    if (sp > 16) sp = 16;
+    if (sp < 1) sp = 1;
+  }
+  if (forced_splits > 0) sp = forced_splits;
+  *cfg = mt * 1000 + bn;
+  *splits = sp;
+}
 
 extern "C" int uvx_gemm_bf16(const uvx_gemm_args* a, uvx_stream_t stream_) {
   using namespace uvx;
@@ -371,8 +565,16 @@ extern "C" int uvx_gemm_bf16(const uvx_gemm_args* a, uvx_stream_t stream_) {
   UVX_REQUIRE(a->c_row_stride % 8 == 0 && (!a->R || (a->r_row_stride % 8 == 0 && a->r_batch_stride % 8 == 0)),
               "uvx_gemm_bf16: output / residual strides must be multiples of 8");
   UVX_REQUIRE(a->a_rows < (1ll << 31) && a->K < (1ll << 31) && a->N < (1ll << 31), "uvx_gemm_bf16: dimension too large");
-  // Tile width: keep >= ~1 wave of CTAs on 148 SMs when M is small, otherwise the widest tile.
-  const int64_t m_tiles = (a->a_rows + kBM - 1) / kBM * a->a_batch;
-  if (a->N % 128 == 0 && m_tiles * (a->N / 128) >= 120) return launch_gemm<128>(a, stream);
-  return launch_gemm<64>(a, stream);
+  UVX_REQUIRE(!a->workspace || (uintptr_t)a->workspace % 256 == 0, "uvx_gemm_bf16: workspace must be 256-byte aligned");
+  int cfg, splits;
+  pick_cfg(a->a_rows, a->a_batch, a->N, a->K, &cfg, &splits);
+  switch (cfg) {
+    case 1064: return launch_gemm<1, 64>(a, splits, stream);
+    case 1128: return launch_gemm<1, 128>(a, splits, stream);
+    case 1256: return launch_gemm<1, 256>(a, splits, stream);
+    case 2064: return launch_gemm<2, 64>(a, splits, stream);
+    case 2128: return launch_gemm<2, 128>(a, splits, stream);
+    case 2256: return launch_gemm<2, 256>(a, splits, stream);
+    default: return launch_gemm<1, 64>(a, splits, stream);
+  }
 }

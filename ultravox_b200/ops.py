@@ -69,6 +69,20 @@ def mel_to_timemajor(audio_values: torch.Tensor, out: Optional[torch.Tensor] = N
 
 
 # ------------------------------------------------------------------------------------------ GEMM
+_GEMM_WS: dict = {}
+GEMM_WS_BYTES = 160 << 20
+
+
+def gemm_workspace(device) -> torch.Tensor:
+    """Per-device split-K workspace (counters must start at zero; the kernel keeps them zero)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    ws = _GEMM_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(GEMM_WS_BYTES, dtype=torch.uint8, device=torch.device("cuda", key))
+        _GEMM_WS[key] = ws
+    return ws
+
+
 def gemm_raw(A_ptr: int, a_batch: int, a_rows: int, K: int, a_row_stride: int, a_batch_stride: int,
              W: torch.Tensor, C_t: torch.Tensor, c_row_stride: int, c_batch_rows: int, c_row_offset: int = 0,
              c_row_map: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
@@ -84,6 +98,8 @@ def gemm_raw(A_ptr: int, a_batch: int, a_rows: int, K: int, a_row_stride: int, a
     a.r_row_stride, a.r_batch_stride = r_row_stride, r_batch_stride
     a.alpha, a.act = alpha, act
     a.out_dtype = 1 if C_t.dtype == torch.float32 else 0
+    ws = gemm_workspace(C_t.device)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     check(lib().uvx_gemm_bf16(C.byref(a), _stream()), "uvx_gemm_bf16")
 
 
