@@ -75,7 +75,7 @@ int uvx_mel_to_timemajor(const float* mel, int64_t N, int n_mels, int64_t T, voi
  * R (optional) is addressed R + b*r_batch_stride + m*r_row_stride + n: residual stream (whisper/llama) or the
  * positional embedding added after GELU (ref :896-899, r_batch_stride = 0).
  * Requirements: K % 8 == 0, N % 64 == 0, strides % 8 == 0, 16-byte aligned bases.
- * Split-K partial sums are reduced in a fixed order by the last CTA to finish a tile: results are deterministic.  */
+ * Split-K partial sums are reduced in a fixed order by a second kernel: results are deterministic.  */
 enum { UVX_ACT_NONE = 0, UVX_ACT_GELU = 1 };
 enum { UVX_DT_BF16 = 0, UVX_DT_F32 = 1 };
 
@@ -94,9 +94,8 @@ typedef struct uvx_gemm_args {
   float alpha;
   int32_t act;              /* UVX_ACT_* */
   int32_t out_dtype;        /* UVX_DT_* */
-  void* workspace;          /* optional, 256-byte aligned: enables split-K when the tile count cannot fill the SMs.   */
-  int64_t workspace_bytes;  /* First ceil(4*tiles/256)*256 bytes are per-tile counters and must be ZERO on entry (the */
-                            /* kernel leaves them zero); the rest holds fp32 partial tiles (contents don't matter).   */
+  void* workspace;          /* optional, 256-byte aligned scratch: enables split-K when the tile count cannot fill   */
+  int64_t workspace_bytes;  /* the SMs (fp32 partial sums [splits][rows][N]; contents on entry do not matter).       */
 } uvx_gemm_args;
 
 int uvx_gemm_bf16(const uvx_gemm_args* args, uvx_stream_t stream);
@@ -133,6 +132,7 @@ typedef struct uvx_attn_args {
   int32_t causal;                   /* query i sees keys j <= i + (Skv - Sq) */
   int32_t block;                    /* >0: block-causal, query i sees keys j with j/block <= i/block */
   float scale;
+  float* lse;                       /* optional [B, Hq, Sq] fp32: log-sum-exp of the scaled scores (training) */
 } uvx_attn_args;
 int uvx_attention(const uvx_attn_args* args, uvx_stream_t stream);
 
@@ -172,9 +172,44 @@ int uvx_argmax(const float* logits, int64_t B, int64_t V, int64_t* out_idx, uvx_
 /* Shifted causal-LM cross entropy (hf:loss/loss_utils.py:28-67; called through LlamaForCausalLM.forward(labels=)
  * from ref:ultravox/model/ultravox_model.py:328-334).  logits [B*S, V] fp32 (row_stride elements), labels [B, S]
  * un-shifted (the shift and the ignore_index padding happen inside).  row_loss/row_lse [B*S] are kept for the
- * backward; out_loss2[0] = mean loss over non-ignored positions, out_loss2[1] = their count.              */
+ * backward; out_loss2[0] = mean loss over non-ignored positions, out_loss2[1] = their count.  shift = 1 is the
+ * HF convention above; shift = 0 takes labels[row] as is (rows pre-gathered by the caller).               */
 int uvx_ce_loss(const float* logits, int64_t row_stride, const int64_t* labels, int64_t B, int64_t S, int64_t V,
-                int64_t ignore_index, float* row_loss, float* row_lse, float* out_loss2, uvx_stream_t stream);
+                int64_t ignore_index, int shift, float* row_loss, float* row_lse, float* out_loss2, uvx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a14: adapter backward (encoder + LLM frozen: ref apply_lora r=0, ultravox_model.py:690-709).  These are the
+ * pieces torch.autograd runs for the reference between `loss.backward()` and the projector weights; dense
+ * contractions reuse uvx_gemm_bf16 (dgrad against pre-transposed weights, wgrad against transposed activations). */
+int uvx_rope_bwd(void* dqkv, int64_t rows, int64_t row_stride, int Hq, int Hkv, int D, const float* cos_tab,
+                 const float* sin_tab, const int32_t* positions, int64_t rows_per_seq, int64_t pos_offset,
+                 uvx_stream_t stream);
+/* dQ/dK/dV of uvx_attention; `a` is the forward's argument struct (with a->lse filled by the forward), o the
+ * forward output, dout its gradient (same strides as o); delta_ws is [B, Hq, Sq] fp32 scratch.               */
+int uvx_attention_bwd(const uvx_attn_args* a, const void* o, const void* dout, void* dq, void* dk, void* dv,
+                      int64_t dq_rs, int64_t dq_bs, int64_t dk_rs, int64_t dk_bs, int64_t dv_rs, int64_t dv_bs,
+                      float* delta_ws, uvx_stream_t stream);
+int uvx_transpose_bf16(const void* in, int64_t rows, int64_t cols, int64_t in_row_stride, void* out,
+                       int64_t out_row_stride, uvx_stream_t stream);
+/* dx = dres + d(rmsnorm)/dx . dy (dx may be NULL), dw[cols] += sum_rows dy * xhat (fp32, dw may be NULL);
+ * group_* as in uvx_rmsnorm (stack mode: no dx).                                                              */
+int uvx_rmsnorm_bwd(const void* dy, const void* x, const void* w, const void* dres, void* dx, float* dw,
+                    int64_t rows, int64_t cols, int64_t x_row_stride, int64_t group_rows, int64_t group_stride,
+                    int64_t valid_elems, float eps, uvx_stream_t stream);
+int uvx_swiglu_bwd(const void* x, const void* dout, void* dx, int64_t rows, int64_t H, int64_t x_row_stride,
+                   int gate_first, uvx_stream_t stream);
+/* dlogits (bf16 [B*S, V]) of uvx_ce_loss: (softmax - onehot) * grad_scale / count on valid rows, 0 elsewhere. */
+int uvx_ce_bwd(const float* logits, int64_t row_stride, const int64_t* labels, int64_t B, int64_t S, int64_t V,
+               int64_t ignore_index, int shift, const float* row_lse, const float* loss2, float grad_scale,
+               void* dlogits, uvx_stream_t stream);
+/* out[i, :] = idx[i] >= 0 ? src[idx[i], :] : 0  (gradient of the splice: rows of d(inputs_embeds) -> d(audio_embeds)) */
+int uvx_gather_rows(const void* src, const int32_t* idx, int64_t rows, int64_t d, void* out, uvx_stream_t stream);
+/* inverse of the splice table: inv[audio_row] = position (b*S+s) it was spliced to, or -1                     */
+int uvx_splice_inverse(const int32_t* src, int64_t n_pos, int32_t* inv, int64_t n_audio_rows, uvx_stream_t stream);
+/* AdamW on bf16 parameters with fp32 gradient / moments (torch.optim.AdamW semantics, ref meta_config.yaml:27) */
+int uvx_adamw(void* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+              float weight_decay, int64_t step, float grad_scale, uvx_stream_t stream);
+int uvx_cast_f32_bf16(const float* in, void* out, int64_t n, uvx_stream_t stream);
 
 #ifdef __cplusplus
 }

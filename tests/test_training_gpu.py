@@ -1,0 +1,200 @@
+"""Adapter-training path: backward kernels per op, then the full forward+backward against
+torch.autograd on the fp32 CPU oracle with the same weights, then one AdamW step."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(BF).cuda()
+
+
+def test_transpose_and_gather():
+    from ultravox_b200 import ops
+    x = rnd(203, 130, seed=1)
+    t = ops.transpose(x)
+    assert t.shape == (130, 208) and torch.equal(t[:, :203], x.T) and torch.count_nonzero(t[:, 203:]) == 0
+    idx = torch.tensor([5, -1, 0, 202, 7], dtype=torch.int32).cuda()
+    g = ops.gather_rows(rnd(203, 128, seed=2), idx)
+    src = rnd(203, 128, seed=2)
+    assert torch.equal(g[0], src[5]) and torch.count_nonzero(g[1]) == 0 and torch.equal(g[3], src[202])
+
+
+@pytest.mark.parametrize("rows,cols", [(37, 256), (201, 4096)])
+def test_rmsnorm_bwd(rows, cols):
+    from ultravox_b200 import ops
+    x, w, dy, dres = rnd(rows, cols, seed=1), rnd(cols, seed=2), rnd(rows, cols, seed=3), rnd(rows, cols, seed=4)
+    xf = x.float().requires_grad_(True)
+    wf = w.float().requires_grad_(True)
+    y = wf * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5))
+    y.backward(dy.float())
+    dw = torch.zeros(cols, device="cuda")
+    dx = ops.rmsnorm_bwd(dy, x, w, 1e-5, dres=dres, dw=dw)
+    assert rel(dx, (xf.grad + dres.float()).to(BF)) < 2e-3
+    assert rel(dw, wf.grad) < 1e-3
+
+
+def test_stack_rmsnorm_bwd_weight_grad():
+    from ultravox_b200 import ops
+    T, C = 50, 128
+    enc, w = rnd(2, T, C, seed=1), rnd(8 * C, seed=2)
+    rows = (T + 7) // 8
+    dy = rnd(2 * rows, 8 * C, seed=3)
+    st = F.pad(enc.float(), (0, 0, 0, rows * 8 - T)).reshape(2 * rows, 8 * C)
+    wf = w.float().requires_grad_(True)
+    (wf * (st * torch.rsqrt(st.pow(2).mean(-1, keepdim=True) + 1e-6))).backward(dy.float())
+    dw = torch.zeros(8 * C, device="cuda")
+    ops.rmsnorm_bwd(dy, enc, w, 1e-6, want_dx=False, dw=dw, stack=(rows, T * C))
+    assert rel(dw, wf.grad) < 1e-3
+
+
+@pytest.mark.parametrize("gate_first", [False, True])
+def test_swiglu_bwd(gate_first):
+    from ultravox_b200 import ops
+    x, d = rnd(77, 512, seed=1), rnd(77, 256, seed=2)
+    xf = x.float().requires_grad_(True)
+    a, g = xf.chunk(2, -1)
+    out = F.silu(a) * g if gate_first else F.silu(g) * a
+    out.backward(d.float())
+    assert rel(ops.swiglu_bwd(x, d, gate_first), xf.grad.to(BF)) < 2e-3
+
+
+@pytest.mark.parametrize("B,Hq,Hkv,S,D", [(2, 4, 2, 77, 64), (1, 8, 2, 201, 128), (2, 2, 2, 130, 64)])
+def test_attention_bwd(B, Hq, Hkv, S, D):
+    from ultravox_b200 import ops
+    W = (Hq + 2 * Hkv) * D
+    qkv = rnd(B * S, W, seed=3)
+    dout = rnd(B * S, Hq * D, seed=4)
+    out = torch.empty(B * S, Hq * D, dtype=BF, device="cuda")
+    lse = torch.empty(B * Hq * S, dtype=torch.float32, device="cuda")
+    ops.attention_fused_qkv_train(qkv, B, S, Hq, Hkv, D, D ** -0.5, True, out, lse)
+    dqkv = ops.attention_fused_qkv_bwd(qkv, out, dout, lse, B, S, Hq, Hkv, D, D ** -0.5, True)
+    t = qkv.float().view(B, S, Hq + 2 * Hkv, D).requires_grad_(True)
+    q, k, v = t[:, :, :Hq].transpose(1, 2), t[:, :, Hq:Hq + Hkv].transpose(1, 2), t[:, :, Hq + Hkv:].transpose(1, 2)
+    k2, v2 = k.repeat_interleave(Hq // Hkv, 1), v.repeat_interleave(Hq // Hkv, 1)
+    s = (q @ k2.transpose(-1, -2)) * D ** -0.5
+    mask = torch.triu(torch.ones(S, S, dtype=torch.bool, device="cuda"), 1)
+    ref = torch.softmax(s.masked_fill(mask, float("-inf")), -1) @ v2
+    ref_o = ref.transpose(1, 2).reshape(B * S, Hq * D)
+    assert rel(out, ref_o.to(BF)) < 3e-3
+    lse_ref = torch.logsumexp(s.masked_fill(mask, float("-inf")), -1)
+    assert torch.allclose(lse.view(B, Hq, S), lse_ref, atol=2e-3, rtol=1e-3)
+    ref_o.backward(dout.float())
+    g = t.grad.view(B * S, W)
+    qd = Hq * D
+    assert rel(dqkv[:, :qd], g[:, :qd]) < 1e-2           # dQ
+    assert rel(dqkv[:, qd:qd + Hkv * D], g[:, qd:qd + Hkv * D]) < 1e-2   # dK
+    assert rel(dqkv[:, qd + Hkv * D:], g[:, qd + Hkv * D:]) < 1e-2       # dV
+
+
+def test_rope_bwd_is_transpose_of_forward():
+    from ultravox_b200 import ops
+    Hq, Hkv, D, S = 4, 2, 64, 33
+    inv = ops.llama3_inv_freq(D, 500000.0, None)
+    cos, sin = ops.rope_tables(inv, 64, "cuda")
+    x, y = rnd(S, (Hq + 2 * Hkv) * D, seed=1), rnd(S, (Hq + 2 * Hkv) * D, seed=2)
+    fx = ops.rope_(x.clone(), Hq, Hkv, D, cos, sin, rows_per_seq=S).float()
+    bty = ops.rope_bwd_(y.clone(), Hq, Hkv, D, cos, sin, rows_per_seq=S).float()
+    lhs, rhs = (fx * y.float()).sum(), (x.float() * bty).sum()      # <R x, y> == <x, R^T y>
+    assert abs(float(lhs - rhs)) < 2e-2 * abs(float(lhs))
+
+
+def test_ce_loss_and_bwd():
+    from ultravox_b200.losses import causal_lm_loss, causal_lm_loss_bwd
+    B, S, V = 2, 9, 1000
+    lg = torch.randn(B, S, V, generator=torch.Generator().manual_seed(1)).cuda()
+    lab = torch.randint(0, V, (B, S), generator=torch.Generator().manual_seed(2)).cuda()
+    lab[:, :4] = -100
+    lf = lg.clone().requires_grad_(True)
+    ref = F.cross_entropy(lf[:, :-1].reshape(-1, V), lab[:, 1:].reshape(-1), ignore_index=-100)
+    ref.backward()
+    keep = {}
+    loss = causal_lm_loss(lg, lab, keep=keep)
+    assert abs(float(loss) - float(ref)) < 1e-5
+    assert rel(causal_lm_loss_bwd(keep).view(B, S, V), lf.grad.to(BF)) < 1e-3
+
+
+def _setup(lens, seed=7):
+    from oracle import logmel as ol, model as om
+    from ultravox_b200.config import preset
+    from ultravox_b200.model import UltravoxModel
+    cfg = preset("micro")
+    model = UltravoxModel(cfg, device="cuda").init_random_(seed=42)
+    with torch.no_grad():   # norm weights away from their constant init so their gradients are exercised
+        for n, p in model.multi_modal_projector.named_parameters():
+            if "ln_" in n:
+                p.add_(torch.randn(p.shape, generator=torch.Generator().manual_seed(3)).to(p.device, p.dtype) * 0.1)
+    waves = [np.random.default_rng(1000 + i).standard_normal(n).astype(np.float32) for i, n in enumerate(lens)]
+    padded, frames = ol.pad_batch(waves)
+    g = torch.Generator().manual_seed(seed)
+    tok = [int(-(-int(f) // 16)) for f in frames]
+    S = 8 + max(tok) + 5
+    ids = torch.randint(0, cfg.vocab_size, (len(waves), S), generator=g)
+    labels = ids.clone()
+    labels[:, :-5] = -100
+    batch = dict(input_ids=ids, audio_token_start_idx=torch.tensor([8] * len(waves)),
+                 audio_lens=torch.tensor([int(f) for f in frames]), audio_token_len=torch.tensor(tok, dtype=torch.int32),
+                 audio_batch_size=torch.ones(len(waves), dtype=torch.int64), labels=labels)
+    return cfg, model, padded, batch
+
+
+def test_adapter_backward_matches_oracle_autograd():
+    from oracle import model as om
+    from ultravox_b200 import ops
+    from ultravox_b200.training import AdapterTrainer
+    cfg, model, padded, batch = _setup([16000 * 2, 16000 + 77])
+    mel = ops.logmel(torch.from_numpy(padded).cuda(), cfg.audio_config.num_mel_bins)
+    tr = AdapterTrainer(model, lr=1e-3)
+    loss = tr.forward_backward(audio_values=mel, **batch)
+    sd, sh = om.state_dict_fp32(model), om.shapes_from_config(cfg)
+    names = ["multi_modal_projector." + n + ".weight" for n in ("ln_pre", "linear_1", "ln_mid", "linear_2")]
+    for n in names:
+        sd[n] = sd[n].clone().requires_grad_(True)
+    _, ref_loss = om.forward(sd, sh, batch["input_ids"], mel.cpu().to(BF).float(), batch["audio_token_start_idx"],
+                             batch["audio_lens"], batch["audio_token_len"], batch["audio_batch_size"], labels=batch["labels"])
+    ref_loss.backward()
+    assert abs(float(loss) - float(ref_loss)) < 3e-2 * max(1.0, abs(float(ref_loss)))
+    for n in names:
+        got = tr.grad_view(n.split(".")[1])
+        r = rel(got, sd[n].grad)
+        cos = float(F.cosine_similarity(got.float().cpu().flatten(), sd[n].grad.flatten(), dim=0))
+        assert r < 8e-2 and cos > 0.995, (n, r, cos)   # bf16 activations end to end vs fp32 autograd
+
+
+def test_adamw_step_matches_torch():
+    from ultravox_b200 import ops
+    n = 10007
+    p = rnd(n, seed=1)
+    g = torch.randn(n, generator=torch.Generator().manual_seed(2)).cuda() * 0.1
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    pf = p.float().clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pf], lr=2e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    cur = p.clone()
+    for step in (1, 2, 3):
+        pf.grad = g.clone()
+        opt.step()
+        ops.adamw_(cur, g, m, v, step, 2e-3, (0.9, 0.999), 1e-8, 0.01)
+    # bf16 parameter storage rounds every step; moments are fp32
+    assert rel(cur, pf.detach().to(BF)) < 4e-3
+
+
+def test_train_step_reduces_loss():
+    from ultravox_b200 import ops
+    from ultravox_b200.training import AdapterTrainer
+    cfg, model, padded, batch = _setup([16000, 16000])
+    mel = ops.logmel(torch.from_numpy(padded).cuda(), cfg.audio_config.num_mel_bins)
+    tr = AdapterTrainer(model, lr=2e-3)
+    losses = [float(tr.train_step(audio_values=mel, **batch)) for _ in range(6)]
+    assert all(math.isfinite(l) for l in losses) and losses[-1] < losses[0], losses

@@ -18,7 +18,8 @@ struct AttnParams {
   bf16* o;
   int64_t q_rs, q_bs, k_rs, k_bs, v_rs, v_bs, o_rs, o_bs;
   const int32_t* kv_len;
-  int Sq, Skv, group;  // group = Hq / Hkv
+  float* lse;  // optional [B, Hq, Sq]: natural-log sum-exp of the scaled scores (for the backward)
+  int Sq, Skv, group, Hq;  // group = Hq / Hkv
   int causal, block;
   float scale_log2;  // scale * log2(e)
 };
@@ -212,6 +213,12 @@ __global__ void __launch_bounds__(kAThreads) attn_fwd_kernel(const AttnParams p)
     row_l[r] += __shfl_xor_sync(0xffffffffu, row_l[r], 1);
     row_l[r] += __shfl_xor_sync(0xffffffffu, row_l[r], 2);
   }
+  if (p.lse && t4 == 0) {
+    float* lp = p.lse + ((int64_t)b * p.Hq + h) * p.Sq;
+    const float ln2 = 0.6931471805599453f;
+    if (qrow0 < p.Sq) lp[qrow0] = row_m[0] * p.scale_log2 * ln2 + logf(row_l[0]);
+    if (qrow0 + 8 < p.Sq) lp[qrow0 + 8] = row_m[1] * p.scale_log2 * ln2 + logf(row_l[1]);
+  }
   const float inv0 = row_l[0] > 0.f ? 1.f / row_l[0] : 0.f;
   const float inv1 = row_l[1] > 0.f ? 1.f / row_l[1] : 0.f;
   bf16* ob = p.o + (int64_t)b * p.o_bs + (int64_t)h * D;
@@ -246,6 +253,8 @@ static int launch_attn(const uvx_attn_args* a, cudaStream_t st) {
   p.q_rs = a->q_rs; p.q_bs = a->q_bs; p.k_rs = a->k_rs; p.k_bs = a->k_bs;
   p.v_rs = a->v_rs; p.v_bs = a->v_bs; p.o_rs = a->o_rs; p.o_bs = a->o_bs;
   p.kv_len = a->kv_len;
+  p.lse = a->lse;
+  p.Hq = (int)a->Hq;
   p.Sq = (int)a->Sq;
   p.Skv = (int)a->Skv;
   p.group = (int)(a->Hq / a->Hkv);

@@ -8,7 +8,7 @@ namespace uvx {
 // one thread handles 8 consecutive dims j..j+7 (j < D/2) of one (row, head): loads x[j..] and x[j+D/2..]
 __global__ void rope_kernel(bf16* __restrict__ qkv, int64_t rows, int64_t row_stride, int heads_rot, int D,
                             const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
-                            const int32_t* __restrict__ positions, int64_t rows_per_seq, int64_t pos_offset) {
+                            const int32_t* __restrict__ positions, int64_t rows_per_seq, int64_t pos_offset, float sgn) {
   const int half = D / 2;
   const int vec_per_head = half / 8;
   const int64_t total = rows * heads_rot * vec_per_head;
@@ -29,8 +29,9 @@ __global__ void rope_kernel(bf16* __restrict__ qkv, int64_t rows, int64_t row_st
     *reinterpret_cast<float4*>(s + 4) = sp[1];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      o1[e] = x1[e] * c[e] - x2[e] * s[e];  // x*cos + rotate_half(x)*sin, first half: -x2
-      o2[e] = x2[e] * c[e] + x1[e] * s[e];  // second half: +x1
+      const float se = sgn * s[e];            // sgn = -1 applies the transposed rotation (backward)
+      o1[e] = x1[e] * c[e] - x2[e] * se;      // x*cos + rotate_half(x)*sin, first half: -x2
+      o2[e] = x2[e] * c[e] + x1[e] * se;      // second half: +x1
     }
     *reinterpret_cast<bf16x8*>(base) = pack8(o1);
     *reinterpret_cast<bf16x8*>(base + half) = pack8(o2);
@@ -133,9 +134,9 @@ __global__ void embed_splice_kernel(const int64_t* __restrict__ ids, const bf16*
 
 }  // namespace uvx
 
-extern "C" int uvx_rope(void* qkv, int64_t rows, int64_t row_stride, int Hq, int Hkv, int D, const float* cos_tab,
-                        const float* sin_tab, const int32_t* positions, int64_t rows_per_seq, int64_t pos_offset,
-                        uvx_stream_t stream) {
+static int rope_launch(void* qkv, int64_t rows, int64_t row_stride, int Hq, int Hkv, int D, const float* cos_tab,
+                       const float* sin_tab, const int32_t* positions, int64_t rows_per_seq, int64_t pos_offset, float sgn,
+                       uvx_stream_t stream) {
   using namespace uvx;
   UVX_REQUIRE(qkv && cos_tab && sin_tab, "uvx_rope: null pointer");
   UVX_REQUIRE(D % 16 == 0 && row_stride % 8 == 0 && rows_per_seq > 0, "uvx_rope: D %% 16 == 0 required");
@@ -144,8 +145,20 @@ extern "C" int uvx_rope(void* qkv, int64_t rows, int64_t row_stride, int Hq, int
   const int threads = 256;
   const int64_t blocks = (total + threads - 1) / threads;
   rope_kernel<<<(unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks), threads, 0, (cudaStream_t)stream>>>(
-      (bf16*)qkv, rows, row_stride, Hq + Hkv, D, cos_tab, sin_tab, positions, rows_per_seq, pos_offset);
+      (bf16*)qkv, rows, row_stride, Hq + Hkv, D, cos_tab, sin_tab, positions, rows_per_seq, pos_offset, sgn);
   return check_launch("rope_kernel");
+}
+
+extern "C" int uvx_rope(void* qkv, int64_t rows, int64_t row_stride, int Hq, int Hkv, int D, const float* cos_tab,
+                        const float* sin_tab, const int32_t* positions, int64_t rows_per_seq, int64_t pos_offset,
+                        uvx_stream_t stream) {
+  return rope_launch(qkv, rows, row_stride, Hq, Hkv, D, cos_tab, sin_tab, positions, rows_per_seq, pos_offset, 1.f, stream);
+}
+
+extern "C" int uvx_rope_bwd(void* dqkv, int64_t rows, int64_t row_stride, int Hq, int Hkv, int D, const float* cos_tab,
+                            const float* sin_tab, const int32_t* positions, int64_t rows_per_seq, int64_t pos_offset,
+                            uvx_stream_t stream) {
+  return rope_launch(dqkv, rows, row_stride, Hq, Hkv, D, cos_tab, sin_tab, positions, rows_per_seq, pos_offset, -1.f, stream);
 }
 
 extern "C" int uvx_swiglu(const void* x, void* out, int64_t rows, int64_t H, int64_t x_row_stride, int gate_first,

@@ -38,8 +38,7 @@ struct GemmParams {
   int m_tiles;  // per batch (of MT*128 rows)
   int n_tiles, num_tiles;
   int splits, kb_per_split;  // split-K: units = num_tiles * splits
-  float* ws_partial;         // [num_tiles * splits][MT*128][BN] fp32
-  int* ws_counter;           // [num_tiles], zero between launches (self-cleaning)
+  float* ws_partial;         // [splits][a_batch * a_rows][N] fp32 partial sums (reduced by splitk_reduce_kernel)
 };
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -242,7 +241,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ---- epilogue -------------------------------------------------------------------------
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    uint32_t* flag = tmem_slot + 1;
     uint32_t tcount = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++tcount) {
       const int tile = unit / p.splits, split = unit % p.splits;
@@ -257,20 +255,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const bool direct = p.splits == 1;
       if (!direct) {
-        // split-K: park the raw fp32 partial tile in the workspace (rows past the matrix are skipped)
-        float* part = p.ws_partial + (size_t)unit * (MT * kBM) * BN;
+        // split-K: park the raw fp32 partial tile in the workspace; splitk_reduce_kernel sums the splits in a fixed
+        // order and applies the epilogue (deterministic, and the reduction is spread over every SM)
+        float* part = p.ws_partial + (size_t)split * (size_t)(p.a_batch * p.a_rows) * (size_t)p.N;
 #pragma unroll 1
         for (int mt = 0; mt < MT; ++mt) {
           if ((int64_t)m0 + mt * kBM + q * 32 >= p.a_rows) continue;
-          const int r = mt * kBM + q * 32 + lane;
-          const bool row_ok = (int64_t)m0 + r < p.a_rows;
+          const int64_t m = (int64_t)m0 + mt * kBM + q * 32 + lane;
+          const bool row_ok = m < p.a_rows;
 #pragma unroll 1
           for (int c = 0; c < BN / 32; ++c) {
             uint32_t raw[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * BN) + (uint32_t)(mt * BN + c * 32), raw);
             tmem_ld_wait();
             if (row_ok) {
-              uint4* dst = reinterpret_cast<uint4*>(part + (size_t)r * BN + c * 32);
+              uint4* dst = reinterpret_cast<uint4*>(part + ((size_t)b * p.a_rows + m) * p.N + n0 + c * 32);
 #pragma unroll
               for (int g = 0; g < 8; ++g) dst[g] = make_uint4(raw[4 * g], raw[4 * g + 1], raw[4 * g + 2], raw[4 * g + 3]);
             }
@@ -279,14 +278,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);  // accumulator stage is free again
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) *flag = (atomicAdd(p.ws_counter + tile, 1) == p.splits - 1) ? 1u : 0u;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const bool last = *flag != 0u;
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // flag may be rewritten by the next unit only after everyone read it
-        if (!last) continue;
-        __threadfence();
+        continue;
       }
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
@@ -304,30 +296,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           float v[32];
-          if (direct) {
+          {
             uint32_t raw[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * BN) + (uint32_t)(mt * BN + c * 32), raw);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-          } else {
-            // last-arriving CTA of this tile: sum the partials in split order (deterministic)
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;
-            if (row_ok) {
-              for (int sidx = 0; sidx < p.splits; ++sidx) {
-                const float4* src = reinterpret_cast<const float4*>(
-                    p.ws_partial + ((size_t)(tile * p.splits + sidx) * (MT * kBM) + mt * kBM + row) * BN + c * 32);
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                  const float4 t = __ldcg(src + g);
-                  v[4 * g] += t.x;
-                  v[4 * g + 1] += t.y;
-                  v[4 * g + 2] += t.z;
-                  v[4 * g + 3] += t.w;
-                }
-              }
-            }
           }
           if (orow >= 0) {
             const int64_t n = (int64_t)n0 + c * 32;
@@ -367,14 +341,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
-      if (direct) {
-        // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator stage back
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      } else if (threadIdx.x == 64) {
-        p.ws_counter[tile] = 0;  // self-cleaning: the next launch finds zeros
-      }
+      // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator stage back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
   }
   tc_fence_before();
@@ -382,6 +352,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L::kTmemCols)
                  : "memory");
+  }
+}
+
+// Split-K second pass: sums the fp32 partials in split order and applies the same epilogue as the direct path.
+// One thread per 8 consecutive output columns; spread over the whole grid so no single SM has to pull all partials.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmParams p) {
+  const int64_t rows = p.a_batch * p.a_rows;
+  const int64_t vec_per_row = p.N / 8;
+  const int64_t total = rows * vec_per_row;
+  const size_t split_stride = (size_t)rows * (size_t)p.N;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / vec_per_row, n = (idx % vec_per_row) * 8;
+    const int64_t b = r / p.a_rows, m = r % p.a_rows;
+    const float* src = p.ws_partial + (size_t)r * p.N + n;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int sidx = 0; sidx < p.splits; ++sidx) {
+      const float4 t0 = __ldcg(reinterpret_cast<const float4*>(src + sidx * split_stride));
+      const float4 t1 = __ldcg(reinterpret_cast<const float4*>(src + sidx * split_stride) + 1);
+      v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
+      v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
+    }
+    const int64_t orow = p.c_row_map ? (int64_t)p.c_row_map[r] : b * p.c_batch_rows + m + p.c_row_offset;
+    if (orow < 0) continue;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= p.alpha;
+    if (p.bias) {
+      float t[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(p.bias + n), t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += t[i];
+    }
+    if (p.act == UVX_ACT_GELU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+    }
+    if (p.R) {
+      float t[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(p.R + b * p.r_batch_stride + m * p.r_row_stride + n), t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += t[i];
+    }
+    if (p.out_f32) {
+      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + orow * p.c_row_stride + n);
+      dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+      dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      *reinterpret_cast<bf16x8*>(reinterpret_cast<bf16*>(p.C) + orow * p.c_row_stride + n) = pack8(v);
+    }
   }
 }
 
@@ -478,16 +497,14 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, cudaStream_t stream) 
   p.n_tiles = (int)(a->N / BN);
   p.num_tiles = p.m_tiles * (int)a->a_batch * p.n_tiles;
   const int num_kb = (int)((a->K + kBK - 1) / kBK);
-  // split-K needs the caller's workspace: counters first (4 B per tile, 256-byte aligned), then fp32 partial tiles
-  const size_t counter_bytes = (((size_t)p.num_tiles * 4) + 255) / 256 * 256;
-  while (splits > 1 && (!a->workspace || counter_bytes + (size_t)p.num_tiles * splits * MT * kBM * BN * 4 > (size_t)a->workspace_bytes))
-    --splits;
+  // split-K needs the caller's workspace: [splits][rows][N] fp32 partial sums
+  const size_t per_split = (size_t)a->a_batch * (size_t)a->a_rows * (size_t)a->N * 4;
+  while (splits > 1 && (!a->workspace || per_split * (size_t)splits > (size_t)a->workspace_bytes)) --splits;
   if (splits > num_kb) splits = num_kb;
   if (splits < 1) splits = 1;
   p.kb_per_split = (num_kb + splits - 1) / splits;
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
-  p.ws_counter = (int*)a->workspace;
-  p.ws_partial = (float*)((uint8_t*)a->workspace + counter_bytes);
+  p.ws_partial = (float*)a->workspace;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -500,7 +517,13 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, cudaStream_t stream) 
   const int units = p.num_tiles * p.splits;
   const int grid = units < num_sms() ? units : num_sms();
   gemm_tc_kernel<MT, BN><<<(unsigned)grid, kThreads, L::kTotal, stream>>>(tmA, tmW, p);
-  return check_launch("gemm_tc_kernel");
+  int rc = check_launch("gemm_tc_kernel");
+  if (rc || p.splits == 1) return rc;
+  const int64_t total = a->a_batch * a->a_rows * (a->N / 8);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > (int64_t)num_sms() * 8) blocks = (int64_t)num_sms() * 8;
+  splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+  return check_launch("splitk_reduce_kernel");
 }
 
 }  // namespace uvx

@@ -55,7 +55,19 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ 
   const float* row = logits + (int64_t)blockIdx.x * V;
   float best = -INFINITY;
   int64_t bi = INT64_MAX;
-  for (int64_t i = threadIdx.x; i < V; i += blockDim.x) {
+  const int64_t v4 = ((uintptr_t)row % 16 == 0) ? V / 4 : 0;  // 128-bit loads over the aligned body
+  for (int64_t i = threadIdx.x; i < v4; i += blockDim.x) {
+    const float4 t = reinterpret_cast<const float4*>(row)[i];
+    const float xs[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (xs[e] > best) {  // within a thread indices grow monotonically: strict > keeps the first maximum
+        best = xs[e];
+        bi = i * 4 + e;
+      }
+    }
+  }
+  for (int64_t i = v4 * 4 + threadIdx.x; i < V; i += blockDim.x) {
     const float x = row[i];
     if (x > best || (x == best && i < bi)) {
       best = x;

@@ -7,12 +7,12 @@ namespace uvx {
 
 __global__ void __launch_bounds__(512) ce_rows_kernel(const float* __restrict__ logits, int64_t row_stride,
                                                      const int64_t* __restrict__ labels, int64_t S, int64_t V,
-                                                     int64_t ignore_index, float* __restrict__ row_loss,
+                                                     int64_t ignore_index, int shift, float* __restrict__ row_loss,
                                                      float* __restrict__ row_lse) {
   __shared__ float red[32];
   const int64_t row = blockIdx.x;
   const int64_t b = row / S, s = row % S;
-  const int64_t label = (s + 1 < S) ? labels[b * S + s + 1] : ignore_index;
+  const int64_t label = shift ? ((s + 1 < S) ? labels[b * S + s + 1] : ignore_index) : labels[row];
   const float* x = logits + row * row_stride;
   // pass 1: max
   float mx = -INFINITY;
@@ -49,13 +49,13 @@ __global__ void __launch_bounds__(512) ce_rows_kernel(const float* __restrict__ 
 }
 
 __global__ void __launch_bounds__(1024) ce_mean_kernel(const float* __restrict__ row_loss, const int64_t* __restrict__ labels,
-                                                      int64_t B, int64_t S, int64_t V, int64_t ignore_index,
+                                                      int64_t B, int64_t S, int64_t V, int64_t ignore_index, int shift,
                                                       float* __restrict__ out) {
   __shared__ float red[32];
   float sum = 0.f, cnt = 0.f;
   for (int64_t r = threadIdx.x; r < B * S; r += blockDim.x) {
     const int64_t s = r % S;
-    const int64_t label = (s + 1 < S) ? labels[r + 1] : ignore_index;
+    const int64_t label = shift ? ((s + 1 < S) ? labels[r + 1] : ignore_index) : labels[r];
     if (label != ignore_index && label >= 0 && label < V) {
       sum += row_loss[r];
       cnt += 1.f;
@@ -72,14 +72,15 @@ __global__ void __launch_bounds__(1024) ce_mean_kernel(const float* __restrict__
 }  // namespace uvx
 
 extern "C" int uvx_ce_loss(const float* logits, int64_t row_stride, const int64_t* labels, int64_t B, int64_t S, int64_t V,
-                           int64_t ignore_index, float* row_loss, float* row_lse, float* out_loss2, uvx_stream_t stream) {
+                           int64_t ignore_index, int shift, float* row_loss, float* row_lse, float* out_loss2,
+                           uvx_stream_t stream) {
   using namespace uvx;
   UVX_REQUIRE(logits && labels && row_loss && row_lse && out_loss2, "uvx_ce_loss: null pointer");
   UVX_REQUIRE(B >= 1 && S >= 1 && V >= 1 && row_stride % 4 == 0 && (uintptr_t)logits % 16 == 0, "uvx_ce_loss: bad shape");
-  ce_rows_kernel<<<(unsigned)(B * S), 512, 0, (cudaStream_t)stream>>>(logits, row_stride, labels, S, V, ignore_index, row_loss,
-                                                                     row_lse);
+  ce_rows_kernel<<<(unsigned)(B * S), 512, 0, (cudaStream_t)stream>>>(logits, row_stride, labels, S, V, ignore_index, shift,
+                                                                     row_loss, row_lse);
   int rc = check_launch("ce_rows_kernel");
   if (rc) return rc;
-  ce_mean_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_loss, labels, B, S, V, ignore_index, out_loss2);
+  ce_mean_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_loss, labels, B, S, V, ignore_index, shift, out_loss2);
   return check_launch("ce_mean_kernel");
 }

@@ -53,6 +53,55 @@ __global__ void __launch_bounds__(kNormThreads) layernorm_kernel(const bf16* __r
   }
 }
 
+// Warp-per-row variant for cols <= 2048 (the Whisper encoder's d_model): no block barriers, 4 rows per CTA.
+static constexpr int kLnWarpVec = 8;
+__global__ void __launch_bounds__(128) layernorm_warp_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                             const bf16* __restrict__ b, bf16* __restrict__ y, int64_t rows,
+                                                             int64_t cols, int64_t x_row_stride, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const bf16* xr = x + row * x_row_stride;
+  const int nvec = (int)(cols / 8);
+  float v[kLnWarpVec][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnWarpVec; ++i) {
+    const int j = lane + i * 32;
+    if (j < nvec) {
+      unpack8(*reinterpret_cast<const bf16x8*>(xr + (int64_t)j * 8), v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[i][e];
+    }
+  }
+  const float mean = warp_sum(s) / (float)cols;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnWarpVec; ++i) {
+    const int j = lane + i * 32;
+    if (j < nvec) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = v[i][e] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)cols + eps);
+#pragma unroll
+  for (int i = 0; i < kLnWarpVec; ++i) {
+    const int j = lane + i * 32;
+    if (j < nvec) {
+      float wv[8], bv[8], o[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(w + (int64_t)j * 8), wv);
+      unpack8(*reinterpret_cast<const bf16x8*>(b + (int64_t)j * 8), bv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (v[i][e] - mean) * rstd * wv[e] + bv[e];
+      *reinterpret_cast<bf16x8*>(y + row * cols + (int64_t)j * 8) = pack8(o);
+    }
+  }
+}
+
 // RMSNorm with the exact rounding order of LlamaRMSNorm: y = w * bf16(x * rsqrt(mean(x^2) + eps)).
 // Grouped mode implements StackAudioFrames: elements past `valid` in a row read as zero.
 __global__ void __launch_bounds__(kNormThreads) rmsnorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
@@ -111,6 +160,11 @@ extern "C" int uvx_layernorm(const void* x, const void* w, const void* b, void* 
   UVX_REQUIRE(cols % 8 == 0 && cols <= kNormThreads * kMaxVec * 8 && x_row_stride % 8 == 0,
               "uvx_layernorm: cols must be a multiple of 8 and <= %d", kNormThreads * kMaxVec * 8);
   if (rows == 0) return UVX_OK;
+  if (cols <= 32 * kLnWarpVec * 8) {
+    layernorm_warp_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)w, (const bf16*)b,
+                                                                                       (bf16*)y, rows, cols, x_row_stride, eps);
+    return check_launch("layernorm_warp_kernel");
+  }
   layernorm_kernel<<<(unsigned)rows, kNormThreads, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)w, (const bf16*)b,
                                                                              (bf16*)y, cols, x_row_stride, eps);
   return check_launch("layernorm_kernel");

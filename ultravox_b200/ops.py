@@ -298,3 +298,106 @@ def llama3_inv_freq(head_dim: int, theta: float, scaling: Optional[dict]) -> tor
     sm = (1 - smooth) * inv_l / factor + smooth * inv_l
     mid = ~(wl < old / hi) * ~(wl > old / lo)
     return torch.where(mid, sm, inv_l)
+
+
+# ------------------------------------------------------------------------------------------ backward pieces (a14)
+def transpose(x: torch.Tensor, out: Optional[torch.Tensor] = None, pad_cols_to: int = 8) -> torch.Tensor:
+    """[R, C] bf16 -> [C, R'] with R' = R rounded up to ``pad_cols_to`` (zero tail) so it can be a GEMM operand."""
+    _cuda(x, BF16, "x")
+    R, Cc = x.shape
+    Rp = -(-R // pad_cols_to) * pad_cols_to
+    if out is None:
+        out = torch.zeros(Cc, Rp, dtype=BF16, device=x.device) if Rp != R else torch.empty(Cc, Rp, dtype=BF16, device=x.device)
+    check(lib().uvx_transpose_bf16(x.data_ptr(), R, Cc, x.stride(0), out.data_ptr(), out.stride(0), _stream()),
+          "uvx_transpose_bf16")
+    return out
+
+
+def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, eps: float, dres: Optional[torch.Tensor] = None,
+                want_dx: bool = True, dw: Optional[torch.Tensor] = None, stack: Optional[tuple] = None,
+                out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """dx (bf16, + dres) and/or dw (fp32, accumulated) of uvx_rmsnorm.  ``stack=(group_rows, T*C)`` for ln_pre."""
+    _cuda(dy, BF16, "dy")
+    cols = dy.shape[-1]
+    rows = dy.numel() // cols
+    if want_dx and out is None:
+        out = torch.empty(dy.shape, dtype=BF16, device=dy.device)
+    g_rows, g_stride, valid = (stack[0], stack[1], stack[1]) if stack else (0, 0, 0)
+    xs = cols if stack else x.reshape(-1, cols).stride(0)
+    check(lib().uvx_rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), _p(dres), _p(out) if want_dx else None, _p(dw), rows,
+                                cols, xs, g_rows, g_stride, valid, eps, _stream()), "uvx_rmsnorm_bwd")
+    return out if want_dx else None
+
+
+def swiglu_bwd(x: torch.Tensor, dout: torch.Tensor, gate_first: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    H = x.shape[-1] // 2
+    x2 = x.reshape(-1, 2 * H)
+    if out is None:
+        out = torch.empty(x2.shape, dtype=BF16, device=x.device)
+    check(lib().uvx_swiglu_bwd(x2.data_ptr(), dout.data_ptr(), out.data_ptr(), x2.shape[0], H, x2.stride(0), int(gate_first),
+                               _stream()), "uvx_swiglu_bwd")
+    return out
+
+
+def rope_bwd_(dqkv: torch.Tensor, Hq: int, Hkv: int, D: int, cos: torch.Tensor, sin: torch.Tensor, rows_per_seq: int,
+              pos_offset: int = 0) -> torch.Tensor:
+    rows = dqkv.numel() // dqkv.shape[-1]
+    check(lib().uvx_rope_bwd(dqkv.data_ptr(), rows, dqkv.stride(-2), Hq, Hkv, D, cos.data_ptr(), sin.data_ptr(), None,
+                             rows_per_seq, pos_offset, _stream()), "uvx_rope_bwd")
+    return dqkv
+
+
+def attention_fused_qkv_train(qkv: torch.Tensor, B: int, S: int, Hq: int, Hkv: int, D: int, scale: float, causal: bool,
+                              out: torch.Tensor, lse: torch.Tensor, kv_len: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Forward that also records the log-sum-exp ([B, Hq, S] fp32) needed by the backward."""
+    rs = qkv.stride(-2)
+    base = qkv.data_ptr()
+    a = AttnArgs()
+    a.q, a.k, a.v, a.o = base, base + 2 * Hq * D, base + 2 * (Hq + Hkv) * D, out.data_ptr()
+    a.B, a.Hq, a.Hkv, a.Sq, a.Skv, a.D = B, Hq, Hkv, S, S, D
+    (a.q_rs, a.q_bs, a.k_rs, a.k_bs, a.v_rs, a.v_bs, a.o_rs, a.o_bs) = (rs, S * rs, rs, S * rs, rs, S * rs, Hq * D, S * Hq * D)
+    a.kv_len, a.causal, a.block, a.scale, a.lse = _p(kv_len), int(causal), 0, float(scale), lse.data_ptr()
+    check(lib().uvx_attention(C.byref(a), _stream()), "uvx_attention")
+    return out
+
+
+def attention_fused_qkv_bwd(qkv: torch.Tensor, o: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor, B: int, S: int, Hq: int,
+                            Hkv: int, D: int, scale: float, causal: bool, dqkv: Optional[torch.Tensor] = None,
+                            kv_len: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dqkv [B*S, (Hq+2Hkv)*D] (same fused layout as qkv) from dout [B*S, Hq*D]."""
+    rs = qkv.stride(-2)
+    base = qkv.data_ptr()
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    a = AttnArgs()
+    a.q, a.k, a.v, a.o = base, base + 2 * Hq * D, base + 2 * (Hq + Hkv) * D, o.data_ptr()
+    a.B, a.Hq, a.Hkv, a.Sq, a.Skv, a.D = B, Hq, Hkv, S, S, D
+    (a.q_rs, a.q_bs, a.k_rs, a.k_bs, a.v_rs, a.v_bs, a.o_rs, a.o_bs) = (rs, S * rs, rs, S * rs, rs, S * rs, Hq * D, S * Hq * D)
+    a.kv_len, a.causal, a.block, a.scale, a.lse = _p(kv_len), int(causal), 0, float(scale), lse.data_ptr()
+    delta = torch.empty(B * Hq * S, dtype=torch.float32, device=qkv.device)
+    drs = dqkv.stride(-2)
+    dbase = dqkv.data_ptr()
+    check(lib().uvx_attention_bwd(C.byref(a), o.data_ptr(), dout.data_ptr(), dbase, dbase + 2 * Hq * D, dbase + 2 * (Hq + Hkv) * D,
+                                  drs, S * drs, drs, S * drs, drs, S * drs, delta.data_ptr(), _stream()), "uvx_attention_bwd")
+    return dqkv
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    d = src.shape[-1]
+    if out is None:
+        out = torch.empty(idx.numel(), d, dtype=BF16, device=src.device)
+    check(lib().uvx_gather_rows(src.data_ptr(), idx.data_ptr(), idx.numel(), d, out.data_ptr(), _stream()), "uvx_gather_rows")
+    return out
+
+
+def splice_inverse(src: torch.Tensor, n_audio_rows: int) -> torch.Tensor:
+    inv = torch.empty(n_audio_rows, dtype=torch.int32, device=src.device)
+    check(lib().uvx_splice_inverse(src.data_ptr(), src.numel(), inv.data_ptr(), n_audio_rows, _stream()), "uvx_splice_inverse")
+    return inv
+
+
+def adamw_(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step: int, lr: float, betas=(0.9, 0.999),
+           eps: float = 1e-8, weight_decay: float = 0.0, grad_scale: float = 1.0) -> None:
+    _cuda(p, BF16, "p"), _cuda(g, torch.float32, "g")
+    check(lib().uvx_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, betas[0], betas[1], eps,
+                          weight_decay, step, grad_scale, _stream()), "uvx_adamw")
