@@ -62,6 +62,23 @@ def test_gemm_forced_configs_and_split_k(ops, cfg, splits):
     assert torch.equal(y1, y2)  # split-K reduction order is fixed -> bitwise reproducible
 
 
+@pytest.mark.parametrize("cfg", [4128, 4256])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (1500, 1280, 1280), (201, 512, 4096), (700, 768, 200)])
+def test_gemm_two_sm_pairs(ops, cfg, M, N, K):
+    """cta_group::2 kernel (cluster of 2 CTAs, 256-row pair tiles), all epilogue features, M / K tails."""
+    from ultravox_b200 import _lib
+    x, w, b, r = rnd(M, K, seed=1), rnd(N, K, scale=0.05, seed=2), rnd(N, seed=3), rnd(M, N, seed=4)
+    ref = F.gelu(x.float() @ w.float().T + b.float()) + r.float()
+    _lib.lib().uvx_debug_gemm_override(cfg, 1)
+    try:
+        y = ops.linear(x, w, bias=b, act=ops.ACT_GELU, residual=r)
+        y32 = ops.linear(x, w, out_dtype=torch.float32)
+    finally:
+        _lib.lib().uvx_debug_gemm_override(0, 0)
+    assert rel(y, ref) < 1e-3
+    assert rel(y32, x.float() @ w.float().T) < 1e-5
+
+
 def test_gemm_epilogues(ops):
     M, N, K = 333, 384, 320
     x, w, b, r = rnd(M, K, seed=1), rnd(N, K, scale=0.05, seed=2), rnd(N, seed=3), rnd(M, N, seed=4)

@@ -187,7 +187,7 @@ def test_adamw_step_matches_torch():
         opt.step()
         ops.adamw_(cur, g, m, v, step, 2e-3, (0.9, 0.999), 1e-8, 0.01)
     # bf16 parameter storage rounds every step; moments are fp32
-    assert rel(cur, pf.detach().to(BF)) < 4e-3
+    assert rel(cur, pf.detach().to(BF)) < 8e-3
 
 
 def test_train_step_reduces_loss():

@@ -355,6 +355,247 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// =====================================================================================================
+// 2-SM variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BN tile with ONE tcgen05.mma per k-step.
+// CTA r stages rows [r*128, r*128+128) of A and rows [r*BN/2, (r+1)*BN/2) of W; the tensor core of the leader reads both
+// halves, so each SM ingests only 16 KB + BN*64 B per k-block for 2*128*BN*64 flops of its own accumulator - twice the
+// flops per byte of the 1-SM 128x128 tile (the 1-SM kernel is bound by bytes into the SM, see profiles/).
+//   - both CTAs run a TMA producer; all bytes are signalled on the LEADER's full barrier (peer bit masked off);
+//   - only the leader issues MMAs; tcgen05.commit.multicast frees the ring slot / publishes the accumulator in both CTAs;
+//   - each CTA's epilogue drains its own 128 TMEM lanes; all 8 epilogue warps arrive on the leader's tmem_empty barrier.
+static constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-pair bit of a shared::cluster address -> leader CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+template <int BN>
+struct Smem2 {
+  static constexpr int kABytes = kBM * kBK * 2;        // this CTA's 128 rows
+  static constexpr int kWBytes = (BN / 2) * kBK * 2;   // this CTA's half of the W tile
+  static constexpr int kStageBytes = kABytes + kWBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kAcc = (BN * 2 <= 512) ? 2 : 1;
+  static constexpr int kTmemCols = kAcc * BN < 32 ? 32 : kAcc * BN;
+  static constexpr int kBarOff = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOff + 256 + 1024;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tc2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+  using L = Smem2<BN>;
+  constexpr int kStages = L::kStages;
+  constexpr int kAcc = L::kAcc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + kAcc;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + kAcc);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int tiles_m_total = p.m_tiles * (int)p.a_batch;  // m_tiles counts 256-row pair tiles
+  const int num_kb = (int)((p.K + kBK - 1) / kBK);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 2);   // leader's expect_tx arrive + the peer producer's arrive
+      mbar_init(&empty_bar[s], 1);  // one multicast commit from the leader's MMA thread
+    }
+    for (int a = 0; a < kAcc; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 8);  // 4 epilogue warps x 2 CTAs (used on the leader only)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)L::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+      uint32_t it = 0;
+      for (int tile = pair; tile < p.num_tiles; tile += num_pairs) {
+        const int tm_idx = tile % tiles_m_total;
+        const int tn_idx = tile / tiles_m_total;
+        const int b = tm_idx / p.m_tiles;
+        const int m0 = (tm_idx % p.m_tiles) * (2 * kBM) + (int)rank * kBM;
+        const int n0 = tn_idx * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* sa = smem + s * L::kStageBytes;
+          tma2_load_3d(sa, &tmA, kb * kBK, m0, b, &full_bar[s]);
+          tma2_load_2d(sa + L::kABytes, &tmW, kb * kBK, n0, &full_bar[s]);
+          if (leader) mbar_expect_tx(&full_bar[s], (uint32_t)(2 * L::kStageBytes));
+          else mbar_arrive_leader(&full_bar[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++tcount) {
+        const uint32_t acc = tcount % kAcc;
+        const uint32_t aph = (tcount / kAcc) & 1u;
+        mbar_wait(&tmem_empty[acc], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
+          const uint64_t da = make_smem_desc(sa);
+          const uint64_t dw = make_smem_desc(sa + L::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            umma2_f16(d_tmem, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma2_commit_mc(&empty_bar[s]);
+        }
+        umma2_commit_mc(&tmem_full[acc]);
+      }
+      // keep the leader's barriers alive until the last epilogue arrivals from the peer have landed
+      if (tcount > 0) {
+        const uint32_t last = tcount - 1;
+        mbar_wait(&tmem_empty[last % kAcc], (last / kAcc) & 1u);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    uint32_t tcount = 0;
+    for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++tcount) {
+      const int tm_idx = tile % tiles_m_total;
+      const int tn_idx = tile / tiles_m_total;
+      const int b = tm_idx / p.m_tiles;
+      const int m0 = (tm_idx % p.m_tiles) * (2 * kBM) + (int)rank * kBM;
+      const int n0 = tn_idx * BN;
+      const uint32_t acc = tcount % kAcc;
+      const uint32_t aph = (tcount / kAcc) & 1u;
+      mbar_wait(&tmem_full[acc], aph);
+      tc_fence_after();
+      const int64_t m = (int64_t)m0 + q * 32 + lane;
+      const bool row_ok = m < p.a_rows;
+      int64_t orow = -1;
+      if (row_ok) {
+        orow = p.c_row_map ? (int64_t)p.c_row_map[(int64_t)b * p.a_rows + m] : (int64_t)b * p.c_batch_rows + m + p.c_row_offset;
+      }
+      const bf16* rrow = (p.R && row_ok) ? p.R + (int64_t)b * p.r_batch_stride + m * p.r_row_stride : nullptr;
+      if ((int64_t)m0 + q * 32 < p.a_rows) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c * 32), raw);
+          tmem_ld_wait();
+          if (orow >= 0) {
+            const int64_t n = (int64_t)n0 + c * 32;
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
+            if (p.bias) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float t[8];
+                unpack8(*reinterpret_cast<const bf16x8*>(p.bias + n + g * 8), t);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[g * 8 + i] += t[i];
+              }
+            }
+            if (p.act == UVX_ACT_GELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+            }
+            if (rrow) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float t[8];
+                unpack8(*reinterpret_cast<const bf16x8*>(rrow + n + g * 8), t);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[g * 8 + i] += t[i];
+              }
+            }
+            if (p.out_f32) {
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + orow * p.c_row_stride + n);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+            } else {
+              bf16x8* dst = reinterpret_cast<bf16x8*>(reinterpret_cast<bf16*>(p.C) + orow * p.c_row_stride + n);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) dst[g] = pack8(v + g * 8);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L::kTmemCols)
+                 : "memory");
+  }
+}
+
 // Split-K second pass: sums the fp32 partials in split order and applies the same epilogue as the direct path.
 // One thread per 8 consecutive output columns; spread over the whole grid so no single SM has to pull all partials.
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmParams p) {
@@ -526,6 +767,62 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, cudaStream_t stream) 
   return check_launch("splitk_reduce_kernel");
 }
 
+template <int BN>
+static int launch_gemm_2sm(const uvx_gemm_args* a, cudaStream_t stream) {
+  using L = Smem2<BN>;
+  CUtensorMap tmA, tmW;
+  {
+    uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->a_rows, (uint64_t)a->a_batch};
+    uint64_t st[2] = {(uint64_t)a->a_row_stride * 2, (uint64_t)(a->a_batch > 1 ? a->a_batch_stride : a->a_row_stride) * 2};
+    uint32_t box[3] = {kBK, (uint32_t)kBM, 1};
+    int rc = encode_map(&tmA, a->A, 3, dims, st, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
+    uint64_t st[1] = {(uint64_t)a->w_row_stride * 2};
+    uint32_t box[2] = {kBK, (uint32_t)(BN / 2)};
+    int rc = encode_map(&tmW, a->W, 2, dims, st, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (rc) return rc;
+  }
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.a_rows = a->a_rows;
+  p.a_batch = a->a_batch;
+  p.K = a->K;
+  p.N = a->N;
+  p.C = a->C;
+  p.c_row_stride = a->c_row_stride;
+  p.c_batch_rows = a->c_batch_rows;
+  p.c_row_offset = a->c_row_offset;
+  p.c_row_map = a->c_row_map;
+  p.bias = (const bf16*)a->bias;
+  p.R = (const bf16*)a->R;
+  p.r_row_stride = a->r_row_stride;
+  p.r_batch_stride = a->r_batch_stride;
+  p.alpha = a->alpha;
+  p.act = a->act;
+  p.out_f32 = a->out_dtype == UVX_DT_F32;
+  p.m_tiles = (int)((a->a_rows + 2 * kBM - 1) / (2 * kBM));
+  p.n_tiles = (int)(a->N / BN);
+  p.num_tiles = p.m_tiles * (int)a->a_batch * p.n_tiles;
+  p.splits = 1;
+  p.kb_per_split = (int)((a->K + kBK - 1) / kBK);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2sm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm_tc2sm_kernel<%d>, smem %d): %s", BN, L::kTotal, cudaGetErrorString(e));
+      return UVX_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int max_pairs = num_sms() / 2;
+  const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
+  gemm_tc2sm_kernel<BN><<<(unsigned)(2 * pairs), kThreads, L::kTotal, stream>>>(tmA, tmW, p);
+  return check_launch("gemm_tc2sm_kernel");
+}
+
 }  // namespace uvx
 
 // Tile / split selection.  cfg = MT*1000 + BN; UVX_GEMM_CFG / UVX_GEMM_SPLITS (env, tuning only) override the heuristic.
@@ -598,6 +895,8 @@ extern "C" int uvx_gemm_bf16(const uvx_gemm_args* a, uvx_stream_t stream_) {
     case 2064: return launch_gemm<2, 64>(a, splits, stream);
     case 2128: return launch_gemm<2, 128>(a, splits, stream);
     case 2256: return launch_gemm<2, 256>(a, splits, stream);
+    case 4128: return launch_gemm_2sm<128>(a, stream);
+    case 4256: return launch_gemm_2sm<256>(a, stream);
     default: return launch_gemm<1, 64>(a, splits, stream);
   }
 }
