@@ -123,16 +123,91 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+
+// ---------------------------------------------------------------------------------- coalesced epilogue
+// A warp owns 32 accumulator rows (TMEM lanes); tcgen05.ld hands each LANE one row x 32 columns.  Storing that
+// directly makes every 16-byte store hit a different row (measured 8x write amplification on the SM->L2 path), so
+// the 32x32 fp32 chunk is transposed through a per-warp shared-memory pad and written back with 4 lanes per row:
+// every store instruction covers 8 rows x 64 contiguous bytes (full 32-byte sectors), residual reads likewise.
+static constexpr int kStageLd = 36;                           // floats per staged row (16-byte aligned, conflict-light)
+static constexpr int kStageBytesPerWarp = 32 * kStageLd * 4;  // 4608 B
+
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t* raw, float* stage, int lane, int b,
+                                               int64_t m_warp0, int64_t n) {
+  // phase 1: this lane's row, 32 columns: alpha, bias, activation (fp32)
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
+  if (p.bias) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float t[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(p.bias + n + g * 8), t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[g * 8 + i] += t[i];
+    }
+  }
+  if (p.act == UVX_ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+  }
+  float4* srow = reinterpret_cast<float4*>(stage + lane * kStageLd);
+#pragma unroll
+  for (int g = 0; g < 8; ++g) srow[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+  __syncwarp();
+  // phase 2: transposed read-back, residual add, coalesced stores
+  if (p.out_f32) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = (lane >> 3) + 4 * j, pc = (lane & 7) * 4;
+      const int64_t m = m_warp0 + r;
+      if (m >= p.a_rows) continue;
+      const int64_t orow = p.c_row_map ? (int64_t)p.c_row_map[(int64_t)b * p.a_rows + m] : (int64_t)b * p.c_batch_rows + m + p.c_row_offset;
+      if (orow < 0) continue;
+      float4 t = *reinterpret_cast<const float4*>(stage + r * kStageLd + pc);
+      if (p.R) {
+        const bf16* rr = p.R + (int64_t)b * p.r_batch_stride + m * p.r_row_stride + n + pc;
+        const float2 r01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(rr));
+        const float2 r23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(rr + 2));
+        t.x += r01.x; t.y += r01.y; t.z += r23.x; t.w += r23.y;
+      }
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + orow * p.c_row_stride + n + pc) = t;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = (lane >> 2) + 8 * j, pc = (lane & 3) * 8;
+      const int64_t m = m_warp0 + r;
+      if (m >= p.a_rows) continue;
+      const int64_t orow = p.c_row_map ? (int64_t)p.c_row_map[(int64_t)b * p.a_rows + m] : (int64_t)b * p.c_batch_rows + m + p.c_row_offset;
+      if (orow < 0) continue;
+      const float4 t0 = *reinterpret_cast<const float4*>(stage + r * kStageLd + pc);
+      const float4 t1 = *reinterpret_cast<const float4*>(stage + r * kStageLd + pc + 4);
+      float o[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+      if (p.R) {
+        float rv[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(p.R + (int64_t)b * p.r_batch_stride + m * p.r_row_stride + n + pc), rv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += rv[i];
+      }
+      *reinterpret_cast<bf16x8*>(reinterpret_cast<bf16*>(p.C) + orow * p.c_row_stride + n + pc) = pack8(o);
+    }
+  }
+  __syncwarp();  // the pad is reused by the next chunk
+}
+
 template <int MT, int BN>
 struct SmemLayout {
   static constexpr int kABytes = MT * kBM * kBK * 2;  // 16 KB per row sub-tile
   static constexpr int kWBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kWBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kStages = (196 * 1024) / kStageBytes > 8 ? 8 : (196 * 1024) / kStageBytes;
   static constexpr int kAcc = (MT * BN * 2 <= 512) ? 2 : 1;  // TMEM accumulator stages
   static constexpr int kTmemCols = kAcc * MT * BN < 32 ? 32 : kAcc * MT * BN;
   static constexpr int kBarOff = kStages * kStageBytes;
-  static constexpr int kTotal = kBarOff + 256 + 1024;  // barriers + slack for 1024-byte alignment
+  static constexpr int kPadOff = kBarOff + 256;                                  // epilogue transpose pads (4 warps)
+  static constexpr int kTotal = kPadOff + 4 * kStageBytesPerWarp + 1024;         // + slack for 1024-byte alignment
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
   static_assert(kStages >= 2, "ring too shallow");
   static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns must be a power of two <= 512");
 };
@@ -280,65 +355,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);  // accumulator stage is free again
         continue;
       }
+      float* pad = reinterpret_cast<float*>(smem + L::kPadOff) + (warp - 2) * (kStageBytesPerWarp / 4);
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
-        const int row = q * 32 + lane;
-        const int64_t m = (int64_t)m0 + mt * kBM + row;
-        const bool row_ok = m < p.a_rows;
-        int64_t orow = -1;
-        if (row_ok) {
-          orow = p.c_row_map ? (int64_t)p.c_row_map[(int64_t)b * p.a_rows + m]
-                             : (int64_t)b * p.c_batch_rows + m + p.c_row_offset;
-        }
-        const bf16* rrow = (p.R && row_ok) ? p.R + (int64_t)b * p.r_batch_stride + m * p.r_row_stride : nullptr;
-        // skip sub-tiles that are entirely out of range (warp-uniform)
-        if ((int64_t)m0 + mt * kBM + q * 32 >= p.a_rows) continue;
+        const int64_t m_warp0 = (int64_t)m0 + mt * kBM + q * 32;
+        if (m_warp0 >= p.a_rows) continue;  // sub-tile entirely out of range (warp-uniform)
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
-          float v[32];
-          {
-            uint32_t raw[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * BN) + (uint32_t)(mt * BN + c * 32), raw);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-          }
-          if (orow >= 0) {
-            const int64_t n = (int64_t)n0 + c * 32;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
-            if (p.bias) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float t[8];
-                unpack8(*reinterpret_cast<const bf16x8*>(p.bias + n + g * 8), t);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[g * 8 + i] += t[i];
-              }
-            }
-            if (p.act == UVX_ACT_GELU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-            }
-            if (rrow) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float t[8];
-                unpack8(*reinterpret_cast<const bf16x8*>(rrow + n + g * 8), t);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[g * 8 + i] += t[i];
-              }
-            }
-            if (p.out_f32) {
-              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + orow * p.c_row_stride + n);
-#pragma unroll
-              for (int g = 0; g < 8; ++g) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-            } else {
-              bf16x8* dst = reinterpret_cast<bf16x8*>(reinterpret_cast<bf16*>(p.C) + orow * p.c_row_stride + n);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) dst[g] = pack8(v + g * 8);
-            }
-          }
+          uint32_t raw[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * BN) + (uint32_t)(mt * BN + c * 32), raw);
+          tmem_ld_wait();
+          epilogue_chunk(p, raw, pad, lane, b, m_warp0, (int64_t)n0 + c * 32);
         }
       }
       // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator stage back
@@ -413,11 +440,13 @@ struct Smem2 {
   static constexpr int kABytes = kBM * kBK * 2;        // this CTA's 128 rows
   static constexpr int kWBytes = (BN / 2) * kBK * 2;   // this CTA's half of the W tile
   static constexpr int kStageBytes = kABytes + kWBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kStages = (196 * 1024) / kStageBytes > 8 ? 8 : (196 * 1024) / kStageBytes;
   static constexpr int kAcc = (BN * 2 <= 512) ? 2 : 1;
   static constexpr int kTmemCols = kAcc * BN < 32 ? 32 : kAcc * BN;
   static constexpr int kBarOff = kStages * kStageBytes;
-  static constexpr int kTotal = kBarOff + 256 + 1024;
+  static constexpr int kPadOff = kBarOff + 256;
+  static constexpr int kTotal = kPadOff + 4 * kStageBytesPerWarp + 1024;
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
 
 template <int BN>
@@ -531,56 +560,15 @@ gemm_tc2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t aph = (tcount / kAcc) & 1u;
       mbar_wait(&tmem_full[acc], aph);
       tc_fence_after();
-      const int64_t m = (int64_t)m0 + q * 32 + lane;
-      const bool row_ok = m < p.a_rows;
-      int64_t orow = -1;
-      if (row_ok) {
-        orow = p.c_row_map ? (int64_t)p.c_row_map[(int64_t)b * p.a_rows + m] : (int64_t)b * p.c_batch_rows + m + p.c_row_offset;
-      }
-      const bf16* rrow = (p.R && row_ok) ? p.R + (int64_t)b * p.r_batch_stride + m * p.r_row_stride : nullptr;
-      if ((int64_t)m0 + q * 32 < p.a_rows) {
+      float* pad = reinterpret_cast<float*>(smem + L::kPadOff) + (warp - 2) * (kStageBytesPerWarp / 4);
+      const int64_t m_warp0 = (int64_t)m0 + q * 32;
+      if (m_warp0 < p.a_rows) {
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t raw[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c * 32), raw);
           tmem_ld_wait();
-          if (orow >= 0) {
-            const int64_t n = (int64_t)n0 + c * 32;
-            float v[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
-            if (p.bias) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float t[8];
-                unpack8(*reinterpret_cast<const bf16x8*>(p.bias + n + g * 8), t);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[g * 8 + i] += t[i];
-              }
-            }
-            if (p.act == UVX_ACT_GELU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-            }
-            if (rrow) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float t[8];
-                unpack8(*reinterpret_cast<const bf16x8*>(rrow + n + g * 8), t);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[g * 8 + i] += t[i];
-              }
-            }
-            if (p.out_f32) {
-              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + orow * p.c_row_stride + n);
-#pragma unroll
-              for (int g = 0; g < 8; ++g) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-            } else {
-              bf16x8* dst = reinterpret_cast<bf16x8*>(reinterpret_cast<bf16*>(p.C) + orow * p.c_row_stride + n);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) dst[g] = pack8(v + g * 8);
-            }
-          }
+          epilogue_chunk(p, raw, pad, lane, b, m_warp0, (int64_t)n0 + c * 32);
         }
       }
       tc_fence_before();
