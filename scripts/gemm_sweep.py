@@ -41,11 +41,16 @@ for name, M, N, K in SHAPES:
             print(f"{name} cfg={cfg} sp={sp} WRONG rel={err:.3e}"); continue
         for i in range(3):
             ops.linear(x, Ws[i % copies], out=out)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
         iters = 20
+        g = torch.cuda.CUDAGraph()          # graph replay: kernel time only, no per-launch host cost
+        with torch.cuda.graph(g):
+            for i in range(iters):
+                ops.linear(x, Ws[i % copies], out=out)
+        g.replay(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(iters):
-            ops.linear(x, Ws[i % copies], out=out)
+        g.replay()
         e1.record(); torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / iters
         gbs = (wbytes + M * K * 2 + M * N * 2) / us / 1e3

@@ -838,9 +838,11 @@ static void pick_cfg(int64_t rows, int64_t batch, int64_t N, int64_t K, int* cfg
     mt = 2;
     bn = (N % 256 == 0 && N / 256 >= sms / 2) ? 256 : (N % 128 == 0 ? 128 : 64);
   } else {
+    // tensor-bound regime (encoder, training): 128-row tiles; 256-wide when that still gives >= ~1.3 waves of tiles
     mt = 1;
     const int64_t m_tiles = (rows + 127) / 128 * batch;
-    bn = (N % 128 == 0 && m_tiles * (N / 128) >= sms / 2) ? 128 : 64;
+    if (N % 256 == 0 && m_tiles * (N / 256) >= (sms * 4) / 3) bn = 256;
+    else bn = (N % 128 == 0 && m_tiles * (N / 128) >= sms / 2) ? 128 : 64;
   }
   if (forced > 0 && N % (forced % 1000) == 0) {
     mt = forced / 1000;
