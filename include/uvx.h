@@ -177,6 +177,16 @@ int uvx_argmax(const float* logits, int64_t B, int64_t V, int64_t* out_idx, uvx_
 int uvx_ce_loss(const float* logits, int64_t row_stride, const int64_t* labels, int64_t B, int64_t S, int64_t V,
                 int64_t ignore_index, int shift, float* row_loss, float* row_lse, float* out_loss2, uvx_stream_t stream);
 
+/* a15: KL distillation loss of ref:ultravox/model/ultravox_model.py:202-257 (the reference's default training loss):
+ * F.kl_div(log_softmax(student / T), softmax(teacher / T), "batchmean") on the prediction rows + eot_loss_weight x the
+ * same on the EOT rows.  Rows are pre-gathered ([R, V] fp32 each) and carry a weight row_w[r] (1/#pred, plus
+ * eot_weight/#eot on EOT rows): out_loss[0] = sum_r row_w[r] * KL_r.  uvx_kl_bwd gives d/d(student logits) in bf16.  */
+int uvx_kl_loss(const float* student, const float* teacher, int64_t row_stride, int64_t R, int64_t V, float temperature,
+                const float* row_w, float* row_kl, float* lse_s, float* lse_t, float* out_loss, uvx_stream_t stream);
+int uvx_kl_bwd(const float* student, const float* teacher, int64_t row_stride, int64_t R, int64_t V, float temperature,
+               const float* row_w, const float* lse_s, const float* lse_t, float grad_scale, void* dlogits,
+               uvx_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a14: adapter backward (encoder + LLM frozen: ref apply_lora r=0, ultravox_model.py:690-709).  These are the
  * pieces torch.autograd runs for the reference between `loss.backward()` and the projector weights; dense

@@ -186,3 +186,66 @@ def test_prefill_engine_graph_matches_eager():
     t2 = eng.run_e2e(host2).clone()
     eng.wave.copy_(host2)
     assert int(eng.run()[0]) == int(t2[0])
+
+
+class _Tok:
+    eos_token = "<|eot_id|>"
+    eos_token_id = 1000
+    pad_token_id = None
+    padding_side = "right"
+    model_input_names = ["input_ids", "attention_mask"]
+
+    def get_vocab(self):
+        return {self.eos_token: self.eos_token_id}
+
+    def __call__(self, parts, add_special_tokens=False, **kw):
+        return {"input_ids": [[(sum(map(ord, w)) * 31 + len(w)) % 1000 for w in p.split()] for p in parts]}
+
+
+def test_processor_to_model_long_clip_two_chunks_device_mel_both_ways():
+    """35 s clip -> 2 encoder chunks.  (a) processor computes the mel on the GPU (reference output contract, CUDA
+    `audio_values`); (b) processor defers and the model computes mel + chunking from the raw waveform.  Same logits."""
+    from oracle import model as om, processing as oproc
+    from ultravox_b200.processing import MelSpec, UltravoxProcessor
+    cfg, model, sd, sh = build()
+    w = wave(3, 16000 * 35)
+    text = "a b c <|audio|> d e"
+    pa = UltravoxProcessor(MelSpec(feature_size=80), _Tok(), mel_device="cuda")
+    ba = pa(text, audio=w, sampling_rate=16000)
+    assert ba["audio_values"].is_cuda and tuple(ba["audio_values"].shape) == (2, 80, 3000)
+    assert ba["audio_lens"].tolist() == [3000, 500] and ba["audio_token_len"].tolist() == [188, 32]
+    ref = oproc.process(text, [w], lambda parts: _Tok()(parts)["input_ids"], 1000, n_mels=80)
+    assert ba["input_ids"].tolist() == ref["input_ids"].tolist()
+    assert np.abs(ba["audio_values"].cpu().numpy() - ref["audio_values"]).max() < 2e-3
+    out_a = model(**{k: v for k, v in ba.items()})
+    pb = UltravoxProcessor(MelSpec(feature_size=80), _Tok(), defer_mel=True)
+    bb = pb(text, audio=w, sampling_rate=16000)
+    assert "audio_values" not in bb and bb["audio_waveforms"].shape == (1, 16000 * 35)
+    out_b = model(**{k: v for k, v in bb.items()})
+    assert rel(out_b.logits, out_a.logits) < 2e-3
+    ref_logits, _ = om.forward(sd, sh, ref_t(ref["input_ids"]), torch.from_numpy(ref["audio_values"]).to(torch.bfloat16).float(),
+                               ref_t(ref["audio_token_start_idx"]), ref_t(ref["audio_lens"]), ref_t(ref["audio_token_len"]),
+                               ref_t(ref["audio_batch_size"]))
+    assert rel(out_a.logits, ref_logits) < 3e-2
+
+
+def ref_t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def test_cfg1_shapes_tiny_whisper_llama_1b_one_second_clip():
+    """BASELINE config 1 shapes (Whisper-tiny + Llama-3.2-1B, 1 s clip): finite logits [1, 20, 128256], parity of the
+    last-position logits with the fp32 oracle."""
+    from oracle import logmel as ol, model as om
+    from ultravox_b200 import ops
+    cfg, model, sd, sh = build("tiny_1b")
+    padded, batch = make_batch(cfg, [16000])
+    assert batch["input_ids"].shape == (1, 20) and batch["audio_token_len"].tolist() == [7]
+    mel = ops.logmel(torch.from_numpy(padded).cuda(), 80)
+    assert tuple(mel.shape) == (1, 80, 100)
+    out = model(audio_values=mel, **{k: v.cuda() for k, v in batch.items()})
+    assert tuple(out.logits.shape) == (1, 20, 128256) and bool(torch.isfinite(out.logits).all())
+    ref, _ = om.forward(sd, sh, batch["input_ids"], mel.cpu().to(torch.bfloat16).float(), batch["audio_token_start_idx"],
+                        batch["audio_lens"], batch["audio_token_len"], batch["audio_batch_size"], last_only=True)
+    got = out.logits[:, -1:].cpu()
+    assert rel(got, ref) < 3e-2 and int(got.argmax(-1)) == int(ref.argmax(-1))

@@ -198,3 +198,72 @@ def test_train_step_reduces_loss():
     tr = AdapterTrainer(model, lr=2e-3)
     losses = [float(tr.train_step(audio_values=mel, **batch)) for _ in range(6)]
     assert all(math.isfinite(l) for l in losses) and losses[-1] < losses[0], losses
+
+
+def test_kl_loss_kernel_matches_torch():
+    from ultravox_b200.losses import kl_distill_loss, kl_distill_loss_bwd
+    R, V, T = 11, 1000, 2.0
+    s = torch.randn(R, V, generator=torch.Generator().manual_seed(1)).cuda() * 3
+    t = torch.randn(R, V, generator=torch.Generator().manual_seed(2)).cuda() * 3
+    is_eot = torch.zeros(R, dtype=torch.bool)
+    is_eot[[4, 10]] = True
+    sf = s.clone().requires_grad_(True)
+    ref = F.kl_div(F.log_softmax(sf / T, -1), F.softmax(t / T, -1), reduction="batchmean") \
+        + 1.0 * F.kl_div(F.log_softmax(sf[is_eot.cuda()] / T, -1), F.softmax(t[is_eot.cuda()] / T, -1), reduction="batchmean")
+    ref.backward()
+    keep = {}
+    loss = kl_distill_loss(s, t, is_eot, T, 1.0, keep=keep)
+    assert abs(float(loss) - float(ref)) < 1e-4 * max(1.0, abs(float(ref)))
+    assert rel(kl_distill_loss_bwd(keep), sf.grad.to(BF)) < 2e-3
+
+
+def test_kl_training_step_and_forward_loss_match_oracle():
+    """Reference default objective (meta_config.yaml:5-6): KL to the text-only teacher, ref ultravox_model.py:202-257."""
+    from oracle import model as om
+    from ultravox_b200 import ops
+    from ultravox_b200.config import LossConfig, LossFunction
+    from ultravox_b200.training import AdapterTrainer
+    cfg, model, padded, batch = _setup([16000, 16000 + 77])
+    model.set_loss_config(LossConfig(loss_function=LossFunction.KL_Divergence))
+    mel = ops.logmel(torch.from_numpy(padded).cuda(), cfg.audio_config.num_mel_bins)
+    g = torch.Generator().manual_seed(11)
+    B = batch["input_ids"].shape[0]
+    alt_ids = torch.cat([torch.randint(0, cfg.vocab_size, (B, 12), generator=g), batch["input_ids"][:, -5:]], 1)
+    alt_labels = alt_ids.clone()
+    alt_labels[:, :-5] = -100
+    tr = AdapterTrainer(model, lr=1e-3)
+    loss = tr.forward_backward(audio_values=mel, alt_input_ids=alt_ids, alt_labels=alt_labels, **batch)
+    # oracle: student / teacher logits in fp32, torch kl_div exactly as the reference composes it
+    sd, sh = om.state_dict_fp32(model), om.shapes_from_config(cfg)
+    names = ["multi_modal_projector." + n + ".weight" for n in ("ln_pre", "linear_1", "ln_mid", "linear_2")]
+    for n in names:
+        sd[n] = sd[n].clone().requires_grad_(True)
+    s_logits, _ = om.forward(sd, sh, batch["input_ids"], mel.cpu().to(BF).float(), batch["audio_token_start_idx"],
+                             batch["audio_lens"], batch["audio_token_len"], batch["audio_batch_size"])
+    with torch.no_grad():
+        t_logits = om.llama_forward(sd, sh, sd["language_model.model.embed_tokens.weight"][alt_ids])
+
+    def masks(lab):
+        lm_ = lab != -100
+        pm = torch.zeros_like(lm_)
+        pm[:, :-1] = lm_[:, 1:]
+        em = torch.zeros_like(pm)
+        for i in range(lab.shape[0]):
+            pos = torch.where(pm[i])[0]
+            em[i, pos[-1]] = True
+        return pm, em
+    pm, em = masks(batch["labels"])
+    apm, aem = masks(alt_labels)
+    T = 2.0
+    ref = F.kl_div(F.log_softmax(s_logits[pm] / T, -1), F.softmax(t_logits[apm] / T, -1), reduction="batchmean") \
+        + F.kl_div(F.log_softmax(s_logits[em] / T, -1), F.softmax(t_logits[aem] / T, -1), reduction="batchmean")
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 5e-2 * max(1e-3, abs(float(ref))) + 2e-4, (float(loss), float(ref))
+    got = tr.grad_view("linear_2")
+    cos = float(F.cosine_similarity(got.float().cpu().flatten(), sd[names[3]].grad.flatten(), dim=0))
+    assert cos > 0.98, cos
+    # API parity: model.forward in training mode returns the KL loss too
+    model.train()
+    out = model(audio_values=mel, alt_input_ids=alt_ids, alt_labels=alt_labels, **{k: v for k, v in batch.items()})
+    model.eval()
+    assert abs(float(out.loss) - float(loss)) < 1e-2 * max(1e-3, abs(float(loss))) + 1e-4

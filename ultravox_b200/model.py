@@ -323,6 +323,28 @@ class UltravoxModel(nn.Module):
             a = ops.rmsnorm(a, pj.ln_post.weight, 1e-6)
         return a
 
+    def mel_chunks_from_waveforms(self, audio_waveforms: torch.Tensor, audio_num_frames: torch.Tensor,
+                                  context: int = 3000) -> torch.Tensor:
+        """Zero-padded waveforms [B, L] (what ``UltravoxProcessor(defer_mel=True)`` hands over) -> time-major mel chunks
+        [N, T+2, n_mels] bf16 with guard rows, chunked exactly like ``_chunk_and_pad_audio`` (ref processing :153-215):
+        the log-mel (with its per-CLIP max) is computed once per clip on the GPU, then cut into <= ``context``-frame pieces;
+        continuation chunks are zero-padded to ``context``, first chunks keep the batch width."""
+        from .processing import frame_chunks
+        dev = self.device
+        waves = audio_waveforms.to(dev, torch.float32, non_blocking=True)
+        n_mels = self.audio_tower.n_mels
+        tm = ops.logmel(waves, n_mels, want_f32=False, want_tm=True)            # [B, Tfull+2, n_mels]
+        t_full = tm.shape[1] - 2
+        plan, _ = frame_chunks(audio_num_frames.tolist(), context)
+        if len(plan) == tm.shape[0] and t_full <= context:
+            return tm                                                             # one chunk per clip: nothing to cut
+        width = context if any(p[3] for p in plan) else min(t_full, context)
+        out = torch.zeros(len(plan), width + 2, n_mels, dtype=BF16, device=dev)
+        for i, (clip, off, _, cont) in enumerate(plan):
+            n = min(width, t_full - off)
+            out[i, 1:1 + n] = tm[clip, 1 + off:1 + off + n]
+        return out
+
     def _prepare_audio_embeds(self, input_ids, audio_values=None, audio_token_start_idx=None, audio_lens=None,
                               audio_token_len=None, audio_batch_size=None, audio_tm=None) -> torch.Tensor:
         """Embedding gather + audio splice (ref :354-396).  Returns the spliced ``inputs_embeds`` [B, S, D]."""
@@ -415,13 +437,18 @@ class UltravoxModel(nn.Module):
                 audio_lens: Optional[torch.Tensor] = None, audio_token_len: Optional[torch.Tensor] = None,
                 audio_batch_size: Optional[torch.Tensor] = None, past_key_values: Optional[KVCache] = None,
                 alt_input_ids=None, alt_attention_mask=None, alt_labels=None, logits_to_keep: int = 0,
+                audio_waveforms: Optional[torch.Tensor] = None, audio_num_frames: Optional[torch.Tensor] = None,
                 **kwargs) -> CausalLMOutputWithPast:
         """Same signature and semantics as the reference ``forward`` (ref :277-352).  ``logits_to_keep=1`` computes
         only the last position's logits (the TTFT path, hf:modeling_llama.py:485-491)."""
         dev = self.device
         input_ids = input_ids.to(dev)
         if inputs_embeds is None:
-            if audio_values is not None and len(audio_values) > 0:
+            if audio_waveforms is not None and len(audio_waveforms) > 0:
+                tm = self.mel_chunks_from_waveforms(audio_waveforms, audio_num_frames)
+                inputs_embeds = self._prepare_audio_embeds(input_ids, None, audio_token_start_idx, audio_lens,
+                                                           audio_token_len, audio_batch_size, audio_tm=tm)
+            elif audio_values is not None and len(audio_values) > 0:
                 inputs_embeds = self._prepare_audio_embeds(input_ids, audio_values, audio_token_start_idx, audio_lens,
                                                            audio_token_len, audio_batch_size)
             else:
@@ -442,7 +469,27 @@ class UltravoxModel(nn.Module):
         if labels is not None:
             from .losses import causal_lm_loss
             loss = causal_lm_loss(logits, labels.to(dev), self.config.ignore_index)
+        if self.training and self.loss_config.loss_function == LossFunction.KL_Divergence:
+            loss = self._compute_kl_loss(logits, labels, alt_input_ids, alt_labels)
         return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=past_key_values)
+
+    def _compute_kl_loss(self, logits: torch.Tensor, labels, alt_input_ids, alt_labels) -> torch.Tensor:
+        """ref :202-257: teacher = this LLM on the text-only ``alt_*`` twin (no grad), KL at ``kl_temperature`` on the
+        prediction rows + ``eot_loss_weight`` x KL on the EOT rows."""
+        from .losses import kl_distill_loss, prediction_rows
+        if labels is None or alt_labels is None or alt_input_ids is None:
+            raise ValueError("labels must be provided")
+        dev = self.device
+        rows, is_eot = prediction_rows(labels, self.config.ignore_index)
+        t_rows, _ = prediction_rows(alt_labels, self.config.ignore_index)
+        V = logits.shape[-1]
+        student = logits.reshape(-1, V).index_select(0, rows.to(dev)).contiguous()
+        with torch.no_grad():
+            emb = ops.embed_splice(alt_input_ids.to(dev), self.language_model.model.embed_tokens.weight, None, None)
+            hid = self.llama_hidden(emb).view(-1, emb.shape[-1])
+            teacher = ops.linear(ops.gather_rows(hid, t_rows.to(dev, torch.int32)), self.language_model.lm_head.weight,
+                                 out_dtype=torch.float32)
+        return kl_distill_loss(student, teacher, is_eot, self.loss_config.kl_temperature, self.loss_config.eot_loss_weight)
 
     @torch.no_grad()
     def generate(self, input_ids: torch.Tensor, audio_values: Optional[torch.Tensor] = None,

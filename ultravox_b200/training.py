@@ -21,6 +21,7 @@ import torch
 
 from . import ops
 from .losses import causal_lm_loss, causal_lm_loss_bwd
+from .config import LossFunction
 from .model import BF16, UltravoxModel
 
 
@@ -57,7 +58,8 @@ class AdapterTrainer:
 
     # -- forward + backward --------------------------------------------------------------------------
     def forward_backward(self, input_ids, audio_values, audio_token_start_idx, audio_lens, audio_token_len,
-                         audio_batch_size, labels, audio_tm: Optional[torch.Tensor] = None) -> torch.Tensor:
+                         audio_batch_size, labels, audio_tm: Optional[torch.Tensor] = None, alt_input_ids=None,
+                         alt_labels=None, alt_attention_mask=None) -> torch.Tensor:
         """Accumulates d(loss)/d(projector) into ``self.grad`` (zeroed first) and returns the loss (device scalar).
         Unpadded batches of equal length (the cfg3 synthetic workload); labels follow the HF convention."""
         m, cfg = self.model, self.model.config
@@ -121,10 +123,26 @@ class AdapterTrainer:
         hn_sel = ops.gather_rows(hn, rows_dev)
         logits = ops.linear(hn_sel, lm.lm_head.weight, out_dtype=torch.float32)        # [R, V]
         keep: dict = {}
-        loss = causal_lm_loss(logits, tgt, cfg.ignore_index, keep=keep, shift=False)
+        if m.loss_config.loss_function == LossFunction.KL_Divergence:
+            # teacher = the same frozen LLM on the text-only twin of the sample (ref ultravox_model.py:202-226), no grad
+            if alt_input_ids is None or alt_labels is None:
+                raise ValueError("labels must be provided")
+            from .losses import kl_distill_loss, kl_distill_loss_bwd, prediction_rows
+            t_rows, _ = prediction_rows(alt_labels, cfg.ignore_index)
+            _, is_eot = prediction_rows(labels, cfg.ignore_index)
+            if t_rows.numel() != rows.numel():
+                raise ValueError("student and teacher must predict the same number of tokens for the KL loss")
+            alt_ids = alt_input_ids.to(dev)
+            t_emb = ops.embed_splice(alt_ids, lm.model.embed_tokens.weight, None, None)
+            t_hid = m.llama_hidden(t_emb).view(-1, Dm)
+            t_logits = ops.linear(ops.gather_rows(t_hid, t_rows.to(dev, torch.int32)), lm.lm_head.weight, out_dtype=torch.float32)
+            loss = kl_distill_loss(logits, t_logits, is_eot, m.loss_config.kl_temperature, m.loss_config.eot_loss_weight, keep=keep)
+            dlogits = kl_distill_loss_bwd(keep)
+        else:
+            loss = causal_lm_loss(logits, tgt, cfg.ignore_index, keep=keep, shift=False)
+            dlogits = causal_lm_loss_bwd(keep)                                         # [R, V] bf16
 
         # ---- backward through the head and the frozen LLM (data gradients only)
-        dlogits = causal_lm_loss_bwd(keep)                                             # [R, V] bf16
         d_hn = torch.zeros(B * S, Dm, dtype=BF16, device=dev)
         ops.linear(dlogits, self._lm_head_T, out=d_hn, row_map=rows_dev)
         dh = ops.rmsnorm_bwd(d_hn, h_last, lm.model.norm.weight, eps)
