@@ -135,6 +135,12 @@ typedef struct uvx_attn_args {
   float* lse;                       /* optional [B, Hq, Sq] fp32: log-sum-exp of the scaled scores (training) */
 } uvx_attn_args;
 int uvx_attention(const uvx_attn_args* args, uvx_stream_t stream);
+/* Whisper-encoder specialisation on tcgen05 tensor cores (head_dim 64, Sq == Skv, non-causal + key-length / block-causal
+ * masks): qkv is the fused projection [B*S, row_stride] with head h's q / k / v at columns q_col + 64h, k_col + 64h,
+ * v_col + 64h; output o[b*S + i, 64h .. 64h+63] (row stride o_rs).  Same math as uvx_attention.                      */
+int uvx_attention_enc_tc(const void* qkv, int64_t row_stride, int64_t B, int64_t S, int64_t H, int64_t q_col, int64_t k_col,
+                         int64_t v_col, void* o, int64_t o_rs, const int32_t* kv_len, int32_t block, float scale,
+                         uvx_stream_t stream);
 
 /* RoPE on the q and k sections of a fused [rows, (Hq + 2*Hkv) * D] projection, in place
  * (hf:modeling_llama.py:124-168; cos/sin tables [max_pos, D/2] fp32 built by the host exactly like

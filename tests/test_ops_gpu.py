@@ -186,6 +186,23 @@ def test_attention(ops, B, Hq, Hkv, S, D, causal, block, ragged):
     assert rel(out, ref) < 3e-3  # P is rounded to bf16 before PV (as in every flash kernel)
 
 
+@pytest.mark.parametrize("B,H,S,block,ragged", [(1, 2, 128, 0, False), (1, 3, 256, 0, False), (2, 6, 50, 0, True),
+                                                 (1, 20, 1500, 0, False), (2, 4, 300, 100, True), (3, 2, 700, 0, True)])
+def test_attention_encoder_tcgen05(ops, B, H, S, block, ragged):
+    """tcgen05 / TMEM encoder attention against fp32 math and against the mma.sync kernel."""
+    D = 64
+    qkv = rnd(B * S, 3 * H * D, seed=3)
+    kv_len = torch.tensor([S, max(1, S // 3), S - 1][:B], dtype=torch.int32).cuda() if ragged else None
+    out = ops.attention_encoder_tc(qkv, B, S, H, D ** -0.5, kv_len, block)
+    torch.cuda.synchronize()
+    t = qkv.view(B, S, 3 * H, D).permute(0, 2, 1, 3)
+    ref = _attn_ref(t[:, :H], t[:, H:2 * H], t[:, 2 * H:], D ** -0.5, False, kv_len, block)
+    ref = ref.permute(0, 2, 1, 3).reshape(B * S, H * D)
+    assert rel(out, ref) < 3e-3, rel(out, ref)
+    other = ops.attention_fused_qkv(qkv, B, S, H, H, D, D ** -0.5, False, kv_len, block)
+    assert rel(out, other.float()) < 3e-3
+
+
 def test_rope(ops):
     Hq, Hkv, D, S, B = 8, 2, 128, 40, 2
     qkv = rnd(B * S, (Hq + 2 * Hkv) * D, seed=1)

@@ -301,7 +301,10 @@ class UltravoxModel(nn.Module):
             sa = layer.self_attn
             ops.layernorm(h, layer.self_attn_layer_norm.weight, layer.self_attn_layer_norm.bias, 1e-5, out=x)
             ops.linear(x, sa.qkv_w, sa.qkv_b, out=qkv)
-            ops.attention_fused_qkv(qkv, N, T2, H, H, hd, hd ** -0.5, False, kv_len, block, out=att)
+            if hd == 64:
+                ops.attention_encoder_tc(qkv, N, T2, H, hd ** -0.5, kv_len, block, out=att)
+            else:
+                ops.attention_fused_qkv(qkv, N, T2, H, H, hd, hd ** -0.5, False, kv_len, block, out=att)
             ops.linear(att, sa.out_proj.weight, sa.out_proj.bias, residual=h, out=h)
             ops.layernorm(h, layer.final_layer_norm.weight, layer.final_layer_norm.bias, 1e-5, out=x)
             ops.linear(x, layer.fc1.weight, layer.fc1.bias, act=ops.ACT_GELU, out=ff)

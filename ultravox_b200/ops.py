@@ -211,6 +211,19 @@ def attention_fused_qkv(qkv: torch.Tensor, B: int, S: int, Hq: int, Hkv: int, D:
                      (rs, S * rs, rs, S * rs, rs, S * rs, Hq * D, S * Hq * D), scale, causal, kv_len, block)
 
 
+def attention_encoder_tc(qkv: torch.Tensor, B: int, S: int, H: int, scale: float, kv_len: Optional[torch.Tensor] = None,
+                         block: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """tcgen05 encoder attention over a fused [B*S, 3*H*64] q|k|v projection (head_dim 64)."""
+    _cuda(qkv, BF16, "qkv")
+    d = H * 64
+    assert qkv.shape[-1] == 3 * d and qkv.stride(-1) == 1
+    if out is None:
+        out = torch.empty(B * S, d, dtype=BF16, device=qkv.device)
+    check(lib().uvx_attention_enc_tc(qkv.data_ptr(), qkv.stride(-2), B, S, H, 0, d, 2 * d, out.data_ptr(), out.stride(-2),
+                                     _p(kv_len), int(block), float(scale), _stream()), "uvx_attention_enc_tc")
+    return out
+
+
 # ------------------------------------------------------------------------------------------ rope / swiglu
 def rope_tables(inv_freq: torch.Tensor, max_pos: int, device) -> tuple[torch.Tensor, torch.Tensor]:
     """cos/sin [max_pos, D/2] fp32 exactly as LlamaRotaryEmbedding computes them (fp32 outer product)."""
