@@ -6,8 +6,9 @@
 //   warp 1        single-thread MMA issuer:  S_t = Q_t K_j^T  (UMMA 128x128x16, fp32 in TMEM) and
 //                 O_t += P_t V_j  (UMMA 128x64x16, A = P_t from shared memory, B = V_j taken MN-major as TMA left it).
 //   warps 2-5     softmax warpgroup of query tile 0; warps 6-9 of query tile 1: one thread per query row (= TMEM lane),
-//                 so row max / sum need no shuffles.  Two TMEM passes per tile (max, then exp2 + bf16 P written straight
-//                 into the swizzled K-major layout the next MMA reads), O rescaled in TMEM (tcgen05.ld / st).
+//                 so row max / sum need no shuffles.  One TMEM pass per tile (the 128 scores of a row live in registers),
+//                 lazy rescaling (the reference max only moves when it grows by > 2^8), ex2.approx, bf16 P written straight
+//                 into the swizzled K-major layout the next MMA reads; O rescaled in TMEM (tcgen05.ld / st) only when needed.
 // The two query tiles ping-pong: while one warpgroup does its softmax the tensor core works for the other.
 #include "uvx_common.cuh"
 
@@ -228,53 +229,60 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p) 
     const int qi = q0 + t * kQT + row;                       // global query index
     const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
     uint8_t* sPt = smem + AtSmem::kP + t * (2 * kQT * 64 * 2);
-    float m_run = -INFINITY, l_run = 0.f;
+    // Running reference maximum m_ref (raw score units) and row sum l relative to it.  The reference only moves when the
+    // tile maximum exceeds it by more than 2^8 in the exponent (lazy rescaling): P stays <= 256, well inside bf16 / fp32
+    // range, and the TMEM read-modify-write of O is skipped for almost every tile.
+    float m_ref = -INFINITY, l_run = 0.f;
+    const float kLazy = 8.0f;
     for (int j = 0; j < n_tiles; ++j) {
       at_wait(&s_full[t], j & 1);
       at_fence_after();
-      // pass 1: row maximum over the 128 keys of this tile (masked)
-      float tmax = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < kKT / 32; ++c) {
-        uint32_t raw[32];
-        at_ld32(tS[t] + lane_sel + c * 32, raw);
-        at_wait_ld();
+      // one TMEM pass: the whole 128-key score row of this query lives in registers
+      uint32_t raw[kKT];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int key = j * kKT + c * 32 + i;
+      for (int c = 0; c < kKT / 32; ++c) at_ld32(tS[t] + lane_sel + c * 32, raw + c * 32);
+      at_wait_ld();
+      const bool need_mask = (j * kKT + kKT > kv_end) || (p.block > 0);  // CTA-uniform
+      if (need_mask) {
+#pragma unroll
+        for (int i = 0; i < kKT; ++i) {
+          const int key = j * kKT + i;
           bool ok = key < kv_end;
           if (p.block > 0) ok = ok && (key / p.block <= qi / p.block);
-          tmax = fmaxf(tmax, ok ? __uint_as_float(raw[i]) : -INFINITY);
+          if (!ok) raw[i] = 0xff800000u;  // -inf
         }
       }
-      const float m_new = fmaxf(m_run, tmax);
-      const float m_ref = (m_new == -INFINITY) ? 0.f : m_new;
-      const float corr = exp2f((m_run - m_ref) * p.scale_log2);
+      float tmax = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < kKT; ++i) tmax = fmaxf(tmax, __uint_as_float(raw[i]));
+      // lazy reference update (warp-uniform decision so that the TMEM ld/st below stay converged)
+      const bool grow = (tmax - m_ref) * p.scale_log2 > kLazy;  // also true for the first tile (m_ref = -inf)
+      const bool any_grow = __any_sync(0xffffffffu, grow) != 0;
+      float corr = 1.f;
+      if (grow) {
+        const float m_new = (tmax == -INFINITY) ? m_ref : tmax;
+        corr = (m_ref == -INFINITY) ? 0.f : exp2f((m_ref - m_new) * p.scale_log2);
+        m_ref = m_new;
+      }
+      const float mb = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;
       // P_t(j-1) must have been consumed (and O_t updated) before P_t smem / O_t are touched again
       if (j > 0) {
         at_wait(&pv_done[t], (j - 1) & 1);
         at_fence_after();
       }
-      // pass 2: P = exp2((s - m) * scale) -> bf16 -> swizzled K-major smem; row sum
       float psum = 0.f;
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < kKT / 32; ++c) {
-        uint32_t raw[32];
-        at_ld32(tS[t] + lane_sel + c * 32, raw);
-        at_wait_ld();
         uint32_t packed[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float pv[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int key = j * kKT + c * 32 + i + e;
-            bool ok = key < kv_end;
-            if (p.block > 0) ok = ok && (key / p.block <= qi / p.block);
-            pv[e] = ok ? exp2f((__uint_as_float(raw[i + e]) - m_ref) * p.scale_log2) : 0.f;
-            psum += pv[e];
-          }
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[0], pv[1]);
+          float e0, e1;
+          const float a0 = fmaf(__uint_as_float(raw[c * 32 + i]), p.scale_log2, -mb);
+          const float a1 = fmaf(__uint_as_float(raw[c * 32 + i + 1]), p.scale_log2, -mb);
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+          psum += e0 + e1;
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
           packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
         }
         // 32 keys = 4 chunks of 16 bytes; key column kc = c*32 .. : sub-tile (kc / 64), chunk ((kc % 64) / 8) ^ (row & 7)
@@ -286,17 +294,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p) 
         }
       }
       l_run = l_run * corr + psum;
-      m_run = m_new;
-      // rescale the running output in TMEM
-      if (j > 0) {
+      // rescale the running output in TMEM only when some row of this warp moved its reference
+      if (j > 0 && any_grow) {
 #pragma unroll 1
         for (int c = 0; c < kHD / 32; ++c) {
-          uint32_t raw[32];
-          at_ld32(tO[t] + lane_sel + c * 32, raw);
+          uint32_t o32[32];
+          at_ld32(tO[t] + lane_sel + c * 32, o32);
           at_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * corr);
-          at_st32(tO[t] + lane_sel + c * 32, raw);
+          for (int i = 0; i < 32; ++i) o32[i] = __float_as_uint(__uint_as_float(o32[i]) * corr);
+          at_st32(tO[t] + lane_sel + c * 32, o32);
         }
         at_wait_st();
       }
