@@ -131,7 +131,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p) 
   uint64_t* s_full = kv_empty + kKvStages;    // [2]  MMA -> softmax: S_t ready
   uint64_t* p_full = s_full + 2;              // [2]  softmax -> MMA: P_t written, S_t consumed, O_t rescaled
   uint64_t* pv_done = p_full + 2;             // [2]  MMA -> softmax: O_t += P_t V done (P_t smem and O_t reusable)
-  uint32_t* tmem_slot = (uint32_t*)(pv_done + 2);
+  uint64_t* s_free = pv_done + 2;             // [2]  softmax -> MMA: S_t is in registers, the TMEM buffer may be overwritten
+  uint32_t* tmem_slot = (uint32_t*)(s_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * (2 * kQT), h = blockIdx.y, b = blockIdx.z;
@@ -150,6 +151,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p) 
       at_mbar_init(&s_full[t], 1);
       at_mbar_init(&p_full[t], 128);
       at_mbar_init(&pv_done[t], 1);
+      at_mbar_init(&s_free[t], 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -202,11 +204,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p) 
         const int s = j % kKvStages;
         const bool more = j + 1 < n_tiles;
         if (more) {
+          // next tile's scores as soon as the softmax warps have pulled S_t(j) into registers: this runs under their
+          // exp / pack work instead of after it (otherwise the two warpgroups and the tensor core move in lockstep)
           at_wait(&kv_full[(j + 1) % kKvStages], ((j + 1) / kKvStages) & 1);
-          at_fence_after();
+          for (int t = 0; t < 2; ++t) {
+            at_wait(&s_free[t], j & 1);
+            at_fence_after();
+            issue_S(t, (j + 1) % kKvStages);
+          }
         }
         for (int t = 0; t < 2; ++t) {
-          at_wait(&p_full[t], j & 1);  // P_t(j) in smem, S_t free, O_t rescaled
+          at_wait(&p_full[t], j & 1);  // P_t(j) in smem, O_t rescaled
           at_fence_after();
           const uint64_t dv = at_desc_mnmajor(sV + s * (kKT * kHD * 2));
 #pragma unroll
@@ -216,7 +224,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p) 
             at_mma(tO[t], dp, dv + (uint64_t)(k * (16 * 128 >> 4)), idO, (j > 0 || k > 0) ? 1u : 0u);
           }
           at_commit(&pv_done[t]);
-          if (more) issue_S(t, (j + 1) % kKvStages);
         }
         at_commit(&kv_empty[s]);  // K_j / V_j no longer needed once everything issued so far has completed
       }
@@ -242,6 +249,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p) 
 #pragma unroll
       for (int c = 0; c < kKT / 32; ++c) at_ld32(tS[t] + lane_sel + c * 32, raw + c * 32);
       at_wait_ld();
+      at_fence_before();
+      at_arrive(&s_free[t]);  // the tensor core may start S_t(j+1) now
       const bool need_mask = (j * kKT + kKT > kv_end) || (p.block > 0);  // CTA-uniform
       if (need_mask) {
 #pragma unroll
