@@ -4,11 +4,11 @@
 // One CTA = 256 queries (two 128-row tiles) of one (clip, head); K/V stream through a TMA ring of 128-key tiles.
 //   warp 0        TMA producer: Q once (2 x [128 x 64]), then K_j / V_j tiles (128B swizzle, zero-filled past the clip).
 //   warp 1        single-thread MMA issuer:  S_t = Q_t K_j^T  (UMMA 128x128x16, fp32 in TMEM) and
-//                 O_t += P_t V_j  (UMMA 128x64x16, A = P_t from shared memory, B = V_j taken MN-major as TMA left it).
+//                 O_t += P_t V_j  (UMMA 128x64x16, A = P_t from TENSOR memory (TS form), B = V_j MN-major as TMA left it).
 //   warps 2-5     softmax warpgroup of query tile 0; warps 6-9 of query tile 1: one thread per query row (= TMEM lane),
 //                 so row max / sum need no shuffles.  One TMEM pass per tile (the 128 scores of a row live in registers),
-//                 lazy rescaling (the reference max only moves when it grows by > 2^8), ex2.approx, bf16 P written straight
-//                 into the swizzled K-major layout the next MMA reads; O rescaled in TMEM (tcgen05.ld / st) only when needed.
+//                 lazy rescaling (the reference max only moves when it grows by > 2^8), ex2.approx, bf16 P stored with tcgen05.st
+//                 into its own TMEM columns (no shared-memory round trip); O rescaled in TMEM only when needed.
 // The two query tiles ping-pong: while one warpgroup does its softmax the tensor core works for the other.
 #include "uvx_common.cuh"
 
@@ -17,7 +17,7 @@ namespace uvx {
 static constexpr int kQT = 128;         // rows per query tile
 static constexpr int kKT = 128;         // keys per K/V tile
 static constexpr int kHD = 64;          // head dim
-static constexpr int kKvStages = 3;
+static constexpr int kKvStages = 4;
 static constexpr int kAtThreads = 320;  // 10 warps
 
 struct AttnTcParams {
@@ -71,6 +71,17 @@ __device__ __forceinline__ void at_mma(uint32_t d, uint64_t a, uint64_t b, uint3
       "l"(a), "l"(b), "r"(idesc), "r"(acc)
       : "memory");
 }
+// A operand from tensor memory (TS form): P never touches shared memory
+__device__ __forceinline__ void at_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d),
+      "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void at_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(at_smem(bar)) : "memory");
 }
@@ -116,8 +127,8 @@ struct AtSmem {
   static constexpr int kQ = 0;                                   // 2 x 16 KB
   static constexpr int kK = kQ + 2 * kQT * kHD * 2;              // stages x 16 KB
   static constexpr int kV = kK + kKvStages * kKT * kHD * 2;      // stages x 16 KB
-  static constexpr int kP = kV + kKvStages * kKT * kHD * 2;      // 2 query tiles x 2 sub-tiles x 16 KB
-  static constexpr int kBar = kP + 2 * 2 * kQT * 64 * 2;
+  static constexpr int kP = kV + kKvStages * kKT * kHD * 2;      // output staging: 2 query tiles x 16 KB
+  static constexpr int kBar = kP + 2 * kQT * kHD * 2;
   static constexpr int kTotal = kBar + 256 + 1024;
 };
 
@@ -164,9 +175,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p) 
   __syncthreads();
   at_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S_0 [0,128), S_1 [128,256), O_0 [256,320), O_1 [320,384)
+  // TMEM columns: S_0 [0,128), S_1 [128,256), O_0 [256,320), O_1 [320,384), P_0 [384,448), P_1 [448,512) (bf16 pairs)
   const uint32_t tS[2] = {tmem_base, tmem_base + 128};
   const uint32_t tO[2] = {tmem_base + 256, tmem_base + 320};
+  const uint32_t tP[2] = {tmem_base + 384, tmem_base + 448};
 
   if (warp == 0) {
     if (lane == 0) {
@@ -187,7 +199,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p) 
       constexpr uint32_t idS = at_idesc(kKT, false);
       constexpr uint32_t idO = at_idesc(kHD, true);
       const uint32_t sQ = at_smem(smem + AtSmem::kQ), sK = at_smem(smem + AtSmem::kK), sV = at_smem(smem + AtSmem::kV),
-                     sP = at_smem(smem + AtSmem::kP);
+                     sP = 0;
+      (void)sP;
       auto issue_S = [&](int t, int stage) {
         const uint64_t da = at_desc_kmajor(sQ + t * (kQT * kHD * 2));
         const uint64_t db = at_desc_kmajor(sK + stage * (kKT * kHD * 2));
@@ -219,9 +232,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p) 
           const uint64_t dv = at_desc_mnmajor(sV + s * (kKT * kHD * 2));
 #pragma unroll
           for (int k = 0; k < kKT / 16; ++k) {
-            // P: two K-major [128 x 64] sub-tiles; 16 keys = 32 B inside a sub-tile.  V: 16 keys = 16 rows of 128 B.
-            const uint64_t dp = at_desc_kmajor(sP + t * (2 * kQT * 64 * 2) + (k >> 2) * (kQT * 64 * 2)) + (uint64_t)(2 * (k & 3));
-            at_mma(tO[t], dp, dv + (uint64_t)(k * (16 * 128 >> 4)), idO, (j > 0 || k > 0) ? 1u : 0u);
+            // P_t sits in TMEM as packed bf16 pairs: 16 keys = 8 columns per k-step.  V: 16 keys = 16 rows of 128 B.
+            at_mma_ts(tO[t], tP[t] + (uint32_t)(k * 8), dv + (uint64_t)(k * (16 * 128 >> 4)), idO, (j > 0 || k > 0) ? 1u : 0u);
           }
           at_commit(&pv_done[t]);
         }
@@ -235,7 +247,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p) 
     const int row = qd * 32 + lane;                          // row inside the query tile
     const int qi = q0 + t * kQT + row;                       // global query index
     const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
-    uint8_t* sPt = smem + AtSmem::kP + t * (2 * kQT * 64 * 2);
+    uint8_t* sPt = smem + AtSmem::kP + t * (kQT * kHD * 2);  // output staging only (P lives in TMEM)
     // Running reference maximum m_ref (raw score units) and row sum l relative to it.  The reference only moves when the
     // tile maximum exceeds it by more than 2^8 in the exponent (lazy rescaling): P stays <= 256, well inside bf16 / fp32
     // range, and the TMEM read-modify-write of O is skipped for almost every tile.
@@ -281,26 +293,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p) 
       }
       float psum = 0.f;
 #pragma unroll
-      for (int c = 0; c < kKT / 32; ++c) {
-        uint32_t packed[16];
+      for (int h2i = 0; h2i < 2; ++h2i) {
+        uint32_t packed[32];  // 64 keys -> 32 packed bf16 pairs -> 32 TMEM columns
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
+        for (int i = 0; i < 64; i += 2) {
           float e0, e1;
-          const float a0 = fmaf(__uint_as_float(raw[c * 32 + i]), p.scale_log2, -mb);
-          const float a1 = fmaf(__uint_as_float(raw[c * 32 + i + 1]), p.scale_log2, -mb);
+          const float a0 = fmaf(__uint_as_float(raw[h2i * 64 + i]), p.scale_log2, -mb);
+          const float a1 = fmaf(__uint_as_float(raw[h2i * 64 + i + 1]), p.scale_log2, -mb);
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
           psum += e0 + e1;
           __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
           packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
         }
-        // 32 keys = 4 chunks of 16 bytes; key column kc = c*32 .. : sub-tile (kc / 64), chunk ((kc % 64) / 8) ^ (row & 7)
-        uint8_t* sub = sPt + (c >> 1) * (kQT * 64 * 2) + row * 128;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int chunk = ((c & 1) * 4 + g) ^ (row & 7);
-          *reinterpret_cast<uint4*>(sub + chunk * 16) = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
-        }
+        at_st32(tP[t] + lane_sel + h2i * 32, packed);
       }
       l_run = l_run * corr + psum;
       // rescale the running output in TMEM only when some row of this warp moved its reference
@@ -314,9 +320,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p) 
           for (int i = 0; i < 32; ++i) o32[i] = __float_as_uint(__uint_as_float(o32[i]) * corr);
           at_st32(tO[t] + lane_sel + c * 32, o32);
         }
-        at_wait_st();
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P stores -> visible to the tensor core's smem reads
+      at_wait_st();  // P (and any O rescale) are in tensor memory
       at_fence_before();
       at_arrive(&p_full[t]);
     }
