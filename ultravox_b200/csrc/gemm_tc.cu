@@ -268,7 +268,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n0 = tn_idx * BN;
         const int kb_begin = split * p.kb_per_split;
         const int kb_end = min(num_kb, kb_begin + p.kb_per_split);
-        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+        // every CTA walks K starting at a different k-block (and wraps): at M <= 256 all CTAs read the SAME activation
+        // tile, and in lockstep they would all hit the same L2 lines at the same time
+        const int nk = kb_end - kb_begin;
+        const int rot = (int)(((unsigned)tile * 7u + (unsigned)split * 3u) % (unsigned)nk);
+        for (int i = 0; i < nk; ++i, ++it) {
+          const int kb = kb_begin + (i + rot < nk ? i + rot : i + rot - nk);
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -504,7 +509,9 @@ gemm_tc2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int b = tm_idx / p.m_tiles;
         const int m0 = (tm_idx % p.m_tiles) * (2 * kBM) + (int)rank * kBM;
         const int n0 = tn_idx * BN + (int)rank * (BN / 2);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int rot = (int)(((unsigned)tile * 7u) % (unsigned)num_kb);
+        for (int i = 0; i < num_kb; ++i, ++it) {
+          const int kb = i + rot < num_kb ? i + rot : i + rot - num_kb;
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
