@@ -216,8 +216,13 @@ def roofline_pass(model, eng, peaks):
     if llm:
         tt, bb = sum(x[0] for x in llm), sum(x[1] for x in llm)
         peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None
+        try:  # DRAM bytes per launch of the same kernel from the committed ncu capture (profiles/r1_traffic.json)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["dram_bytes_per_launch_avg"]
+        except Exception:
+            pass
         out = {"bound": "hbm", "kernel": "gemm_tc_kernel (Llama prefill GEMMs, M=%d)" % S, "achieved": bb / tt / 1e9,
-               "peak": peak, "unit": "GB/s", "frac": bb / tt / 1e9 / peak, "traffic": None, "launches": len(llm),
+               "peak": peak, "unit": "GB/s", "frac": bb / tt / 1e9 / peak, "traffic": traffic, "launches": len(llm),
                "avg_launch_us": tt / len(llm) * 1e6, "bytes_per_launch_avg": bb / len(llm),
                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                "how": "CUDA events around each launch on the launching stream, eager replay of the step after the timed region"}

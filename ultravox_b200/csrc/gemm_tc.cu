@@ -844,6 +844,7 @@ static void pick_cfg(int64_t rows, int64_t batch, int64_t N, int64_t K, int* cfg
     // weight-streaming regime (LLM prefill at B=1, projector): one CTA tile spans every row, W is read once
     mt = 2;
     bn = (N % 256 == 0 && N / 256 >= sms / 2) ? 256 : (N % 128 == 0 ? 128 : 64);
+    if (bn == 128 && 2 * (N / 128) >= (sms * 3) / 5 && num_kb <= 80) mt = 1;  // enough 128x128 tiles: skip split-K + reduce
   } else {
     // tensor-bound regime (encoder, training): 128-row tiles; 256-wide when that still gives >= ~1.3 waves of tiles
     mt = 1;
