@@ -175,6 +175,17 @@ int uvx_lm_head(const void* h, int64_t B, int64_t h_row_stride, const void* W, i
                 float* logits, uvx_stream_t stream);
 int uvx_argmax(const float* logits, int64_t B, int64_t V, int64_t* out_idx, uvx_stream_t stream);
 
+/* a13 decode step (ref:ultravox/model/ultravox_model.py:398-426 -> HF greedy generate): with one token per stream every
+ * linear layer is a weight-streaming matrix-vector product, y[b, n] = sum_k x[b, k] W[n, k] (+ R[b, n]), 1 <= B <= 8.   */
+int uvx_gemv_bf16(const void* x, int64_t B, int64_t x_row_stride, const void* W, int64_t w_row_stride, int64_t N, int64_t K,
+                  const void* R, int64_t r_row_stride, void* out, int64_t o_row_stride, int out_f32, uvx_stream_t stream);
+/* copy this step's k / v sections of the fused projection into the static KV cache at positions[b] (device index, so
+ * the decode step is capturable in a CUDA graph); cache layout [B, S_max, kv_width]                                    */
+int uvx_kv_append(const void* qkv, int64_t row_stride, int64_t k_col, int64_t v_col, int64_t kv_width, void* k_cache,
+                  void* v_cache, int64_t cache_batch_stride, const int32_t* positions, int64_t B, uvx_stream_t stream);
+/* a[i] += delta (and b[i] += delta when b != NULL): advances the device-side positions / lengths after each step     */
+int uvx_add_i32(int32_t* a, int32_t* b, int64_t n, int32_t delta, uvx_stream_t stream);
+
 /* Shifted causal-LM cross entropy (hf:loss/loss_utils.py:28-67; called through LlamaForCausalLM.forward(labels=)
  * from ref:ultravox/model/ultravox_model.py:328-334).  logits [B*S, V] fp32 (row_stride elements), labels [B, S]
  * un-shifted (the shift and the ignore_index padding happen inside).  row_loss/row_lse [B*S] are kept for the

@@ -249,3 +249,37 @@ def test_cfg1_shapes_tiny_whisper_llama_1b_one_second_clip():
                         batch["audio_lens"], batch["audio_token_len"], batch["audio_batch_size"], last_only=True)
     got = out.logits[:, -1:].cpu()
     assert rel(got, ref) < 3e-2 and int(got.argmax(-1)) == int(ref.argmax(-1))
+
+
+def test_decode_engine_graph_matches_generate():
+    """CUDA-graphed decode (device-side positions, GEMV linears) reproduces model.generate token for token."""
+    from ultravox_b200 import ops
+    from ultravox_b200.engine import DecodeEngine
+    cfg, model, sd, sh = build()
+    padded, batch = make_batch(cfg, [16000, 16000 + 500])
+    mel = ops.logmel(torch.from_numpy(padded).cuda(), sh.n_mels)
+    n_new = 6
+    seq = model.generate(audio_values=mel, max_new_tokens=n_new, **{k: v.cuda() for k, v in batch.items()})
+    S = batch["input_ids"].shape[1]
+    emb = model._prepare_audio_embeds(batch["input_ids"].cuda(), mel, batch["audio_token_start_idx"], batch["audio_lens"],
+                                      batch["audio_token_len"], batch["audio_batch_size"])
+    for use_graph in (False, True):
+        eng = DecodeEngine(model, 2, S + n_new + 2, use_graph=use_graph)
+        toks = [eng.prefill(emb.clone()).clone()]
+        for _ in range(n_new - 1):
+            toks.append(eng.step().view(-1).clone())
+        got = torch.stack(toks, 1)
+        assert torch.equal(got, seq[:, S:]), (use_graph, got.tolist(), seq[:, S:].tolist())
+    assert eng.launches_per_step > 20
+
+
+def test_gemv_matches_gemm():
+    from ultravox_b200 import ops
+    for B, N, K in [(1, 512, 256), (3, 1024, 4096), (8, 256, 14336)]:
+        g = torch.Generator().manual_seed(B)
+        x = torch.randn(B, K, generator=g).bfloat16().cuda()
+        w = (torch.randn(N, K, generator=g) * 0.05).bfloat16().cuda()
+        r = torch.randn(B, N, generator=g).bfloat16().cuda()
+        ref = x.float() @ w.float().T + r.float()
+        assert rel(ops.gemv(x, w, residual=r), ref.to(torch.bfloat16)) < 1e-3
+        assert rel(ops.gemv(x, w, out_dtype=torch.float32), x.float() @ w.float().T) < 1e-5

@@ -132,6 +132,32 @@ __global__ void embed_splice_kernel(const int64_t* __restrict__ ids, const bf16*
   for (int64_t i = lane; i < d / 8; i += 32) d4[i] = s4[i];
 }
 
+// --------------------------------------------------------------------------------- decode-step helpers
+// Append this step's (post-RoPE) k and v rows of the fused projection to the static KV cache at positions[b].
+__global__ void kv_append_kernel(const bf16* __restrict__ qkv, int64_t row_stride, int k_col, int v_col, int kv_width,
+                                 bf16* __restrict__ k_cache, bf16* __restrict__ v_cache, int64_t cache_batch_stride,
+                                 const int32_t* __restrict__ positions, int64_t B) {
+  const int vec = kv_width / 8;
+  const int64_t total = B * vec * 2;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int which = (int)(idx / (B * vec));
+    const int64_t rem = idx % (B * vec);
+    const int64_t b = rem / vec;
+    const int j = (int)(rem % vec);
+    const bf16* src = qkv + b * row_stride + (which ? v_col : k_col) + j * 8;
+    bf16* dst = (which ? v_cache : k_cache) + b * cache_batch_stride + (int64_t)positions[b] * kv_width + j * 8;
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+  }
+}
+
+__global__ void add_i32_kernel(int32_t* __restrict__ a, int32_t* __restrict__ b2, int64_t n, int32_t delta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    a[i] += delta;
+    if (b2) b2[i] += delta;
+  }
+}
+
 }  // namespace uvx
 
 static int rope_launch(void* qkv, int64_t rows, int64_t row_stride, int Hq, int Hkv, int D, const float* cos_tab,
@@ -205,4 +231,23 @@ extern "C" int uvx_embed_splice(const int64_t* input_ids, const void* embed_toke
   embed_splice_kernel<<<(unsigned)((rows + warps - 1) / warps), warps * 32, 0, (cudaStream_t)stream>>>(
       input_ids, (const bf16*)embed_tokens, vocab, (const bf16*)audio_embeds, src, rows, d, (bf16*)out);
   return check_launch("embed_splice_kernel");
+}
+
+extern "C" int uvx_kv_append(const void* qkv, int64_t row_stride, int64_t k_col, int64_t v_col, int64_t kv_width, void* k_cache,
+                             void* v_cache, int64_t cache_batch_stride, const int32_t* positions, int64_t B, uvx_stream_t stream) {
+  using namespace uvx;
+  UVX_REQUIRE(qkv && k_cache && v_cache && positions && B >= 1, "uvx_kv_append: bad arguments");
+  UVX_REQUIRE(kv_width % 8 == 0 && row_stride % 8 == 0 && k_col % 8 == 0 && v_col % 8 == 0 && cache_batch_stride % 8 == 0,
+              "uvx_kv_append: alignment");
+  const int64_t total = B * (kv_width / 8) * 2;
+  kv_append_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)qkv, row_stride, (int)k_col, (int)v_col, (int)kv_width, (bf16*)k_cache, (bf16*)v_cache, cache_batch_stride, positions, B);
+  return check_launch("kv_append_kernel");
+}
+
+extern "C" int uvx_add_i32(int32_t* a, int32_t* b, int64_t n, int32_t delta, uvx_stream_t stream) {
+  using namespace uvx;
+  UVX_REQUIRE(a && n >= 1, "uvx_add_i32: bad arguments");
+  add_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, b, n, delta);
+  return check_launch("add_i32_kernel");
 }

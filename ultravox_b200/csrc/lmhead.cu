@@ -106,6 +106,69 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ 
   }
 }
 
+// Small-batch linear layer (decode, M <= 8): y[b, n] = sum_k x[b, k] W[n, k] (+ R[b, n]); same streaming structure as the
+// LM head - no tensor cores, every weight byte read once at HBM rate.
+template <int B>
+__global__ void __launch_bounds__(kLmWarps * 32) gemv_kernel(const bf16* __restrict__ x, int64_t x_row_stride,
+                                                             const bf16* __restrict__ W, int64_t w_row_stride, int64_t N,
+                                                             int64_t K, const bf16* __restrict__ R, int64_t r_row_stride,
+                                                             void* __restrict__ out, int64_t o_row_stride, int out_f32) {
+  extern __shared__ uint8_t lm_smem[];
+  bf16* xs = reinterpret_cast<bf16*>(lm_smem);  // [B][K]
+  for (int64_t i = threadIdx.x; i < (int64_t)B * K / 8; i += blockDim.x) {
+    const int64_t b = i / (K / 8), j = i % (K / 8);
+    reinterpret_cast<uint4*>(xs)[i] = *reinterpret_cast<const uint4*>(x + b * x_row_stride + j * 8);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * kLmWarps + (threadIdx.x >> 5);
+  const int64_t total_warps = (int64_t)gridDim.x * kLmWarps;
+  const int nvec = (int)(K / 8);
+  for (int64_t n = warp_global; n < N; n += total_warps) {
+    const bf16* wr = W + n * w_row_stride;
+    float acc[B];
+#pragma unroll
+    for (int b = 0; b < B; ++b) acc[b] = 0.f;
+#pragma unroll 4
+    for (int j = lane; j < nvec; j += 32) {
+      const uint4 raw = ld_nc_v4(wr + (int64_t)j * 8);
+      float wv[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(&raw), wv);
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        float hv[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(xs + (int64_t)b * K + (int64_t)j * 8), hv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[b] = fmaf(wv[e], hv[e], acc[b]);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      float sres = warp_sum(acc[b]);
+      if (lane == 0) {
+        if (R) sres += __bfloat162float(R[(int64_t)b * r_row_stride + n]);
+        if (out_f32) reinterpret_cast<float*>(out)[(int64_t)b * o_row_stride + n] = sres;
+        else reinterpret_cast<bf16*>(out)[(int64_t)b * o_row_stride + n] = __float2bfloat16_rn(sres);
+      }
+    }
+  }
+}
+
+template <int B>
+static int launch_gemv(const bf16* x, int64_t xs, const bf16* W, int64_t ws, int64_t N, int64_t K, const bf16* R, int64_t rs,
+                       void* out, int64_t os, int out_f32, cudaStream_t st) {
+  const size_t smem = (size_t)B * K * 2;
+  static bool attr = false;
+  if (!attr && smem > 48 * 1024) {
+    cudaFuncSetAttribute(gemv_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  int64_t blocks = (N + kLmWarps - 1) / kLmWarps;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  gemv_kernel<B><<<(unsigned)blocks, kLmWarps * 32, smem, st>>>(x, xs, W, ws, N, K, R, rs, out, os, out_f32);
+  return check_launch("gemv_kernel");
+}
+
 template <int B>
 static int launch_lm(const bf16* h, int64_t hs, const bf16* W, int64_t V, int64_t d, float* logits, cudaStream_t st) {
   const size_t smem = (size_t)B * d * 2;
@@ -151,6 +214,28 @@ extern "C" int uvx_lm_head(const void* h, int64_t B, int64_t h_row_stride, const
     B -= nb;
   }
   return UVX_OK;
+}
+
+extern "C" int uvx_gemv_bf16(const void* x, int64_t B, int64_t x_row_stride, const void* W, int64_t w_row_stride, int64_t N,
+                             int64_t K, const void* R, int64_t r_row_stride, void* out, int64_t o_row_stride, int out_f32,
+                             uvx_stream_t stream) {
+  using namespace uvx;
+  UVX_REQUIRE(x && W && out, "uvx_gemv_bf16: null pointer");
+  UVX_REQUIRE(B >= 1 && B <= kLmMaxB && K % 8 == 0 && x_row_stride % 8 == 0 && w_row_stride % 8 == 0,
+              "uvx_gemv_bf16: 1 <= B <= %d and K %% 8 == 0 required", kLmMaxB);
+  UVX_REQUIRE((size_t)kLmMaxB * K * 2 <= 200 * 1024, "uvx_gemv_bf16: K too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bf16 *xp = (const bf16*)x, *wp = (const bf16*)W, *rp = (const bf16*)R;
+  switch (B) {
+    case 1: return launch_gemv<1>(xp, x_row_stride, wp, w_row_stride, N, K, rp, r_row_stride, out, o_row_stride, out_f32, st);
+    case 2: return launch_gemv<2>(xp, x_row_stride, wp, w_row_stride, N, K, rp, r_row_stride, out, o_row_stride, out_f32, st);
+    case 3: return launch_gemv<3>(xp, x_row_stride, wp, w_row_stride, N, K, rp, r_row_stride, out, o_row_stride, out_f32, st);
+    case 4: return launch_gemv<4>(xp, x_row_stride, wp, w_row_stride, N, K, rp, r_row_stride, out, o_row_stride, out_f32, st);
+    case 5: return launch_gemv<5>(xp, x_row_stride, wp, w_row_stride, N, K, rp, r_row_stride, out, o_row_stride, out_f32, st);
+    case 6: return launch_gemv<6>(xp, x_row_stride, wp, w_row_stride, N, K, rp, r_row_stride, out, o_row_stride, out_f32, st);
+    case 7: return launch_gemv<7>(xp, x_row_stride, wp, w_row_stride, N, K, rp, r_row_stride, out, o_row_stride, out_f32, st);
+    default: return launch_gemv<8>(xp, x_row_stride, wp, w_row_stride, N, K, rp, r_row_stride, out, o_row_stride, out_f32, st);
+  }
 }
 
 extern "C" int uvx_argmax(const float* logits, int64_t B, int64_t V, int64_t* out_idx, uvx_stream_t stream) {

@@ -89,3 +89,91 @@ class PrefillEngine:
         self._host_token.copy_(self.token, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self._host_token
+
+
+class DecodeEngine:
+    """Greedy decode after a prefill, one token per stream per step, the whole step (embedding -> 32/80 layers -> lm head
+    -> argmax -> position bump) captured ONCE in a CUDA graph and replayed per token: positions, KV lengths and the
+    current token live on the device, so nothing in the graph changes between steps.  Linear layers are weight-streaming
+    matrix-vector kernels (uvx_gemv_bf16).  This is the serving loop of ``LocalInference._generate`` with
+    ``temperature in {None, 0}`` (ref:ultravox/inference/infer.py:309-342)."""
+
+    def __init__(self, model: UltravoxModel, batch: int, max_len: int, use_graph: bool = True):
+        if batch > 8:
+            raise ValueError("DecodeEngine handles up to 8 streams per GPU (uvx_gemv_bf16)")
+        self.model, self.B, self.max_len = model, batch, max_len
+        dev = model.device
+        tc, lm = model.config.text_config, model.language_model
+        self.cache = model.new_cache(batch, max_len)
+        self.pos = torch.zeros(batch, dtype=torch.int32, device=dev)       # position of the token being fed
+        self.lens = torch.zeros(batch, dtype=torch.int32, device=dev)      # keys visible to it (= pos + 1)
+        self.token = torch.zeros(batch, 1, dtype=torch.int64, device=dev)
+        self.cos, self.sin = model._rope_tables(max_len)
+        self.graph = None
+        self.use_graph = use_graph
+        self.launches_per_step = 0
+
+    def prefill(self, inputs_embeds: torch.Tensor) -> torch.Tensor:
+        """Runs the prompt through the LLM, fills the cache, returns the first generated token [B]."""
+        m = self.model
+        B, S, _ = inputs_embeds.shape
+        self.cache.length = 0
+        hid = m.llama_hidden(inputs_embeds, self.cache)
+        tok = ops.argmax(ops.lm_head(hid[:, -1, :], m.language_model.lm_head.weight))
+        self.token.copy_(tok.view(B, 1))
+        self.pos.fill_(S)
+        self.lens.fill_(S + 1)
+        return tok
+
+    def _step(self):
+        m = self.model
+        lm, tc = m.language_model, m.config.text_config
+        nq, nkv, hd, Dm = tc.num_attention_heads, tc.num_key_value_heads, lm.head_dim, tc.hidden_size
+        B = self.B
+        h = ops.embed_splice(self.token, lm.model.embed_tokens.weight, None, None).view(B, Dm)
+        smax = self.cache.k.shape[2]
+        for li, layer in enumerate(lm.model.layers):
+            sa, mlp = layer.self_attn, layer.mlp
+            x = ops.rmsnorm(h, layer.input_layernorm.weight, tc.rms_norm_eps)
+            qkv = ops.gemv(x, sa.qkv_w)
+            ops.rope_(qkv, nq, nkv, hd, self.cos, self.sin, rows_per_seq=1, positions=self.pos)
+            kc, vc = self.cache.k[li], self.cache.v[li]
+            ops.kv_append(qkv, kc, vc, self.pos, nq, nkv, hd)
+            att = torch.empty(B, nq * hd, dtype=torch.bfloat16, device=h.device)
+            rs = qkv.stride(0)
+            ops.attention(qkv.data_ptr(), kc.data_ptr(), vc.data_ptr(), att, B, nq, nkv, 1, smax, hd,
+                          (rs, rs, nkv * hd, smax * nkv * hd, nkv * hd, smax * nkv * hd, nq * hd, nq * hd), hd ** -0.5, False,
+                          self.lens, 0)
+            h = ops.gemv(att, sa.o_proj.weight, residual=h)
+            x = ops.rmsnorm(h, layer.post_attention_layernorm.weight, tc.rms_norm_eps)
+            act = ops.swiglu(ops.gemv(x, mlp.gate_up_w), gate_first=True)
+            h = ops.gemv(act, mlp.down_proj.weight, residual=h)
+        hn = ops.rmsnorm(h, lm.model.norm.weight, tc.rms_norm_eps)
+        logits = ops.lm_head(hn, lm.lm_head.weight)
+        ops.argmax(logits, out=self.token.view(-1))
+        ops.add_i32_(self.pos, self.lens, 1)
+
+    def step(self) -> torch.Tensor:
+        """Feeds ``self.token`` (the previous output), writes the next token into it; returns the device tensor."""
+        if self.use_graph and self.graph is None:
+            self._step_warm()
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step()
+        return self.token
+
+    def _step_warm(self):
+        # warm-up on a scratch copy of the state, then capture; the state is restored so no token is lost
+        pos, lens, tok = self.pos.clone(), self.lens.clone(), self.token.clone()
+        self._step()
+        torch.cuda.synchronize()
+        self.pos.copy_(pos), self.lens.copy_(lens), self.token.copy_(tok)
+        before = _lib.launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step()
+        self.launches_per_step = _lib.launch_count() - before
+        self.pos.copy_(pos), self.lens.copy_(lens), self.token.copy_(tok)
+        torch.cuda.synchronize()
+        self.graph = g

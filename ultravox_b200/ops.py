@@ -414,3 +414,30 @@ def adamw_(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, s
     _cuda(p, BF16, "p"), _cuda(g, torch.float32, "g")
     check(lib().uvx_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, betas[0], betas[1], eps,
                           weight_decay, step, grad_scale, _stream()), "uvx_adamw")
+
+
+# ------------------------------------------------------------------------------------------ decode step (a13)
+def gemv(x: torch.Tensor, w: torch.Tensor, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+         out_dtype=BF16) -> torch.Tensor:
+    """y = x @ w.T (+ residual) for x [B <= 8, K]: weight-streaming matrix-vector kernel (no tensor cores)."""
+    _cuda(x, BF16, "x"), _cuda(w, BF16, "w")
+    B, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(B, N, dtype=out_dtype, device=x.device)
+    check(lib().uvx_gemv_bf16(x.data_ptr(), B, x.stride(0), w.data_ptr(), w.stride(0), N, K, _p(residual),
+                              residual.stride(0) if residual is not None else 0, out.data_ptr(), out.stride(0),
+                              int(out.dtype == torch.float32), _stream()), "uvx_gemv_bf16")
+    return out
+
+
+def kv_append(qkv: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, positions: torch.Tensor, Hq: int, Hkv: int,
+              D: int) -> None:
+    """qkv [B, (Hq+2Hkv)*D] -> k_cache / v_cache [B, S_max, Hkv, D] at positions[b] (device int32)."""
+    B = qkv.shape[0]
+    check(lib().uvx_kv_append(qkv.data_ptr(), qkv.stride(0), Hq * D, (Hq + Hkv) * D, Hkv * D, k_cache.data_ptr(),
+                              v_cache.data_ptr(), k_cache.stride(0), positions.data_ptr(), B, _stream()), "uvx_kv_append")
+
+
+def add_i32_(a: torch.Tensor, b: Optional[torch.Tensor], delta: int) -> None:
+    check(lib().uvx_add_i32(a.data_ptr(), _p(b), a.numel(), delta, _stream()), "uvx_add_i32")
