@@ -223,7 +223,7 @@ extern "C" int uvx_gemv_bf16(const void* x, int64_t B, int64_t x_row_stride, con
   UVX_REQUIRE(x && W && out, "uvx_gemv_bf16: null pointer");
   UVX_REQUIRE(B >= 1 && B <= kLmMaxB && K % 8 == 0 && x_row_stride % 8 == 0 && w_row_stride % 8 == 0,
               "uvx_gemv_bf16: 1 <= B <= %d and K %% 8 == 0 required", kLmMaxB);
-  UVX_REQUIRE((size_t)kLmMaxB * K * 2 <= 200 * 1024, "uvx_gemv_bf16: K too large");
+  UVX_REQUIRE((size_t)B * K * 2 <= 200 * 1024, "uvx_gemv_bf16: B * K too large for shared memory (split the batch)");
   cudaStream_t st = (cudaStream_t)stream;
   const bf16 *xp = (const bf16*)x, *wp = (const bf16*)W, *rp = (const bf16*)R;
   switch (B) {

@@ -425,9 +425,14 @@ def gemv(x: torch.Tensor, w: torch.Tensor, residual: Optional[torch.Tensor] = No
     N = w.shape[0]
     if out is None:
         out = torch.empty(B, N, dtype=out_dtype, device=x.device)
-    check(lib().uvx_gemv_bf16(x.data_ptr(), B, x.stride(0), w.data_ptr(), w.stride(0), N, K, _p(residual),
-                              residual.stride(0) if residual is not None else 0, out.data_ptr(), out.stride(0),
-                              int(out.dtype == torch.float32), _stream()), "uvx_gemv_bf16")
+    slab = max(1, min(8, (200 * 1024) // (2 * K)))      # rows whose activations fit the kernel's shared memory
+    for b0 in range(0, B, slab):
+        nb = min(slab, B - b0)
+        xs, os_ = x[b0:b0 + nb], out[b0:b0 + nb]
+        rs = residual[b0:b0 + nb] if residual is not None else None
+        check(lib().uvx_gemv_bf16(xs.data_ptr(), nb, x.stride(0), w.data_ptr(), w.stride(0), N, K, _p(rs),
+                                  residual.stride(0) if residual is not None else 0, os_.data_ptr(), out.stride(0),
+                                  int(out.dtype == torch.float32), _stream()), "uvx_gemv_bf16")
     return out
 
 
