@@ -57,6 +57,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 template <int D>
 __global__ void __launch_bounds__(kAThreads) attn_fwd_kernel(const AttnParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int LD = D + 8;  // padded row (bf16 elements): 16-byte aligned, conflict-free ldmatrix
   extern __shared__ __align__(16) uint8_t attn_smem[];
   bf16* sQ = reinterpret_cast<bf16*>(attn_smem);
@@ -262,7 +264,7 @@ static int launch_attn(const uvx_attn_args* a, cudaStream_t st) {
   p.block = a->block;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   dim3 grid((unsigned)((a->Sq + kAM - 1) / kAM), (unsigned)a->Hq, (unsigned)a->B);
-  attn_fwd_kernel<D><<<grid, kAThreads, smem, st>>>(p);
+  launch_k(attn_fwd_kernel<D>, dim3(grid), dim3(kAThreads), smem, st, p);
   return check_launch("attn_fwd_kernel");
 }
 

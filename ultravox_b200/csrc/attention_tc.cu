@@ -134,6 +134,7 @@ struct AtSmem {
 
 __global__ void __launch_bounds__(kAtThreads, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t at_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)at_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* q_full = (uint64_t*)(smem + AtSmem::kBar);
@@ -147,10 +148,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p) 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * (2 * kQT), h = blockIdx.y, b = blockIdx.z;
-  int kv_end = p.Skv;
-  if (p.kv_len) kv_end = min(kv_end, max(p.kv_len[b], 0));
-  if (p.block > 0) kv_end = min(kv_end, ((min(q0 + 2 * kQT, p.Sq) - 1) / p.block + 1) * p.block);
-  const int n_tiles = (kv_end + kKT - 1) / kKT;
 
   if (threadIdx.x == 0) {
     at_mbar_init(q_full, 1);
@@ -175,6 +172,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p) 
   __syncthreads();
   at_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  int kv_end = p.Skv;
+  if (p.kv_len) kv_end = min(kv_end, max(p.kv_len[b], 0));
+  if (p.block > 0) kv_end = min(kv_end, ((min(q0 + 2 * kQT, p.Sq) - 1) / p.block + 1) * p.block);
+  const int n_tiles = (kv_end + kKT - 1) / kKT;
   // TMEM columns: S_0 [0,128), S_1 [128,256), O_0 [256,320), O_1 [320,384), P_0 [384,448), P_1 [448,512) (bf16 pairs)
   const uint32_t tS[2] = {tmem_base, tmem_base + 128};
   const uint32_t tO[2] = {tmem_base + 256, tmem_base + 320};
@@ -435,6 +437,6 @@ extern "C" int uvx_attention_enc_tc(const void* qkv, int64_t row_stride, int64_t
   p.block = block;
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((unsigned)((S + 2 * kQT - 1) / (2 * kQT)), (unsigned)H, (unsigned)B);
-  attn_tc_kernel<<<grid, kAtThreads, AtSmem::kTotal, (cudaStream_t)stream>>>(tm, p);
+  launch_k(attn_tc_kernel, dim3(grid), dim3(kAtThreads), AtSmem::kTotal, (cudaStream_t)stream, tm, p);
   return check_launch("attn_tc_kernel");
 }

@@ -1,5 +1,6 @@
 // libuvx core: error reporting, launch accounting.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -15,6 +16,15 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UVX_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int check_launch(const char* what) {

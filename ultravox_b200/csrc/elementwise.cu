@@ -9,6 +9,8 @@ namespace uvx {
 __global__ void rope_kernel(bf16* __restrict__ qkv, int64_t rows, int64_t row_stride, int heads_rot, int D,
                             const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
                             const int32_t* __restrict__ positions, int64_t rows_per_seq, int64_t pos_offset, float sgn) {
+  pdl_trigger();
+  pdl_wait();
   const int half = D / 2;
   const int vec_per_head = half / 8;
   const int64_t total = rows * heads_rot * vec_per_head;
@@ -41,6 +43,8 @@ __global__ void rope_kernel(bf16* __restrict__ qkv, int64_t rows, int64_t row_st
 // ------------------------------------------------------------------------------------------- SwiGLU
 __global__ void swiglu_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int64_t rows, int64_t H,
                               int64_t x_row_stride, int gate_first) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t vec_per_row = H / 8;
   const int64_t total = rows * vec_per_row;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -62,6 +66,8 @@ __global__ void swiglu_kernel(const bf16* __restrict__ x, bf16* __restrict__ out
 // --------------------------------------------------------------------- mel [N, C, T] f32 -> [N, T+2, C] bf16
 // 32x32 shared-memory transpose tile; guard rows t = -1 and t = T are zeroed by the same kernel.
 __global__ void mel_to_tm_kernel(const float* __restrict__ mel, int n_mels, int64_t T, bf16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int64_t n = blockIdx.z;
   const int64_t t0 = (int64_t)blockIdx.x * 32;
@@ -94,6 +100,8 @@ __global__ void mel_to_tm_kernel(const float* __restrict__ mel, int n_mels, int6
 __global__ void splice_plan_kernel(const int64_t* __restrict__ start_idx, const int32_t* __restrict__ tok_len,
                                    const int64_t* __restrict__ audio_batch_size, int64_t n_chunks, int64_t B, int64_t S,
                                    int64_t tok_stride, int32_t* __restrict__ src) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = threadIdx.x; i < B * S; i += blockDim.x) src[i] = -1;
   __syncthreads();
   int64_t a = 0;
@@ -115,6 +123,8 @@ __global__ void splice_plan_kernel(const int64_t* __restrict__ start_idx, const 
 __global__ void embed_splice_kernel(const int64_t* __restrict__ ids, const bf16* __restrict__ table, int64_t vocab,
                                     const bf16* __restrict__ audio, const int32_t* __restrict__ src, int64_t rows,
                                     int64_t d, bf16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -137,6 +147,8 @@ __global__ void embed_splice_kernel(const int64_t* __restrict__ ids, const bf16*
 __global__ void kv_append_kernel(const bf16* __restrict__ qkv, int64_t row_stride, int k_col, int v_col, int kv_width,
                                  bf16* __restrict__ k_cache, bf16* __restrict__ v_cache, int64_t cache_batch_stride,
                                  const int32_t* __restrict__ positions, int64_t B) {
+  pdl_trigger();
+  pdl_wait();
   const int vec = kv_width / 8;
   const int64_t total = B * vec * 2;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -151,6 +163,8 @@ __global__ void kv_append_kernel(const bf16* __restrict__ qkv, int64_t row_strid
 }
 
 __global__ void add_i32_kernel(int32_t* __restrict__ a, int32_t* __restrict__ b2, int64_t n, int32_t delta) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     a[i] += delta;
@@ -170,8 +184,7 @@ static int rope_launch(void* qkv, int64_t rows, int64_t row_stride, int Hq, int 
   const int64_t total = rows * (Hq + Hkv) * (D / 16);
   const int threads = 256;
   const int64_t blocks = (total + threads - 1) / threads;
-  rope_kernel<<<(unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks), threads, 0, (cudaStream_t)stream>>>(
-      (bf16*)qkv, rows, row_stride, Hq + Hkv, D, cos_tab, sin_tab, positions, rows_per_seq, pos_offset, sgn);
+  launch_k(rope_kernel, dim3((unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks)), dim3(threads), 0, (cudaStream_t)stream, (bf16*)qkv, rows, row_stride, Hq + Hkv, D, cos_tab, sin_tab, positions, rows_per_seq, pos_offset, sgn);
   return check_launch("rope_kernel");
 }
 
@@ -196,8 +209,7 @@ extern "C" int uvx_swiglu(const void* x, void* out, int64_t rows, int64_t H, int
   const int64_t total = rows * (H / 8);
   const int threads = 256;
   const int64_t blocks = (total + threads - 1) / threads;
-  swiglu_kernel<<<(unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks), threads, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, (bf16*)out, rows, H, x_row_stride, gate_first);
+  launch_k(swiglu_kernel, dim3((unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks)), dim3(threads), 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)out, rows, H, x_row_stride, gate_first);
   return check_launch("swiglu_kernel");
 }
 
@@ -206,7 +218,7 @@ extern "C" int uvx_mel_to_timemajor(const float* mel, int64_t N, int n_mels, int
   UVX_REQUIRE(mel && out_tm, "uvx_mel_to_timemajor: null pointer");
   UVX_REQUIRE(N > 0 && T > 0 && n_mels > 0 && N < 65536, "uvx_mel_to_timemajor: bad shape");
   dim3 grid((unsigned)((T + 31) / 32), (unsigned)((n_mels + 31) / 32), (unsigned)N), block(32, 8);
-  mel_to_tm_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(mel, n_mels, T, (bf16*)out_tm);
+  launch_k(mel_to_tm_kernel, dim3(grid), dim3(block), 0, (cudaStream_t)stream, mel, n_mels, T, (bf16*)out_tm);
   return check_launch("mel_to_tm_kernel");
 }
 
@@ -216,7 +228,7 @@ extern "C" int uvx_splice_plan(const int64_t* start_idx, const int32_t* tok_len,
   using namespace uvx;
   UVX_REQUIRE(src && B > 0 && S > 0, "uvx_splice_plan: bad arguments");
   UVX_REQUIRE(n_chunks == 0 || (start_idx && tok_len && audio_batch_size), "uvx_splice_plan: null index vectors");
-  splice_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(start_idx, tok_len, audio_batch_size, n_chunks, B, S, tok_stride, src);
+  launch_k(splice_plan_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, start_idx, tok_len, audio_batch_size, n_chunks, B, S, tok_stride, src);
   return check_launch("splice_plan_kernel");
 }
 
@@ -228,8 +240,7 @@ extern "C" int uvx_embed_splice(const int64_t* input_ids, const void* embed_toke
   UVX_REQUIRE(!src || audio_embeds, "uvx_embed_splice: src without audio_embeds");
   if (rows == 0) return UVX_OK;
   const int warps = 8;
-  embed_splice_kernel<<<(unsigned)((rows + warps - 1) / warps), warps * 32, 0, (cudaStream_t)stream>>>(
-      input_ids, (const bf16*)embed_tokens, vocab, (const bf16*)audio_embeds, src, rows, d, (bf16*)out);
+  launch_k(embed_splice_kernel, dim3((unsigned)((rows + warps - 1) / warps)), dim3(warps * 32), 0, (cudaStream_t)stream, input_ids, (const bf16*)embed_tokens, vocab, (const bf16*)audio_embeds, src, rows, d, (bf16*)out);
   return check_launch("embed_splice_kernel");
 }
 
@@ -240,14 +251,13 @@ extern "C" int uvx_kv_append(const void* qkv, int64_t row_stride, int64_t k_col,
   UVX_REQUIRE(kv_width % 8 == 0 && row_stride % 8 == 0 && k_col % 8 == 0 && v_col % 8 == 0 && cache_batch_stride % 8 == 0,
               "uvx_kv_append: alignment");
   const int64_t total = B * (kv_width / 8) * 2;
-  kv_append_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)qkv, row_stride, (int)k_col, (int)v_col, (int)kv_width, (bf16*)k_cache, (bf16*)v_cache, cache_batch_stride, positions, B);
+  launch_k(kv_append_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)qkv, row_stride, (int)k_col, (int)v_col, (int)kv_width, (bf16*)k_cache, (bf16*)v_cache, cache_batch_stride, positions, B);
   return check_launch("kv_append_kernel");
 }
 
 extern "C" int uvx_add_i32(int32_t* a, int32_t* b, int64_t n, int32_t delta, uvx_stream_t stream) {
   using namespace uvx;
   UVX_REQUIRE(a && n >= 1, "uvx_add_i32: bad arguments");
-  add_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, b, n, delta);
+  launch_k(add_i32_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, a, b, n, delta);
   return check_launch("add_i32_kernel");
 }

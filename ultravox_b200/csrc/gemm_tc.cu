@@ -215,6 +215,7 @@ struct SmemLayout {
 template <int MT, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+  pdl_trigger();
   using L = SmemLayout<MT, BN>;
   constexpr int kStages = L::kStages;
   constexpr int kAcc = L::kAcc;
@@ -253,6 +254,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // set-up above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -457,6 +459,7 @@ struct Smem2 {
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tc2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+  pdl_trigger();
   using L = Smem2<BN>;
   constexpr int kStages = L::kStages;
   constexpr int kAcc = L::kAcc;
@@ -497,6 +500,7 @@ gemm_tc2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // set-up above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -594,6 +598,8 @@ gemm_tc2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // Split-K second pass: sums the fp32 partials in split order and applies the same epilogue as the direct path.
 // One thread per 8 consecutive output columns; spread over the whole grid so no single SM has to pull all partials.
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t rows = p.a_batch * p.a_rows;
   const int64_t vec_per_row = p.N / 8;
   const int64_t total = rows * vec_per_row;
@@ -752,13 +758,13 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, cudaStream_t stream) 
   }
   const int units = p.num_tiles * p.splits;
   const int grid = units < num_sms() ? units : num_sms();
-  gemm_tc_kernel<MT, BN><<<(unsigned)grid, kThreads, L::kTotal, stream>>>(tmA, tmW, p);
+  launch_k(gemm_tc_kernel<MT, BN>, dim3((unsigned)grid), dim3(kThreads), L::kTotal, stream, tmA, tmW, p);
   int rc = check_launch("gemm_tc_kernel");
   if (rc || p.splits == 1) return rc;
   const int64_t total = a->a_batch * a->a_rows * (a->N / 8);
   int64_t blocks = (total + 255) / 256;
   if (blocks > (int64_t)num_sms() * 8) blocks = (int64_t)num_sms() * 8;
-  splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+  launch_k(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, p);
   return check_launch("splitk_reduce_kernel");
 }
 
@@ -814,7 +820,7 @@ static int launch_gemm_2sm(const uvx_gemm_args* a, cudaStream_t stream) {
   }
   const int max_pairs = num_sms() / 2;
   const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
-  gemm_tc2sm_kernel<BN><<<(unsigned)(2 * pairs), kThreads, L::kTotal, stream>>>(tmA, tmW, p);
+  launch_k(gemm_tc2sm_kernel<BN>, dim3((unsigned)(2 * pairs)), dim3(kThreads), L::kTotal, stream, tmA, tmW, p);
   return check_launch("gemm_tc2sm_kernel");
 }
 

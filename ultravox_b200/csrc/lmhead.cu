@@ -12,6 +12,8 @@ template <int B>
 __global__ void __launch_bounds__(kLmWarps * 32) lm_head_kernel(const bf16* __restrict__ h, int64_t h_row_stride,
                                                                 const bf16* __restrict__ W, int64_t V, int64_t d,
                                                                 float* __restrict__ logits) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ uint8_t lm_smem[];
   bf16* hs = reinterpret_cast<bf16*>(lm_smem);  // [B][d]
   for (int64_t i = threadIdx.x; i < (int64_t)B * d / 8; i += blockDim.x) {
@@ -50,6 +52,8 @@ __global__ void __launch_bounds__(kLmWarps * 32) lm_head_kernel(const bf16* __re
 }
 
 __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int64_t V, int64_t* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sv[32];
   __shared__ int64_t si[32];
   const float* row = logits + (int64_t)blockIdx.x * V;
@@ -113,6 +117,8 @@ __global__ void __launch_bounds__(kLmWarps * 32) gemv_kernel(const bf16* __restr
                                                              const bf16* __restrict__ W, int64_t w_row_stride, int64_t N,
                                                              int64_t K, const bf16* __restrict__ R, int64_t r_row_stride,
                                                              void* __restrict__ out, int64_t o_row_stride, int out_f32) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ uint8_t lm_smem[];
   bf16* xs = reinterpret_cast<bf16*>(lm_smem);  // [B][K]
   for (int64_t i = threadIdx.x; i < (int64_t)B * K / 8; i += blockDim.x) {
@@ -165,7 +171,7 @@ static int launch_gemv(const bf16* x, int64_t xs, const bf16* W, int64_t ws, int
   }
   int64_t blocks = (N + kLmWarps - 1) / kLmWarps;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  gemv_kernel<B><<<(unsigned)blocks, kLmWarps * 32, smem, st>>>(x, xs, W, ws, N, K, R, rs, out, os, out_f32);
+  launch_k(gemv_kernel<B>, dim3((unsigned)blocks), dim3(kLmWarps * 32), smem, st, x, xs, W, ws, N, K, R, rs, out, os, out_f32);
   return check_launch("gemv_kernel");
 }
 
@@ -179,7 +185,7 @@ static int launch_lm(const bf16* h, int64_t hs, const bf16* W, int64_t V, int64_
   }
   int64_t blocks = (V + kLmWarps - 1) / kLmWarps;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  lm_head_kernel<B><<<(unsigned)blocks, kLmWarps * 32, smem, st>>>(h, hs, W, V, d, logits);
+  launch_k(lm_head_kernel<B>, dim3((unsigned)blocks), dim3(kLmWarps * 32), smem, st, h, hs, W, V, d, logits);
   return check_launch("lm_head_kernel");
 }
 
@@ -241,6 +247,6 @@ extern "C" int uvx_gemv_bf16(const void* x, int64_t B, int64_t x_row_stride, con
 extern "C" int uvx_argmax(const float* logits, int64_t B, int64_t V, int64_t* out_idx, uvx_stream_t stream) {
   using namespace uvx;
   UVX_REQUIRE(logits && out_idx && B >= 1 && V >= 1, "uvx_argmax: bad arguments");
-  argmax_kernel<<<(unsigned)B, 1024, 0, (cudaStream_t)stream>>>(logits, V, out_idx);
+  launch_k(argmax_kernel, dim3((unsigned)B), dim3(1024), 0, (cudaStream_t)stream, logits, V, out_idx);
   return check_launch("argmax_kernel");
 }

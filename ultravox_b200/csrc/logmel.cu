@@ -116,6 +116,8 @@ __device__ __forceinline__ int float_to_ordered(float f) {
 __device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
 
 __global__ void logmel_init_kernel(int* clipmax, int64_t B) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) clipmax[i] = float_to_ordered(-INFINITY);
 }
@@ -123,6 +125,8 @@ __global__ void logmel_init_kernel(int* clipmax, int64_t B) {
 __global__ void __launch_bounds__(kThreads) logmel_power_kernel(const float* __restrict__ wave, int64_t L, int64_t T, int n_mels,
                                                                MelTables tab, float* __restrict__ scratch,
                                                                int* __restrict__ clipmax) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float2 s_tw[kNfft];
   __shared__ __align__(16) float s_x[kNfft][kFT];  // windowed samples, [n][frame]
   __shared__ float s_pow[kFT][kBins + 3];
@@ -202,6 +206,8 @@ __global__ void __launch_bounds__(kThreads) logmel_power_kernel(const float* __r
 __global__ void __launch_bounds__(kThreads) logmel_finish_kernel(const float* __restrict__ scratch, const int* __restrict__ clipmax,
                                                                 int64_t T, int n_mels, float* __restrict__ out_f32,
                                                                 bf16* __restrict__ out_tm) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][kMaxMels + 1];
   const int64_t b = blockIdx.y;
   const int64_t t0 = (int64_t)blockIdx.x * 32;
@@ -274,14 +280,14 @@ extern "C" int uvx_logmel(const float* wave, int64_t B, int64_t L, int n_mels, f
   const int64_t T = L / kHop;
   int* clipmax = (int*)workspace;
   float* scratch = (float*)((uint8_t*)workspace + ((B * 4 + 255) / 256) * 256);
-  logmel_init_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(clipmax, B);
+  launch_k(logmel_init_kernel, dim3((unsigned)((B + 255) / 256)), dim3(256), 0, st, clipmax, B);
   int rc = check_launch("logmel_init_kernel");
   if (rc) return rc;
   dim3 g1((unsigned)((T + kFT - 1) / kFT), (unsigned)B);
-  logmel_power_kernel<<<g1, kThreads, 0, st>>>(wave, L, T, n_mels, *tab, scratch, clipmax);
+  launch_k(logmel_power_kernel, dim3(g1), dim3(kThreads), 0, st, wave, L, T, n_mels, *tab, scratch, clipmax);
   rc = check_launch("logmel_power_kernel");
   if (rc) return rc;
   dim3 g2((unsigned)((T + 31) / 32), (unsigned)B);
-  logmel_finish_kernel<<<g2, kThreads, 0, st>>>(scratch, clipmax, T, n_mels, out_f32, (bf16*)out_tm);
+  launch_k(logmel_finish_kernel, dim3(g2), dim3(kThreads), 0, st, scratch, clipmax, T, n_mels, out_f32, (bf16*)out_tm);
   return check_launch("logmel_finish_kernel");
 }

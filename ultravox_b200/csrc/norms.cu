@@ -10,6 +10,8 @@ static constexpr int kMaxVec = 8;  // up to 256 * 8 * 8 = 16384 columns
 __global__ void __launch_bounds__(kNormThreads) layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                                  const bf16* __restrict__ b, bf16* __restrict__ y,
                                                                  int64_t cols, int64_t x_row_stride, float eps) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[32];
   const int64_t row = blockIdx.x;
   const bf16* xr = x + row * x_row_stride;
@@ -58,6 +60,8 @@ static constexpr int kLnWarpVec = 8;
 __global__ void __launch_bounds__(128) layernorm_warp_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                              const bf16* __restrict__ b, bf16* __restrict__ y, int64_t rows,
                                                              int64_t cols, int64_t x_row_stride, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -108,6 +112,8 @@ __global__ void __launch_bounds__(kNormThreads) rmsnorm_kernel(const bf16* __res
                                                                bf16* __restrict__ y, int64_t cols, int64_t x_row_stride,
                                                                int64_t group_rows, int64_t group_stride,
                                                                int64_t valid_elems, float eps) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[32];
   const int64_t row = blockIdx.x;
   const bf16* xr;
@@ -161,11 +167,11 @@ extern "C" int uvx_layernorm(const void* x, const void* w, const void* b, void* 
               "uvx_layernorm: cols must be a multiple of 8 and <= %d", kNormThreads * kMaxVec * 8);
   if (rows == 0) return UVX_OK;
   if (cols <= 32 * kLnWarpVec * 8) {
-    layernorm_warp_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)w, (const bf16*)b,
+    launch_k(layernorm_warp_kernel, dim3((unsigned)((rows + 3) / 4)), dim3(128), 0, (cudaStream_t)stream, (const bf16*)x, (const bf16*)w, (const bf16*)b,
                                                                                        (bf16*)y, rows, cols, x_row_stride, eps);
     return check_launch("layernorm_warp_kernel");
   }
-  layernorm_kernel<<<(unsigned)rows, kNormThreads, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)w, (const bf16*)b,
+  launch_k(layernorm_kernel, dim3((unsigned)rows), dim3(kNormThreads), 0, (cudaStream_t)stream, (const bf16*)x, (const bf16*)w, (const bf16*)b,
                                                                              (bf16*)y, cols, x_row_stride, eps);
   return check_launch("layernorm_kernel");
 }
@@ -178,7 +184,7 @@ extern "C" int uvx_rmsnorm(const void* x, const void* w, void* y, int64_t rows, 
               "uvx_rmsnorm: cols must be a multiple of 8 and <= %d", kNormThreads * kMaxVec * 8);
   UVX_REQUIRE(group_rows == 0 || (valid_elems % 8 == 0 && group_stride % 8 == 0), "uvx_rmsnorm: group alignment");
   if (rows == 0) return UVX_OK;
-  rmsnorm_kernel<<<(unsigned)rows, kNormThreads, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)w, (bf16*)y, cols,
+  launch_k(rmsnorm_kernel, dim3((unsigned)rows), dim3(kNormThreads), 0, (cudaStream_t)stream, (const bf16*)x, (const bf16*)w, (bf16*)y, cols,
                                                                            x_row_stride, group_rows, group_stride,
                                                                            valid_elems, eps);
   return check_launch("rmsnorm_kernel");

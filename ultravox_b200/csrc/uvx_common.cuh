@@ -29,6 +29,33 @@ int check_launch(const char* what);  // cudaGetLastError -> UVX_ERR_CUDA + messa
 
 typedef __nv_bfloat16 bf16;
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// Every kernel on the inference path is launched with the programmatic-stream-serialization attribute and starts with
+// pdl_trigger() (let the next kernel's CTAs be scheduled as soon as SM resources free up) followed - after its
+// input-independent set-up - by pdl_wait() (all memory of the preceding grids is complete and visible).  Inside a CUDA
+// graph this turns the kernel->kernel edges into programmatic edges: launch latency, barrier init, TMEM allocation and
+// descriptor prefetch of kernel N+1 overlap the tail of kernel N.  UVX_PDL=0 disables the attribute (plain launches).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // ---- small device helpers --------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
