@@ -22,7 +22,7 @@ bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("UVX_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured slower than plain graph edges in round 1 (profiles/README)
   }
   return v == 1;
 }
