@@ -96,6 +96,9 @@ typedef struct uvx_gemm_args {
   int32_t out_dtype;        /* UVX_DT_* */
   void* workspace;          /* optional, 256-byte aligned scratch: enables split-K when the tile count cannot fill   */
   int64_t workspace_bytes;  /* the SMs (fp32 partial sums [splits][rows][N]; contents on entry do not matter).       */
+  const void* norm_w;       /* optional: also emit norm_out[row,:] = norm_w * bf16(C[row,:] * rsqrt(mean(C^2) + eps)),  */
+  void* norm_out;           /* the LlamaRMSNorm that follows o_proj / down_proj (hf:modeling_llama.py:53-67, 321-329),  */
+  float norm_eps;           /* fused into the split-K reduction when there is one.  bf16 [rows, N], plain row order.    */
 } uvx_gemm_args;
 
 int uvx_gemm_bf16(const uvx_gemm_args* args, uvx_stream_t stream);

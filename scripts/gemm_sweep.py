@@ -24,7 +24,7 @@ for name, M, N, K in SHAPES:
     ref = (x.float() @ Ws[0].float().T)
     out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
     cfgs = [(1064, 0), (1128, 0), (1256, 0)] if M > 256 or M <= 128 else [(2064, 0), (2128, 0), (2256, 0), (1128, 0), (1064, 0)]
-    cands = [(0, 0), (4128, 1), (4256, 1)]
+    cands = [(0, 0), (4128, 1), (4256, 1), (1208, 1)] + ([(2208, 1)] if 128 < M <= 256 else [])
     for c, _ in cfgs:
         for sp in ((1,) if M > 256 else (1, 2, 3, 4, 6, 8, 12)):
             cands.append((c, sp))

@@ -37,7 +37,7 @@ def ops():
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (201, 256, 512), (1, 128, 256), (300, 192, 200), (1500, 1280, 1280),
-                                   (201, 4096, 4096), (129, 64, 64)])
+                                   (201, 4096, 4096), (129, 64, 64), (201, 28672, 512)])
 def test_gemm_plain(ops, M, N, K):
     x, w = rnd(M, K, seed=1), rnd(N, K, scale=0.05, seed=2)
     y = ops.linear(x, w)
@@ -46,7 +46,7 @@ def test_gemm_plain(ops, M, N, K):
     assert rel(y, ref.to(BF)) < 1e-3, rel(y, ref)
 
 
-@pytest.mark.parametrize("cfg,splits", [(2128, 4), (2256, 3), (1128, 5), (1064, 2), (2064, 7), (1256, 2)])
+@pytest.mark.parametrize("cfg,splits", [(2128, 4), (2256, 3), (1128, 5), (1064, 2), (2064, 7), (1256, 2), (2208, 1), (1208, 1)])
 def test_gemm_forced_configs_and_split_k(ops, cfg, splits):
     from ultravox_b200 import _lib
     M, N, K = 201, 512, 2048
@@ -91,6 +91,23 @@ def test_gemm_epilogues(ops):
     r2 = r.clone()
     ops.linear(x, w, bias=b, residual=r2, out=r2)
     assert rel(r2, x.float() @ w.float().T + b.float() + r.float()) < 1e-3
+
+
+@pytest.mark.parametrize("cfg,splits", [(0, 0), (2128, 4), (1128, 1), (4128, 1), (1064, 3)])
+def test_gemm_fused_rmsnorm(ops, cfg, splits):
+    """o_proj / down_proj shape: C = x@w.T + residual (in place) and norm_out = RMSNorm(C); the fused split-K pass must be
+    bit-identical to running uvx_rmsnorm on the finished C."""
+    from ultravox_b200 import _lib
+    M, N, K = 201, 1024, 4096
+    x, w, r, nw = rnd(M, K, seed=1), rnd(N, K, scale=0.05, seed=2), rnd(M, N, seed=4), rnd(N, seed=5)
+    h, xn = r.clone(), torch.empty(M, N, dtype=BF, device="cuda")
+    _lib.lib().uvx_debug_gemm_override(cfg, splits)
+    try:
+        ops.linear(x, w, residual=h, out=h, norm=(nw, 1e-5, xn))
+    finally:
+        _lib.lib().uvx_debug_gemm_override(0, 0)
+    assert rel(h, x.float() @ w.float().T + r.float()) < 1e-3
+    assert torch.equal(xn, ops.rmsnorm(h, nw, 1e-5))
 
 
 def test_gemm_row_map(ops):

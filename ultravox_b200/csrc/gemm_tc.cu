@@ -4,13 +4,13 @@
 //
 // Persistent, warp-specialised kernel: grid = min(#tiles, #SMs), each CTA walks tiles t = blockIdx.x + i*gridDim.x.
 // A CTA tile is (MT*128) x BN: MT in {1,2} row sub-tiles share one W tile (so at M <= 256 - the LLM prefill - every
-// weight byte is fetched from L2/HBM exactly once), BN in {64,128,256}.
+// weight byte is fetched from L2/HBM exactly once), BN in {64,128,208,256} (208: ragged last column tile allowed).
 //   warp 0      TMA producer: cp.async.bulk.tensor of the A box {64 k, MT*128 rows, 1 batch} and the W box {64 k, BN
 //               rows} into a kStages-deep 128B-swizzled shared-memory ring (mbarrier expect_tx); runs ahead across tiles.
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32 accumulators in TMEM, MT
 //               accumulators per tile); tcgen05.commit releases ring slots and publishes finished accumulators.
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns per warp, fused bias / GELU / residual / row remap, 16-byte
-//               stores.  When MT*BN <= 256 the accumulators are double-buffered in TMEM, so the epilogue of tile i
+//   warps 2..   epilogue (4 warps at MT=2, 8 at MT=1): tcgen05.ld 32 lanes x 32 columns per warp, fused bias / GELU /
+//               residual / row remap, transposed through shared memory into full-sector 16-byte stores.  When MT*BN <= 256 the accumulators are double-buffered in TMEM, so the epilogue of tile i
 //               overlaps the main loop of tile i+1.
 // A is described by a 3-D tensor map (k, row, batch) with caller-chosen strides, so overlapping rows (implicit-GEMM
 // conv over a time-major activation) and batch-strided inputs need no im2col copy; rows or k beyond the tensor bounds
@@ -39,6 +39,12 @@ struct GemmParams {
   int n_tiles, num_tiles;
   int splits, kb_per_split;  // split-K: units = num_tiles * splits
   float* ws_partial;         // [splits][a_batch * a_rows][N] fp32 partial sums (reduced by splitk_reduce_kernel)
+  const bf16* norm_w;        // optional fused RMSNorm of the finished output rows: norm_out = w * bf16(C * rstd)
+  bf16* norm_out;
+  float norm_eps;
+  int a_box_bytes;  // bytes of the A box in one ring stage (box rows * 128): fewer rows than MT*128 when M is small
+  int stage_bytes;  // a_box_bytes + BN * 128
+  int stages;       // ring depth that fits the shared-memory budget (2..8)
 };
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -129,11 +135,36 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // directly makes every 16-byte store hit a different row (measured 8x write amplification on the SM->L2 path), so
 // the 32x32 fp32 chunk is transposed through a per-warp shared-memory pad and written back with 4 lanes per row:
 // every store instruction covers 8 rows x 64 contiguous bytes (full 32-byte sectors), residual reads likewise.
-static constexpr int kStageLd = 36;                           // floats per staged row (16-byte aligned, conflict-light)
-static constexpr int kStageBytesPerWarp = 32 * kStageLd * 4;  // 4608 B
+static constexpr int kStageBytesPerWarp = 32 * 32 * 4;  // 4096 B: 32 rows x 32 fp32, 16-byte chunks XOR-swizzled by row
 
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t* raw, float* stage, int lane, int b,
-                                               int64_t m_warp0, int64_t n) {
+                                               int64_t m_warp0, int64_t n, int64_t n_lim) {
+  // phase 0: this lane's share of the coalesced write-back (rows r_j, 8 (bf16) / 4 (f32) columns) - issue the residual
+  // loads first so that their latency hides behind the activation math and the transpose
+  constexpr int kJ = 8;
+  const bool f32 = p.out_f32 != 0;
+  const int nj = f32 ? 8 : 4;
+  int64_t orow[kJ];
+  uint4 rres[kJ];
+#pragma unroll
+  for (int j = 0; j < kJ; ++j) {
+    orow[j] = -1;
+    rres[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (j >= nj) continue;
+    const int r = f32 ? (lane >> 3) + 4 * j : (lane >> 2) + 8 * j;
+    const int pc = f32 ? (lane & 7) * 4 : (lane & 3) * 8;
+    const int64_t m = m_warp0 + r;
+    if (m >= p.a_rows || n + pc >= n_lim) continue;
+    orow[j] = p.c_row_map ? (int64_t)p.c_row_map[(int64_t)b * p.a_rows + m] : (int64_t)b * p.c_batch_rows + m + p.c_row_offset;
+    if (orow[j] < 0 || !p.R) continue;
+    const bf16* rr = p.R + (int64_t)b * p.r_batch_stride + m * p.r_row_stride + n + pc;
+    if (f32) {
+      const uint2 t = *reinterpret_cast<const uint2*>(rr);
+      rres[j].x = t.x; rres[j].y = t.y;
+    } else {
+      rres[j] = *reinterpret_cast<const uint4*>(rr);
+    }
+  }
   // phase 1: this lane's row, 32 columns: alpha, bias, activation (fp32)
   float v[32];
 #pragma unroll
@@ -142,6 +173,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       float t[8];
+      if (n + g * 8 >= n_lim) break;  // columns past the tile / matrix edge are never stored
       unpack8(*reinterpret_cast<const bf16x8*>(p.bias + n + g * 8), t);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[g * 8 + i] += t[i];
@@ -149,97 +181,100 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   }
   if (p.act == UVX_ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
   }
-  float4* srow = reinterpret_cast<float4*>(stage + lane * kStageLd);
+  float4* srow = reinterpret_cast<float4*>(stage + lane * 32);
 #pragma unroll
-  for (int g = 0; g < 8; ++g) srow[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+  for (int g = 0; g < 8; ++g) srow[g ^ (lane & 7)] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
   __syncwarp();
-  // phase 2: transposed read-back, residual add, coalesced stores
-  if (p.out_f32) {
+  // phase 2: transposed read-back, residual add, coalesced stores (full 32-byte sectors)
+  if (f32) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+      if (orow[j] < 0) continue;
       const int r = (lane >> 3) + 4 * j, pc = (lane & 7) * 4;
-      const int64_t m = m_warp0 + r;
-      if (m >= p.a_rows) continue;
-      const int64_t orow = p.c_row_map ? (int64_t)p.c_row_map[(int64_t)b * p.a_rows + m] : (int64_t)b * p.c_batch_rows + m + p.c_row_offset;
-      if (orow < 0) continue;
-      float4 t = *reinterpret_cast<const float4*>(stage + r * kStageLd + pc);
+      float4 t = reinterpret_cast<const float4*>(stage + r * 32)[(lane & 7) ^ (r & 7)];
       if (p.R) {
-        const bf16* rr = p.R + (int64_t)b * p.r_batch_stride + m * p.r_row_stride + n + pc;
-        const float2 r01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(rr));
-        const float2 r23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(rr + 2));
+        const float2 r01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rres[j].x));
+        const float2 r23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rres[j].y));
         t.x += r01.x; t.y += r01.y; t.z += r23.x; t.w += r23.y;
       }
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + orow * p.c_row_stride + n + pc) = t;
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + orow[j] * p.c_row_stride + n + pc) = t;
     }
   } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
+      if (orow[j] < 0) continue;
       const int r = (lane >> 2) + 8 * j, pc = (lane & 3) * 8;
-      const int64_t m = m_warp0 + r;
-      if (m >= p.a_rows) continue;
-      const int64_t orow = p.c_row_map ? (int64_t)p.c_row_map[(int64_t)b * p.a_rows + m] : (int64_t)b * p.c_batch_rows + m + p.c_row_offset;
-      if (orow < 0) continue;
-      const float4 t0 = *reinterpret_cast<const float4*>(stage + r * kStageLd + pc);
-      const float4 t1 = *reinterpret_cast<const float4*>(stage + r * kStageLd + pc + 4);
+      const float4* row4 = reinterpret_cast<const float4*>(stage + r * 32);
+      const float4 t0 = row4[(2 * (lane & 3)) ^ (r & 7)];
+      const float4 t1 = row4[(2 * (lane & 3) + 1) ^ (r & 7)];
       float o[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
       if (p.R) {
         float rv[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(p.R + (int64_t)b * p.r_batch_stride + m * p.r_row_stride + n + pc), rv);
+        unpack8(*reinterpret_cast<const bf16x8*>(&rres[j]), rv);
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] += rv[i];
       }
-      *reinterpret_cast<bf16x8*>(reinterpret_cast<bf16*>(p.C) + orow * p.c_row_stride + n + pc) = pack8(o);
+      *reinterpret_cast<bf16x8*>(reinterpret_cast<bf16*>(p.C) + orow[j] * p.c_row_stride + n + pc) = pack8(o);
     }
   }
   __syncwarp();  // the pad is reused by the next chunk
 }
 
+// Shared-memory plan of the 1-SM kernel (dynamic, 1024-byte aligned base, always the full 227 KB - one CTA per SM):
+//   [0, stages * stage_bytes)   ring of {A box, W box} stages; the geometry is a launch parameter because the A box
+//                               only holds round8(M) rows when one row tile covers the whole problem (M = 201 prefill:
+//                               208 rows instead of 256 -> 4 ring stages instead of 3, i.e. more weight bytes in flight)
+//   [kPadOff, kBarOff)          epilogue transpose pads, 4 KB per epilogue warp
+//   [kBarOff, kSmemTotal)       mbarriers + the TMEM base slot
+static constexpr int kSmemTotal = 227 * 1024;
+static constexpr int kBarOff = kSmemTotal - 256;
+static constexpr int kMaxStages = 8;
+
 template <int MT, int BN>
 struct SmemLayout {
-  static constexpr int kABytes = MT * kBM * kBK * 2;  // 16 KB per row sub-tile
+  static constexpr int kEpiWarps = MT == 1 ? 8 : 4;   // tensor-bound shapes (MT = 1) get two epilogue warps per TMEM lane quarter
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
   static constexpr int kWBytes = BN * kBK * 2;
-  static constexpr int kStageBytes = kABytes + kWBytes;
-  static constexpr int kStages = (196 * 1024) / kStageBytes > 8 ? 8 : (196 * 1024) / kStageBytes;
-  static constexpr int kAcc = (MT * BN * 2 <= 512) ? 2 : 1;  // TMEM accumulator stages
-  static constexpr int kTmemCols = kAcc * MT * BN < 32 ? 32 : kAcc * MT * BN;
-  static constexpr int kBarOff = kStages * kStageBytes;
-  static constexpr int kPadOff = kBarOff + 256;                                  // epilogue transpose pads (4 warps)
-  static constexpr int kTotal = kPadOff + 4 * kStageBytesPerWarp + 1024;         // + slack for 1024-byte alignment
-  static_assert(kTotal <= 227 * 1024, "shared memory budget");
-  static_assert(kStages >= 2, "ring too shallow");
+  static constexpr int kBNT = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);   // TMEM column stride of one 128-row accumulator
+  static constexpr int kAcc = (MT * kBNT * 2 <= 512) ? 2 : 1;            // TMEM accumulator stages
+  static constexpr int kTmemCols = kAcc * MT * kBNT < 32 ? 32 : kAcc * MT * kBNT;
+  static constexpr int kChunks = (BN + 31) / 32;                        // 32-column epilogue chunks (last may be partial)
+  static constexpr int kPadOff = kBarOff - kEpiWarps * kStageBytesPerWarp;
   static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns must be a power of two <= 512");
+  static_assert(2 * (MT * kBM * kBK * 2 + kWBytes) <= kPadOff, "ring too shallow");
 };
 
 template <int MT, int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(SmemLayout<MT, BN>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
   pdl_trigger();
   using L = SmemLayout<MT, BN>;
-  constexpr int kStages = L::kStages;
   constexpr int kAcc = L::kAcc;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = (uint64_t*)(smem + L::kBarOff);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full = empty_bar + kStages;
-  uint64_t* tmem_empty = tmem_full + kAcc;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + kAcc);
+  constexpr int kEpiWarps = L::kEpiWarps;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full_bar = (uint64_t*)(smem + kBarOff);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m_total = p.m_tiles * (int)p.a_batch;
   const int num_kb = (int)((p.K + kBK - 1) / kBK);
   const int num_units = p.num_tiles * p.splits;
+  const int stages = p.stages;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128B-swizzle atoms need a 1024-byte aligned ring
+    for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < kAcc; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[a], kEpiWarps);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -260,7 +295,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-      uint32_t it = 0;  // global k-block counter: the ring runs ahead across tile boundaries
+      int s = 0;           // ring slot and its phase: the ring runs ahead across tile boundaries
+      uint32_t ph = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         const int tile = unit / p.splits, split = unit % p.splits;
         const int tm_idx = tile % tiles_m_total;  // consecutive tiles share the W tile
@@ -274,22 +310,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // tile, and in lockstep they would all hit the same L2 lines at the same time
         const int nk = kb_end - kb_begin;
         const int rot = (int)(((unsigned)tile * 7u + (unsigned)split * 3u) % (unsigned)nk);
-        for (int i = 0; i < nk; ++i, ++it) {
+        for (int i = 0; i < nk; ++i) {
           const int kb = kb_begin + (i + rot < nk ? i + rot : i + rot - nk);
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
-          uint8_t* sa = smem + s * L::kStageBytes;
-          mbar_expect_tx(&full_bar[s], (uint32_t)L::kStageBytes);
+          uint8_t* sa = smem + s * p.stage_bytes;
+          mbar_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
           tma_load_3d(sa, &tmA, kb * kBK, m0, b, &full_bar[s]);
-          tma_load_2d(sa + L::kABytes, &tmW, kb * kBK, n0, &full_bar[s]);
+          tma_load_2d(sa + p.a_box_bytes, &tmW, kb * kBK, n0, &full_bar[s]);
+          if (++s == stages) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN);
-      uint32_t it = 0, tcount = 0;
+      int s = 0;
+      uint32_t ph = 0, tcount = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++tcount) {
         const int split = unit % p.splits;
         const int kb_begin = split * p.kb_per_split;
@@ -298,31 +334,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t aph = (tcount / kAcc) & 1u;
         mbar_wait(&tmem_empty[acc], aph ^ 1u);  // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (MT * BN);
-        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1u;
+        const uint32_t d_tmem = tmem_base + acc * (MT * L::kBNT);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
-          const uint64_t dw = make_smem_desc(sa + L::kABytes);
+          const uint32_t sa = smem_u32(smem + s * p.stage_bytes);
+          const uint64_t dw = make_smem_desc(sa + p.a_box_bytes);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
+            // rows past the A box (M small) read whatever follows in shared memory: they only feed accumulator rows
+            // >= a_rows, which the epilogue never stores
             const uint64_t da = make_smem_desc(sa + mt * (kBM * kBK * 2));
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {
               // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-              umma_f16(d_tmem + mt * BN, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+              umma_f16(d_tmem + mt * L::kBNT, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
             }
           }
           umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+          if (++s == stages) { s = 0; ph ^= 1u; }
         }
         umma_commit(&tmem_full[acc]);  // accumulators of this tile complete
       }
     }
   } else {
-    // ---- epilogue -------------------------------------------------------------------------
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ---- epilogue: warp w reads TMEM lane quarter w % 4; with 8 warps the two warps of a quarter take alternate chunks
+    const int q = warp & 3;
+    const int cpar = (warp - 2) >> 2;              // 0 for the first four epilogue warps, 1 for the second four
+    constexpr int cstep = kEpiWarps / 4;
     uint32_t tcount = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++tcount) {
       const int tile = unit / p.splits, split = unit % p.splits;
@@ -346,9 +385,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int64_t m = (int64_t)m0 + mt * kBM + q * 32 + lane;
           const bool row_ok = m < p.a_rows;
 #pragma unroll 1
-          for (int c = 0; c < BN / 32; ++c) {
+          for (int c = cpar; c < L::kChunks; c += cstep) {
             uint32_t raw[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * BN) + (uint32_t)(mt * BN + c * 32), raw);
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * L::kBNT) + (uint32_t)(mt * L::kBNT + c * 32), raw);
             tmem_ld_wait();
             if (row_ok) {
               uint4* dst = reinterpret_cast<uint4*>(part + ((size_t)b * p.a_rows + m) * p.N + n0 + c * 32);
@@ -363,16 +402,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         continue;
       }
       float* pad = reinterpret_cast<float*>(smem + L::kPadOff) + (warp - 2) * (kStageBytesPerWarp / 4);
+      const int64_t n_lim = (int64_t)n0 + BN < p.N ? (int64_t)n0 + BN : p.N;  // ragged last column tile (N % BN != 0)
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
         const int64_t m_warp0 = (int64_t)m0 + mt * kBM + q * 32;
         if (m_warp0 >= p.a_rows) continue;  // sub-tile entirely out of range (warp-uniform)
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = cpar; c < L::kChunks; c += cstep) {
+          if ((int64_t)n0 + c * 32 >= n_lim) break;
           uint32_t raw[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * BN) + (uint32_t)(mt * BN + c * 32), raw);
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * L::kBNT) + (uint32_t)(mt * L::kBNT + c * 32), raw);
           tmem_ld_wait();
-          epilogue_chunk(p, raw, pad, lane, b, m_warp0, (int64_t)n0 + c * 32);
+          epilogue_chunk(p, raw, pad, lane, b, m_warp0, (int64_t)n0 + c * 32, n_lim);
         }
       }
       // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator stage back
@@ -579,7 +620,7 @@ gemm_tc2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint32_t raw[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c * 32), raw);
           tmem_ld_wait();
-          epilogue_chunk(p, raw, pad, lane, b, m_warp0, (int64_t)n0 + c * 32);
+          epilogue_chunk(p, raw, pad, lane, b, m_warp0, (int64_t)n0 + c * 32, p.N);
         }
       }
       tc_fence_before();
@@ -646,6 +687,72 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmParams p) 
   }
 }
 
+// Split-K second pass fused with the RMSNorm that follows o_proj / down_proj in every Llama layer: one CTA per output row
+// sums the partials, applies the epilogue (bias / residual), writes the residual stream C and, from the same registers,
+// norm_out = w * bf16(C * rsqrt(mean(C^2) + eps)) (LlamaRMSNorm rounding order on the bf16-rounded C).  bf16 output only.
+__global__ void __launch_bounds__(256) splitk_reduce_rmsnorm_kernel(const GemmParams p) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float red[32];
+  const int64_t r = blockIdx.x;
+  const int64_t b = r / p.a_rows, m = r % p.a_rows;
+  const int64_t rows = p.a_batch * p.a_rows;
+  const size_t split_stride = (size_t)rows * (size_t)p.N;
+  const int64_t orow = p.c_row_map ? (int64_t)p.c_row_map[r] : b * p.c_batch_rows + m + p.c_row_offset;
+  constexpr int kMaxV = 4;  // up to 256 * 4 * 8 = 8192 columns
+  float v[kMaxV][8];
+  float sq = 0.f;
+  const int nvec = (int)(p.N / 8);
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    const int j = threadIdx.x + i * 256;
+    if (j < nvec) {
+      const int64_t n = (int64_t)j * 8;
+      const float* src = p.ws_partial + (size_t)r * p.N + n;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
+      for (int sidx = 0; sidx < p.splits; ++sidx) {
+        const float4 t0 = __ldcg(reinterpret_cast<const float4*>(src + sidx * split_stride));
+        const float4 t1 = __ldcg(reinterpret_cast<const float4*>(src + sidx * split_stride) + 1);
+        v[i][0] += t0.x; v[i][1] += t0.y; v[i][2] += t0.z; v[i][3] += t0.w;
+        v[i][4] += t1.x; v[i][5] += t1.y; v[i][6] += t1.z; v[i][7] += t1.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[i][e] *= p.alpha;
+      if (p.bias) {
+        float t[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(p.bias + n), t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[i][e] += t[e];
+      }
+      if (p.R) {
+        float t[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(p.R + b * p.r_batch_stride + m * p.r_row_stride + n), t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[i][e] += t[e];
+      }
+      const bf16x8 packed = pack8(v[i]);
+      if (orow >= 0) *reinterpret_cast<bf16x8*>(reinterpret_cast<bf16*>(p.C) + orow * p.c_row_stride + n) = packed;
+      unpack8(packed, v[i]);  // the norm sees the bf16-rounded residual stream, exactly like a separate kernel would
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sq += v[i][e] * v[i][e];
+    }
+  }
+  const float rstd = rsqrtf(block_sum(sq, red) / (float)p.N + p.norm_eps);
+  if (orow < 0) return;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    const int j = threadIdx.x + i * 256;
+    if (j < nvec) {
+      float wv[8], o[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(p.norm_w + (int64_t)j * 8), wv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = wv[e] * __bfloat162float(__float2bfloat16_rn(v[i][e] * rstd));
+      *reinterpret_cast<bf16x8*>(p.norm_out + orow * p.N + (int64_t)j * 8) = pack8(o);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -704,10 +811,13 @@ template <int MT, int BN>
 static int launch_gemm(const uvx_gemm_args* a, int splits, cudaStream_t stream) {
   using L = SmemLayout<MT, BN>;
   CUtensorMap tmA, tmW;
+  // one row tile covers the whole problem: stage only round8(M) rows of A per k-block (more ring stages fit)
+  int a_box_rows = MT * kBM;
+  if (a->a_batch == 1 && a->a_rows <= MT * kBM) a_box_rows = (int)((a->a_rows + 7) / 8 * 8);
   {
     uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->a_rows, (uint64_t)a->a_batch};
     uint64_t st[2] = {(uint64_t)a->a_row_stride * 2, (uint64_t)(a->a_batch > 1 ? a->a_batch_stride : a->a_row_stride) * 2};
-    uint32_t box[3] = {kBK, (uint32_t)(MT * kBM), 1};
+    uint32_t box[3] = {kBK, (uint32_t)a_box_rows, 1};
     int rc = encode_map(&tmA, a->A, 3, dims, st, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (rc) return rc;
   }
@@ -735,10 +845,14 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, cudaStream_t stream) 
   p.alpha = a->alpha;
   p.act = a->act;
   p.out_f32 = a->out_dtype == UVX_DT_F32;
+  p.norm_w = (const bf16*)a->norm_w;
+  p.norm_out = (bf16*)a->norm_out;
+  p.norm_eps = a->norm_eps;
   p.m_tiles = (int)((a->a_rows + MT * kBM - 1) / (MT * kBM));
-  p.n_tiles = (int)(a->N / BN);
+  p.n_tiles = (int)((a->N + BN - 1) / BN);
   p.num_tiles = p.m_tiles * (int)a->a_batch * p.n_tiles;
   const int num_kb = (int)((a->K + kBK - 1) / kBK);
+  if (BN % 32 != 0 || a->N % BN != 0) splits = 1;  // ragged column tiles exist only in the direct epilogue
   // split-K needs the caller's workspace: [splits][rows][N] fp32 partial sums
   const size_t per_split = (size_t)a->a_batch * (size_t)a->a_rows * (size_t)a->N * 4;
   while (splits > 1 && (!a->workspace || per_split * (size_t)splits > (size_t)a->workspace_bytes)) --splits;
@@ -747,25 +861,41 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, cudaStream_t stream) 
   p.kb_per_split = (num_kb + splits - 1) / splits;
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
   p.ws_partial = (float*)a->workspace;
+  p.a_box_bytes = a_box_rows * kBK * 2;
+  p.stage_bytes = p.a_box_bytes + L::kWBytes;
+  p.stages = L::kPadOff / p.stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(gemm_tc_kernel<%d,%d>, smem %d): %s", MT, BN, L::kTotal, cudaGetErrorString(e));
+      set_error("cudaFuncSetAttribute(gemm_tc_kernel<%d,%d>, smem %d): %s", MT, BN, kSmemTotal, cudaGetErrorString(e));
       return UVX_ERR_CUDA;
     }
     attr_set = true;
   }
   const int units = p.num_tiles * p.splits;
   const int grid = units < num_sms() ? units : num_sms();
-  launch_k(gemm_tc_kernel<MT, BN>, dim3((unsigned)grid), dim3(kThreads), L::kTotal, stream, tmA, tmW, p);
+  launch_k(gemm_tc_kernel<MT, BN>, dim3((unsigned)grid), dim3(L::kThreads), kSmemTotal, stream, tmA, tmW, p);
   int rc = check_launch("gemm_tc_kernel");
-  if (rc || p.splits == 1) return rc;
+  if (rc) return rc;
+  const bool want_norm = a->norm_w && a->norm_out;
+  if (p.splits == 1) {
+    if (!want_norm) return UVX_OK;
+    // direct epilogue (tile-local): the row norm runs as its own kernel on the finished rows
+    return uvx_rmsnorm(a->C, a->norm_w, a->norm_out, a->a_batch * a->a_rows, a->N, a->c_row_stride, 0, 0, 0, a->norm_eps, stream);
+  }
+  if (want_norm && !p.out_f32 && a->N <= 8192 && !a->c_row_map && a->act == UVX_ACT_NONE) {
+    launch_k(splitk_reduce_rmsnorm_kernel, dim3((unsigned)(a->a_batch * a->a_rows)), dim3(256), 0, stream, p);
+    return check_launch("splitk_reduce_rmsnorm_kernel");
+  }
   const int64_t total = a->a_batch * a->a_rows * (a->N / 8);
   int64_t blocks = (total + 255) / 256;
   if (blocks > (int64_t)num_sms() * 8) blocks = (int64_t)num_sms() * 8;
   launch_k(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, p);
-  return check_launch("splitk_reduce_kernel");
+  rc = check_launch("splitk_reduce_kernel");
+  if (rc || !want_norm) return rc;
+  return uvx_rmsnorm(a->C, a->norm_w, a->norm_out, a->a_batch * a->a_rows, a->N, a->c_row_stride, 0, 0, 0, a->norm_eps, stream);
 }
 
 template <int BN>
@@ -821,7 +951,9 @@ static int launch_gemm_2sm(const uvx_gemm_args* a, cudaStream_t stream) {
   const int max_pairs = num_sms() / 2;
   const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
   launch_k(gemm_tc2sm_kernel<BN>, dim3((unsigned)(2 * pairs)), dim3(kThreads), L::kTotal, stream, tmA, tmW, p);
-  return check_launch("gemm_tc2sm_kernel");
+  int rc = check_launch("gemm_tc2sm_kernel");
+  if (rc || !(a->norm_w && a->norm_out)) return rc;
+  return uvx_rmsnorm(a->C, a->norm_w, a->norm_out, a->a_batch * a->a_rows, a->N, a->c_row_stride, 0, 0, 0, a->norm_eps, stream);
 }
 
 }  // namespace uvx
@@ -850,6 +982,12 @@ static void pick_cfg(int64_t rows, int64_t batch, int64_t N, int64_t K, int* cfg
     // weight-streaming regime (LLM prefill at B=1, projector): one CTA tile spans every row, W is read once
     mt = 2;
     bn = (N % 256 == 0 && N / 256 >= sms / 2) ? 256 : (N % 128 == 0 ? 128 : 64);
+    // 208-wide tiles (ragged last tile) when they spread the weight stream over more SMs per wave: N = 28672 is 112
+    // tiles of 256 (76 % of the SMs) but 138 tiles of 208 (93 %)
+    if (bn == 256) {
+      const int64_t t256 = N / 256, t208 = (N + 207) / 208;
+      if (((t208 + sms - 1) / sms) * 208 < ((t256 + sms - 1) / sms) * 256) bn = 208;
+    }
     if (bn == 128 && 2 * (N / 128) >= (sms * 3) / 5 && num_kb <= 80) mt = 1;  // enough 128x128 tiles: skip split-K + reduce
   } else {
     // tensor-bound regime (encoder, training): 128-row tiles; 256-wide when that still gives >= ~1.3 waves of tiles
@@ -858,11 +996,11 @@ static void pick_cfg(int64_t rows, int64_t batch, int64_t N, int64_t K, int* cfg
     if (N % 256 == 0 && m_tiles * (N / 256) >= (sms * 4) / 3) bn = 256;
     else bn = (N % 128 == 0 && m_tiles * (N / 128) >= sms / 2) ? 128 : 64;
   }
-  if (forced > 0 && N % (forced % 1000) == 0) {
+  if (forced > 0 && (N % (forced % 1000) == 0 || forced % 1000 == 208)) {
     mt = forced / 1000;
     bn = forced % 1000;
   }
-  const int64_t tiles = ((rows + mt * 128 - 1) / (mt * 128)) * batch * (N / bn);
+  const int64_t tiles = ((rows + mt * 128 - 1) / (mt * 128)) * batch * ((N + bn - 1) / bn);
   int sp = 1;
   if (tiles * 2 <= sms && num_kb >= 16) {  // too few tiles to occupy the SMs: split K (>= 8 k-blocks per split)
     sp = (int)(sms / tiles);
@@ -890,6 +1028,9 @@ extern "C" int uvx_gemm_bf16(const uvx_gemm_args* a, uvx_stream_t stream_) {
               "uvx_gemm_bf16: output / residual strides must be multiples of 8");
   UVX_REQUIRE(a->a_rows < (1ll << 31) && a->K < (1ll << 31) && a->N < (1ll << 31), "uvx_gemm_bf16: dimension too large");
   UVX_REQUIRE(!a->workspace || (uintptr_t)a->workspace % 256 == 0, "uvx_gemm_bf16: workspace must be 256-byte aligned");
+  UVX_REQUIRE(!(a->norm_w && a->norm_out) || (a->out_dtype == UVX_DT_BF16 && !a->c_row_map && a->c_row_offset == 0 &&
+                                              (a->a_batch == 1 || a->c_batch_rows == a->a_rows)),
+              "uvx_gemm_bf16: fused RMSNorm needs a plain bf16 output");
   int cfg, splits;
   pick_cfg(a->a_rows, a->a_batch, a->N, a->K, &cfg, &splits);
   switch (cfg) {
@@ -899,6 +1040,8 @@ extern "C" int uvx_gemm_bf16(const uvx_gemm_args* a, uvx_stream_t stream_) {
     case 2064: return launch_gemm<2, 64>(a, splits, stream);
     case 2128: return launch_gemm<2, 128>(a, splits, stream);
     case 2256: return launch_gemm<2, 256>(a, splits, stream);
+    case 1208: return launch_gemm<1, 208>(a, splits, stream);
+    case 2208: return launch_gemm<2, 208>(a, splits, stream);
     case 4128: return launch_gemm_2sm<128>(a, stream);
     case 4256: return launch_gemm_2sm<256>(a, stream);
     default: return launch_gemm<1, 64>(a, splits, stream);

@@ -18,6 +18,7 @@ There is no CPU fallback: tensors must be CUDA tensors and ``libuvx.so`` must be
 from __future__ import annotations
 
 import dataclasses
+import os
 from typing import Optional
 
 import torch
@@ -27,6 +28,7 @@ from transformers.modeling_outputs import CausalLMOutputWithPast
 from . import ops
 from .config import LossConfig, LossFunction, UltravoxConfig
 
+FUSE_NORM = os.environ.get("UVX_FUSE_NORM", "1") != "0"   # tuning switch: RMSNorm fused into the o_proj / down_proj split-K pass
 BF16 = torch.bfloat16
 
 
@@ -389,9 +391,10 @@ class UltravoxModel(nn.Module):
         gu = torch.empty(B * S, 2 * ffn, dtype=BF16, device=dev)
         act = torch.empty(B * S, ffn, dtype=BF16, device=dev)
         rs = qkv.stride(0)
-        for li, layer in enumerate(lm.model.layers):
+        layers = lm.model.layers
+        ops.rmsnorm(h, layers[0].input_layernorm.weight, eps, out=x)
+        for li, layer in enumerate(layers):
             sa, mlp = layer.self_attn, layer.mlp
-            ops.rmsnorm(h, layer.input_layernorm.weight, eps, out=x)
             ops.linear(x, sa.qkv_w, out=qkv)
             ops.rope_(qkv, nq, nkv, hd, cos, sin, rows_per_seq=S, pos_offset=past)
             if cache is None:
@@ -404,14 +407,19 @@ class UltravoxModel(nn.Module):
                 ops.attention(qkv.data_ptr(), kc.data_ptr(), vc.data_ptr(), att, B, nq, nkv, S, past + S, hd,
                               (rs, S * rs, nkv * hd, smax * nkv * hd, nkv * hd, smax * nkv * hd, nq * hd, S * nq * hd),
                               hd ** -0.5, True, kv_len, 0)
-            ops.linear(att, sa.o_proj.weight, residual=h, out=h)
-            ops.rmsnorm(h, layer.post_attention_layernorm.weight, eps, out=x)
+            # o_proj / down_proj write the residual stream AND the RMSNorm the next block reads (fused into split-K's pass 2)
+            ops.linear(att, sa.o_proj.weight, residual=h, out=h, norm=(layer.post_attention_layernorm.weight, eps, x) if FUSE_NORM else None)
+            if not FUSE_NORM:
+                ops.rmsnorm(h, layer.post_attention_layernorm.weight, eps, out=x)
             ops.linear(x, mlp.gate_up_w, out=gu)
             ops.swiglu(gu, gate_first=True, out=act)
-            ops.linear(act, mlp.down_proj.weight, residual=h, out=h)
+            nxt = layers[li + 1].input_layernorm.weight if li + 1 < len(layers) else lm.model.norm.weight
+            ops.linear(act, mlp.down_proj.weight, residual=h, out=h, norm=(nxt, eps, x) if FUSE_NORM else None)
+            if not FUSE_NORM:
+                ops.rmsnorm(h, nxt, eps, out=x)
         if cache is not None:
             cache.length = past + S
-        return ops.rmsnorm(h, lm.model.norm.weight, eps, out=x).view(B, S, Dm)
+        return x.view(B, S, Dm)
 
     def new_cache(self, batch: int, max_len: int) -> KVCache:
         tc, lm = self.config.text_config, self.language_model

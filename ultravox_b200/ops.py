@@ -87,7 +87,7 @@ def gemm_raw(A_ptr: int, a_batch: int, a_rows: int, K: int, a_row_stride: int, a
              W: torch.Tensor, C_t: torch.Tensor, c_row_stride: int, c_batch_rows: int, c_row_offset: int = 0,
              c_row_map: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
              R: Optional[torch.Tensor] = None, r_row_stride: int = 0, r_batch_stride: int = 0,
-             alpha: float = 1.0, act: int = ACT_NONE) -> None:
+             alpha: float = 1.0, act: int = ACT_NONE, norm: Optional[tuple] = None) -> None:
     a = GemmArgs()
     a.A, a.a_batch, a.a_rows, a.K = A_ptr, a_batch, a_rows, K
     a.a_row_stride, a.a_batch_stride = a_row_stride, a_batch_stride
@@ -100,13 +100,17 @@ def gemm_raw(A_ptr: int, a_batch: int, a_rows: int, K: int, a_row_stride: int, a
     a.out_dtype = 1 if C_t.dtype == torch.float32 else 0
     ws = gemm_workspace(C_t.device)
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    if norm is not None:                       # (weight, eps, out): fused RMSNorm of the finished rows
+        a.norm_w, a.norm_eps, a.norm_out = norm[0].data_ptr(), float(norm[1]), norm[2].data_ptr()
     check(lib().uvx_gemm_bf16(C.byref(a), _stream()), "uvx_gemm_bf16")
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
            residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-           out_dtype=BF16, row_map: Optional[torch.Tensor] = None, alpha: float = 1.0) -> torch.Tensor:
-    """y = act(alpha * x @ w.T + bias) + residual for x [..., K] (last dim contiguous, uniform row stride)."""
+           out_dtype=BF16, row_map: Optional[torch.Tensor] = None, alpha: float = 1.0,
+           norm: Optional[tuple] = None) -> torch.Tensor:
+    """y = act(alpha * x @ w.T + bias) + residual for x [..., K] (last dim contiguous, uniform row stride).
+    ``norm=(weight, eps, out)`` additionally writes out = RMSNorm(y) (fused into the split-K reduction when possible)."""
     _cuda(x, BF16, "x"), _cuda(w, BF16, "w")
     K = x.shape[-1]
     x2 = x.reshape(-1, K)
@@ -120,7 +124,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     if residual is not None:
         r2 = residual.reshape(-1, N)
     gemm_raw(x2.data_ptr(), 1, M, K, x2.stride(0), 0, w, o2, o2.stride(-2) if o2.dim() >= 2 else N, M, 0,
-             row_map, bias, r2, r2.stride(0) if r2 is not None else 0, 0, alpha, act)
+             row_map, bias, r2, r2.stride(0) if r2 is not None else 0, 0, alpha, act, norm)
     return out
 
 
