@@ -104,6 +104,10 @@ typedef struct uvx_gemm_args {
 int uvx_gemm_bf16(const uvx_gemm_args* args, uvx_stream_t stream);
 /* tuning hook: force tile config MT*1000+BN (0 = heuristic) and split-K count (0 = heuristic) for later calls */
 int uvx_debug_gemm_override(int cfg, int splits);
+/* tuning hook: force the thread-block cluster shape cm x cn (row tiles x column tiles sharing operand loads; 0 = heuristic) */
+int uvx_debug_gemm_cluster(int cm, int cn);
+/* tuning hook: 1 = 1-SM kernel without its MMAs (load pipeline alone), 2 = without its TMA loads; outputs are garbage */
+int uvx_debug_gemm_mode(int mode);
 
 /* ---------------------------------------------------------------------------------------------
  * Row-wise normalisations (fp32 statistics, bf16 in/out).

@@ -62,10 +62,11 @@ def test_gemm_forced_configs_and_split_k(ops, cfg, splits):
     assert torch.equal(y1, y2)  # split-K reduction order is fixed -> bitwise reproducible
 
 
-@pytest.mark.parametrize("cfg", [4128, 4256])
+@pytest.mark.parametrize("cfg", [4128, 4256, 5416, 5512])
 @pytest.mark.parametrize("M,N,K", [(256, 256, 64), (1500, 1280, 1280), (201, 512, 4096), (700, 768, 200)])
 def test_gemm_two_sm_pairs(ops, cfg, M, N, K):
-    """cta_group::2 kernel (cluster of 2 CTAs, 256-row pair tiles), all epilogue features, M / K tails."""
+    """cta_group::2 kernel (cluster of 2 CTAs, 256-row pair tiles; 5xxx = two accumulators per pair tile, ragged N),
+    all epilogue features, M / K tails."""
     from ultravox_b200 import _lib
     x, w, b, r = rnd(M, K, seed=1), rnd(N, K, scale=0.05, seed=2), rnd(N, seed=3), rnd(M, N, seed=4)
     ref = F.gelu(x.float() @ w.float().T + b.float()) + r.float()
@@ -108,6 +109,27 @@ def test_gemm_fused_rmsnorm(ops, cfg, splits):
         _lib.lib().uvx_debug_gemm_override(0, 0)
     assert rel(h, x.float() @ w.float().T + r.float()) < 1e-3
     assert torch.equal(xn, ops.rmsnorm(h, nw, 1e-5))
+
+
+@pytest.mark.parametrize("cm,cn", [(1, 2), (2, 1), (2, 2), (1, 4)])
+@pytest.mark.parametrize("cfg,splits,M,N,K", [(2208, 1, 201, 1024, 1024), (2128, 3, 201, 768, 2048), (1128, 1, 1500, 1280, 640),
+                                              (1256, 1, 700, 1280, 200), (1064, 2, 130, 192, 1024)])
+def test_gemm_multicast_clusters(ops, cm, cn, cfg, splits, M, N, K):
+    """Thread-block clusters sharing operand tiles by TMA multicast (A across cn column tiles, W across cm row tiles),
+    including cluster padding tiles (tile counts not divisible by the cluster shape) and split-K."""
+    from ultravox_b200 import _lib
+    x, w, b, r = rnd(M, K, seed=1), rnd(N, K, scale=0.05, seed=2), rnd(N, seed=3), rnd(M, N, seed=4)
+    ref = x.float() @ w.float().T + b.float() + r.float()
+    _lib.lib().uvx_debug_gemm_override(cfg, splits)
+    _lib.lib().uvx_debug_gemm_cluster(cm, cn)
+    try:
+        y = ops.linear(x, w, bias=b, residual=r)
+        y2 = ops.linear(x, w, bias=b, residual=r)
+    finally:
+        _lib.lib().uvx_debug_gemm_override(0, 0)
+        _lib.lib().uvx_debug_gemm_cluster(0, 0)
+    assert rel(y, ref) < 1e-3
+    assert torch.equal(y, y2)
 
 
 def test_gemm_row_map(ops):

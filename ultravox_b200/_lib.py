@@ -44,6 +44,8 @@ SIGNATURES = {
     "uvx_mel_to_timemajor": (C.c_int, [c_vp, c_i64, C.c_int, c_i64, c_vp, c_vp]),
     "uvx_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), c_vp]),
     "uvx_debug_gemm_override": (C.c_int, [C.c_int, C.c_int]),
+    "uvx_debug_gemm_cluster": (C.c_int, [C.c_int, C.c_int]),
+    "uvx_debug_gemm_mode": (C.c_int, [C.c_int]),
     "uvx_layernorm": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_vp]),
     "uvx_rmsnorm": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_vp]),
     "uvx_attention": (C.c_int, [C.POINTER(AttnArgs), c_vp]),

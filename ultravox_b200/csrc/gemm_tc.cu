@@ -21,9 +21,9 @@
 
 namespace uvx {
 
+static int g_gemm_dbg = 0;  // uvx_debug_gemm_mode
 static constexpr int kBM = 128;
 static constexpr int kBK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
-static constexpr int kThreads = 192;
 
 struct GemmParams {
   int64_t a_rows, a_batch, K, N;
@@ -45,6 +45,13 @@ struct GemmParams {
   int a_box_bytes;  // bytes of the A box in one ring stage (box rows * 128): fewer rows than MT*128 when M is small
   int stage_bytes;  // a_box_bytes + BN * 128
   int stages;       // ring depth that fits the shared-memory budget (2..8)
+  // thread-block cluster of cm x cn CTAs computing cm row tiles x cn column tiles: the A box of a row tile is loaded once
+  // (1/cn slice per CTA, TMA multicast) for its cn CTAs and the W box once for its cm CTAs - the GEMMs are bound by bytes
+  // INTO the SMs (L2 -> SM fabric, ~9 TB/s aggregate), so sharing operand tiles is what raises the ceiling
+  int cm, cn;
+  int a_slice_rows, w_slice_rows;
+  int m_groups, n_groups;  // ceil(tiles / cm), ceil(n_tiles / cn)
+  int dbg_mode;            // tuning only: 1 = skip the MMAs (load pipeline alone), 2 = skip the TMA loads (MMA pipeline alone)
 };
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -83,6 +90,29 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
       "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::
+          "r"(smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;" ::
+          "r"(smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -111,6 +141,12 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -430,6 +466,224 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+
+// Experimental twin of gemm_tc_kernel (tuning hooks only: uvx_debug_gemm_cluster / uvx_debug_gemm_mode): adds thread-block
+// clusters that share operand tiles by TMA multicast and the pipeline-isolation modes.  It is a separate kernel because the
+// single-thread producer / MMA loops are latency-critical - compiling the extra code into the production kernel cost 3-8 %
+// of the whole prefill step.  Measured outcome (profiles/r1_gemm_pipeline_isolation.md): multicast at cluster sizes <= 4
+// does not reduce L2 traffic (the L2 already merges identical requests inside a short window), so production does not use it.
+template <int MT, int BN>
+__global__ void __launch_bounds__(SmemLayout<MT, BN>::kThreads, 1)
+gemm_tc_kernel_x(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+  pdl_trigger();
+  using L = SmemLayout<MT, BN>;
+  constexpr int kAcc = L::kAcc;
+  constexpr int kEpiWarps = L::kEpiWarps;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full_bar = (uint64_t*)(smem + kBarOff);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m_total = p.m_tiles * (int)p.a_batch;
+  const int num_kb = (int)((p.K + kBK - 1) / kBK);
+  const int stages = p.stages;
+  // cluster geometry (cm = cn = 1: plain launch, no cluster instructions on the data path)
+  const int cm = p.cm, cn = p.cn;
+  const int csize = cm * cn;
+  const bool clustered = csize > 1;
+  const uint32_t crank = clustered ? cluster_rank() : 0u;
+  const int rm = (int)crank % cm, rn = (int)crank / cm;
+  uint16_t mask_a = 0, mask_w = 0;
+  for (int j = 0; j < cn; ++j) mask_a |= (uint16_t)(1u << (rm + cm * j));   // CTAs working on the same row tile
+  for (int i = 0; i < cm; ++i) mask_w |= (uint16_t)(1u << (i + cm * rn));   // CTAs working on the same column tile
+  const uint16_t mask_e = mask_a | mask_w;
+  const int m_groups = p.m_groups;
+  const int num_units = p.m_groups * p.n_groups * p.splits;   // (cluster-level) work units
+  const int unit0 = (int)blockIdx.x / csize, unit_step = (int)gridDim.x / csize;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128B-swizzle atoms need a 1024-byte aligned ring
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], cm + cn - 1);  // one (multicast) commit from every CTA that reads what lands here
+    }
+    for (int a = 0; a < kAcc; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], kEpiWarps);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)L::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (clustered) cluster_barrier();  // peers' barriers are initialised before anything is multicast at them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // set-up above overlapped the previous kernel's tail; its outputs are visible from here on
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+      int s = 0;           // ring slot and its phase: the ring runs ahead across tile boundaries
+      uint32_t ph = 0;
+      for (int unit = unit0; unit < num_units; unit += unit_step) {
+        const int tile = unit / p.splits, split = unit % p.splits;
+        const int tm_idx = (tile % m_groups) * cm + rm;  // consecutive units share the W tiles
+        const int tn_idx = (tile / m_groups) * cn + rn;
+        const int b = tm_idx / p.m_tiles;  // padding tiles (index past the end) load zero-filled boxes
+        const int m0 = (tm_idx % p.m_tiles) * (MT * kBM);
+        const int n0 = tn_idx * BN;
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(num_kb, kb_begin + p.kb_per_split);
+        // every CTA walks K starting at a different k-block (and wraps): at M <= 256 all CTAs read the SAME activation
+        // tile, and in lockstep they would all hit the same L2 lines at the same time
+        const int nk = kb_end - kb_begin;
+        const int rot = (int)(((unsigned)tile * 7u + (unsigned)split * 3u) % (unsigned)nk);
+        for (int i = 0; i < nk; ++i) {
+          const int kb = kb_begin + (i + rot < nk ? i + rot : i + rot - nk);
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* sa = smem + s * p.stage_bytes;
+          if (p.dbg_mode == 2) {
+            mbar_arrive(&full_bar[s]);
+            if (++s == stages) { s = 0; ph ^= 1u; }
+            continue;
+          }
+          mbar_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
+          if (cn == 1) tma_load_3d(sa, &tmA, kb * kBK, m0, b, &full_bar[s]);
+          else tma_load_3d_mc(sa + rn * p.a_slice_rows * (kBK * 2), &tmA, kb * kBK, m0 + rn * p.a_slice_rows, b, &full_bar[s], mask_a);
+          if (cm == 1) tma_load_2d(sa + p.a_box_bytes, &tmW, kb * kBK, n0, &full_bar[s]);
+          else tma_load_2d_mc(sa + p.a_box_bytes + rm * p.w_slice_rows * (kBK * 2), &tmW, kb * kBK, n0 + rm * p.w_slice_rows, &full_bar[s], mask_w);
+          if (++s == stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      int s = 0;
+      uint32_t ph = 0, tcount = 0;
+      for (int unit = unit0; unit < num_units; unit += unit_step, ++tcount) {
+        const int split = unit % p.splits;
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(num_kb, kb_begin + p.kb_per_split);
+        const uint32_t acc = tcount % kAcc;
+        const uint32_t aph = (tcount / kAcc) & 1u;
+        mbar_wait(&tmem_empty[acc], aph ^ 1u);  // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (MT * L::kBNT);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * p.stage_bytes);
+          const uint64_t dw = make_smem_desc(sa + p.a_box_bytes);
+          if (p.dbg_mode == 1) {
+            mbar_arrive(&empty_bar[s]);
+            if (++s == stages) { s = 0; ph ^= 1u; }
+            continue;
+          }
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            // rows past the A box (M small) read whatever follows in shared memory: they only feed accumulator rows
+            // >= a_rows, which the epilogue never stores
+            const uint64_t da = make_smem_desc(sa + mt * (kBM * kBK * 2));
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+              umma_f16(d_tmem + mt * L::kBNT, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            }
+          }
+          if (clustered) umma_commit_mc(&empty_bar[s], mask_e);  // tells every CTA that loads into this CTA's slot
+          else umma_commit(&empty_bar[s]);                       // frees the smem slot once these MMAs have read it
+          if (++s == stages) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulators of this tile complete
+      }
+    }
+  } else {
+    // ---- epilogue: warp w reads TMEM lane quarter w % 4; with 8 warps the two warps of a quarter take alternate chunks
+    const int q = warp & 3;
+    const int cpar = (warp - 2) >> 2;              // 0 for the first four epilogue warps, 1 for the second four
+    constexpr int cstep = kEpiWarps / 4;
+    uint32_t tcount = 0;
+    for (int unit = unit0; unit < num_units; unit += unit_step, ++tcount) {
+      const int tile = unit / p.splits, split = unit % p.splits;
+      const int tm_idx = (tile % m_groups) * cm + rm;
+      const int tn_idx = (tile / m_groups) * cn + rn;
+      const bool valid_tile = tm_idx < tiles_m_total && tn_idx < p.n_tiles;  // cluster padding computes zeros, stores nothing
+      const int b = tm_idx / p.m_tiles;
+      const int m0 = (tm_idx % p.m_tiles) * (MT * kBM);
+      const int n0 = tn_idx * BN;
+      const uint32_t acc = tcount % kAcc;
+      const uint32_t aph = (tcount / kAcc) & 1u;
+      mbar_wait(&tmem_full[acc], aph);
+      tc_fence_after();
+      const bool direct = p.splits == 1;
+      if (!direct) {
+        // split-K: park the raw fp32 partial tile in the workspace; splitk_reduce_kernel sums the splits in a fixed
+        // order and applies the epilogue (deterministic, and the reduction is spread over every SM)
+        float* part = p.ws_partial + (size_t)split * (size_t)(p.a_batch * p.a_rows) * (size_t)p.N;
+#pragma unroll 1
+        for (int mt = 0; mt < MT; ++mt) {
+          if (!valid_tile || (int64_t)m0 + mt * kBM + q * 32 >= p.a_rows) continue;
+          const int64_t m = (int64_t)m0 + mt * kBM + q * 32 + lane;
+          const bool row_ok = m < p.a_rows;
+#pragma unroll 1
+          for (int c = cpar; c < L::kChunks; c += cstep) {
+            uint32_t raw[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * L::kBNT) + (uint32_t)(mt * L::kBNT + c * 32), raw);
+            tmem_ld_wait();
+            if (row_ok) {
+              uint4* dst = reinterpret_cast<uint4*>(part + ((size_t)b * p.a_rows + m) * p.N + n0 + c * 32);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) dst[g] = make_uint4(raw[4 * g], raw[4 * g + 1], raw[4 * g + 2], raw[4 * g + 3]);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);  // accumulator stage is free again
+        continue;
+      }
+      float* pad = reinterpret_cast<float*>(smem + L::kPadOff) + (warp - 2) * (kStageBytesPerWarp / 4);
+      const int64_t n_lim = (int64_t)n0 + BN < p.N ? (int64_t)n0 + BN : p.N;  // ragged last column tile (N % BN != 0)
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        const int64_t m_warp0 = (int64_t)m0 + mt * kBM + q * 32;
+        if (!valid_tile || m_warp0 >= p.a_rows) continue;  // sub-tile entirely out of range (warp-uniform)
+#pragma unroll 1
+        for (int c = cpar; c < L::kChunks; c += cstep) {
+          if ((int64_t)n0 + c * 32 >= n_lim) break;
+          uint32_t raw[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * L::kBNT) + (uint32_t)(mt * L::kBNT + c * 32), raw);
+          tmem_ld_wait();
+          epilogue_chunk(p, raw, pad, lane, b, m_warp0, (int64_t)n0 + c * 32, n_lim);
+        }
+      }
+      // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator stage back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (clustered) cluster_barrier();  // no CTA leaves while a peer can still multicast into it or signal its barriers
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L::kTmemCols)
+                 : "memory");
+  }
+}
+
 // =====================================================================================================
 // 2-SM variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BN tile with ONE tcgen05.mma per k-step.
 // CTA r stages rows [r*128, r*128+128) of A and rows [r*BN/2, (r+1)*BN/2) of W; the tensor core of the leader reads both
@@ -483,34 +737,41 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
                : "memory");
 }
 
-template <int BN>
+// Pair tile = 256 rows x (NH * BNH) columns: NH tcgen05.mma (N = BNH) per k-step into NH accumulators.  NH = 2 doubles the
+// columns a row tile of A is used for (A is re-read once per column tile, and the GEMMs are bound by bytes delivered from
+// L2): 256 x 416 for the Llama gate/up projection at M = 201, 256 x 512 for the encoder fc1 / qkv.
+template <int BNH, int NH, int EPW>
 struct Smem2 {
-  static constexpr int kABytes = kBM * kBK * 2;        // this CTA's 128 rows
-  static constexpr int kWBytes = (BN / 2) * kBK * 2;   // this CTA's half of the W tile
+  static constexpr int kThreads = 64 + 32 * EPW;
+  static constexpr int kABytes = kBM * kBK * 2;               // this CTA's 128 rows
+  static constexpr int kWHalfBytes = (BNH / 2) * kBK * 2;     // this CTA's half of one N = BNH operand
+  static constexpr int kWBytes = NH * kWHalfBytes;
   static constexpr int kStageBytes = kABytes + kWBytes;
-  static constexpr int kStages = (196 * 1024) / kStageBytes > 8 ? 8 : (196 * 1024) / kStageBytes;
-  static constexpr int kAcc = (BN * 2 <= 512) ? 2 : 1;
-  static constexpr int kTmemCols = kAcc * BN < 32 ? 32 : kAcc * BN;
-  static constexpr int kBarOff = kStages * kStageBytes;
-  static constexpr int kPadOff = kBarOff + 256;
-  static constexpr int kTotal = kPadOff + 4 * kStageBytesPerWarp + 1024;
-  static_assert(kTotal <= 227 * 1024, "shared memory budget");
+  static constexpr int kBNT = BNH <= 128 ? 128 : 256;         // TMEM column stride of one accumulator
+  static constexpr int kAcc = (NH * kBNT * 2 <= 512) ? 2 : 1;
+  static constexpr int kTmemCols = kAcc * NH * kBNT;
+  static constexpr int kChunks = (BNH + 31) / 32;
+  static constexpr int kPadOff = kBarOff - EPW * kStageBytesPerWarp;
+  static constexpr int kStages = kPadOff / kStageBytes > kMaxStages ? kMaxStages : kPadOff / kStageBytes;
+  static_assert(kStages >= 2, "ring too shallow");
+  static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns must be a power of two <= 512");
+  static_assert((BNH / 2) % 8 == 0 && BNH % 16 == 0 && BNH <= 256, "UMMA N / swizzle-atom constraints");
 };
 
-template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+template <int BNH, int NH, int EPW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Smem2<BNH, NH, EPW>::kThreads, 1)
 gemm_tc2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
   pdl_trigger();
-  using L = Smem2<BN>;
+  using L = Smem2<BNH, NH, EPW>;
   constexpr int kStages = L::kStages;
   constexpr int kAcc = L::kAcc;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = (uint64_t*)(smem + L::kBarOff);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full = empty_bar + kStages;
-  uint64_t* tmem_empty = tmem_full + kAcc;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + kAcc);
+  constexpr int BN = NH * BNH;  // columns of the pair tile
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full_bar = (uint64_t*)(smem + kBarOff);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -520,13 +781,14 @@ gemm_tc2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int num_kb = (int)((p.K + kBK - 1) / kBK);
 
   if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 2);   // leader's expect_tx arrive + the peer producer's arrive
       mbar_init(&empty_bar[s], 1);  // one multicast commit from the leader's MMA thread
     }
     for (int a = 0; a < kAcc; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 8);  // 4 epilogue warps x 2 CTAs (used on the leader only)
+      mbar_init(&tmem_empty[a], 2 * EPW);  // epilogue warps of both CTAs (used on the leader only)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -553,7 +815,7 @@ gemm_tc2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int tn_idx = tile / tiles_m_total;
         const int b = tm_idx / p.m_tiles;
         const int m0 = (tm_idx % p.m_tiles) * (2 * kBM) + (int)rank * kBM;
-        const int n0 = tn_idx * BN + (int)rank * (BN / 2);
+        const int n0 = tn_idx * BN + (int)rank * (BNH / 2);  // operand h of this CTA: W rows [n0 + h*BNH, + BNH/2)
         const int rot = (int)(((unsigned)tile * 7u) % (unsigned)num_kb);
         for (int i = 0; i < num_kb; ++i, ++it) {
           const int kb = i + rot < num_kb ? i + rot : i + rot - num_kb;
@@ -562,7 +824,9 @@ gemm_tc2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* sa = smem + s * L::kStageBytes;
           tma2_load_3d(sa, &tmA, kb * kBK, m0, b, &full_bar[s]);
-          tma2_load_2d(sa + L::kABytes, &tmW, kb * kBK, n0, &full_bar[s]);
+#pragma unroll
+          for (int h = 0; h < NH; ++h)
+            tma2_load_2d(sa + L::kABytes + h * L::kWHalfBytes, &tmW, kb * kBK, n0 + h * BNH, &full_bar[s]);
           if (leader) mbar_expect_tx(&full_bar[s], (uint32_t)(2 * L::kStageBytes));
           else mbar_arrive_leader(&full_bar[s]);
         }
@@ -570,14 +834,14 @@ gemm_tc2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BNH >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       uint32_t it = 0, tcount = 0;
       for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++tcount) {
         const uint32_t acc = tcount % kAcc;
         const uint32_t aph = (tcount / kAcc) & 1u;
         mbar_wait(&tmem_empty[acc], aph ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * (NH * L::kBNT);
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1u;
@@ -585,10 +849,13 @@ gemm_tc2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
           const uint64_t da = make_smem_desc(sa);
-          const uint64_t dw = make_smem_desc(sa + L::kABytes);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k)
-            umma2_f16(d_tmem, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int h = 0; h < NH; ++h) {
+            const uint64_t dw = make_smem_desc(sa + L::kABytes + h * L::kWHalfBytes);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma2_f16(d_tmem + h * L::kBNT, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
           umma2_commit_mc(&empty_bar[s]);
         }
         umma2_commit_mc(&tmem_full[acc]);
@@ -601,13 +868,14 @@ gemm_tc2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     const int q = warp & 3;
+    const int cpar = (warp - 2) >> 2;
+    constexpr int cstep = EPW / 4;
     uint32_t tcount = 0;
     for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++tcount) {
       const int tm_idx = tile % tiles_m_total;
       const int tn_idx = tile / tiles_m_total;
       const int b = tm_idx / p.m_tiles;
       const int m0 = (tm_idx % p.m_tiles) * (2 * kBM) + (int)rank * kBM;
-      const int n0 = tn_idx * BN;
       const uint32_t acc = tcount % kAcc;
       const uint32_t aph = (tcount / kAcc) & 1u;
       mbar_wait(&tmem_full[acc], aph);
@@ -616,11 +884,17 @@ gemm_tc2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int64_t m_warp0 = (int64_t)m0 + q * 32;
       if (m_warp0 < p.a_rows) {
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t raw[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c * 32), raw);
-          tmem_ld_wait();
-          epilogue_chunk(p, raw, pad, lane, b, m_warp0, (int64_t)n0 + c * 32, p.N);
+        for (int h = 0; h < NH; ++h) {
+          const int64_t n0 = (int64_t)tn_idx * BN + h * BNH;
+          const int64_t n_lim = n0 + BNH < p.N ? n0 + BNH : p.N;  // ragged last column tile
+#pragma unroll 1
+          for (int c = cpar; c < L::kChunks; c += cstep) {
+            if (n0 + c * 32 >= n_lim) break;
+            uint32_t raw[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (NH * L::kBNT) + (uint32_t)(h * L::kBNT + c * 32), raw);
+            tmem_ld_wait();
+            epilogue_chunk(p, raw, pad, lane, b, m_warp0, n0 + c * 32, n_lim);
+          }
         }
       }
       tc_fence_before();
@@ -808,23 +1082,26 @@ static int num_sms() {
 }
 
 template <int MT, int BN>
-static int launch_gemm(const uvx_gemm_args* a, int splits, cudaStream_t stream) {
+static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaStream_t stream) {
   using L = SmemLayout<MT, BN>;
   CUtensorMap tmA, tmW;
   // one row tile covers the whole problem: stage only round8(M) rows of A per k-block (more ring stages fit)
+  if (cm < 1 || cn < 1 || cm * cn > 8 || (BN / cm) % 8 != 0 || BN % cm != 0) cm = cn = 1;
   int a_box_rows = MT * kBM;
-  if (a->a_batch == 1 && a->a_rows <= MT * kBM) a_box_rows = (int)((a->a_rows + 7) / 8 * 8);
+  if (a->a_batch == 1 && a->a_rows <= MT * kBM) a_box_rows = (int)((a->a_rows + 8 * cn - 1) / (8 * cn) * (8 * cn));
+  if (a_box_rows % (8 * cn) != 0) cn = 1;
+  const int a_slice_rows = a_box_rows / cn, w_slice_rows = BN / cm;
   {
     uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->a_rows, (uint64_t)a->a_batch};
     uint64_t st[2] = {(uint64_t)a->a_row_stride * 2, (uint64_t)(a->a_batch > 1 ? a->a_batch_stride : a->a_row_stride) * 2};
-    uint32_t box[3] = {kBK, (uint32_t)a_box_rows, 1};
+    uint32_t box[3] = {kBK, (uint32_t)a_slice_rows, 1};
     int rc = encode_map(&tmA, a->A, 3, dims, st, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (rc) return rc;
   }
   {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     uint64_t st[1] = {(uint64_t)a->w_row_stride * 2};
-    uint32_t box[2] = {kBK, (uint32_t)BN};
+    uint32_t box[2] = {kBK, (uint32_t)w_slice_rows};
     int rc = encode_map(&tmW, a->W, 2, dims, st, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     if (rc) return rc;
   }
@@ -865,18 +1142,55 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, cudaStream_t stream) 
   p.stage_bytes = p.a_box_bytes + L::kWBytes;
   p.stages = L::kPadOff / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
+  p.cm = cm;
+  p.dbg_mode = g_gemm_dbg;
+  p.cn = cn;
+  p.a_slice_rows = a_slice_rows;
+  p.w_slice_rows = w_slice_rows;
+  p.m_groups = (p.m_tiles * (int)a->a_batch + cm - 1) / cm;
+  p.n_groups = (p.n_tiles + cn - 1) / cn;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel_x<MT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm_tc_kernel<%d,%d>, smem %d): %s", MT, BN, kSmemTotal, cudaGetErrorString(e));
       return UVX_ERR_CUDA;
     }
     attr_set = true;
   }
-  const int units = p.num_tiles * p.splits;
-  const int grid = units < num_sms() ? units : num_sms();
-  launch_k(gemm_tc_kernel<MT, BN>, dim3((unsigned)grid), dim3(L::kThreads), kSmemTotal, stream, tmA, tmW, p);
+  const int units = p.m_groups * p.n_groups * p.splits;  // cluster-level work units
+  const int csize = cm * cn;
+  UVX_REQUIRE(!(p.dbg_mode && csize > 1), "uvx_gemm_bf16: pipeline-isolation modes are for unclustered launches");
+  if (csize == 1) {
+    const int grid = units < num_sms() ? units : num_sms();
+    if (p.dbg_mode) launch_k(gemm_tc_kernel_x<MT, BN>, dim3((unsigned)grid), dim3(L::kThreads), kSmemTotal, stream, tmA, tmW, p);
+    else launch_k(gemm_tc_kernel<MT, BN>, dim3((unsigned)grid), dim3(L::kThreads), kSmemTotal, stream, tmA, tmW, p);
+  } else {
+    static int max_clusters[9] = {0};
+    if (max_clusters[csize] == 0) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(num_sms() / csize * csize));
+      cfg.blockDim = dim3(L::kThreads);
+      cfg.dynamicSmemBytes = kSmemTotal;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (unsigned)csize;
+      at[0].val.clusterDim.y = at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int n = 0;
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel_x<MT, BN>, &cfg);
+      if (e != cudaSuccess || n < 1) {
+        set_error("cudaOccupancyMaxActiveClusters(gemm_tc_kernel<%d,%d>, cluster %d): %s", MT, BN, csize, cudaGetErrorString(e));
+        return UVX_ERR_CUDA;
+      }
+      max_clusters[csize] = n;
+    }
+    const int clusters = units < max_clusters[csize] ? units : max_clusters[csize];
+    launch_k_cluster(gemm_tc_kernel_x<MT, BN>, dim3((unsigned)(clusters * csize)), dim3(L::kThreads), kSmemTotal, stream, (unsigned)csize, tmA,
+                     tmW, p);
+  }
   int rc = check_launch("gemm_tc_kernel");
   if (rc) return rc;
   const bool want_norm = a->norm_w && a->norm_out;
@@ -898,9 +1212,10 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, cudaStream_t stream) 
   return uvx_rmsnorm(a->C, a->norm_w, a->norm_out, a->a_batch * a->a_rows, a->N, a->c_row_stride, 0, 0, 0, a->norm_eps, stream);
 }
 
-template <int BN>
+template <int BNH, int NH, int EPW>
 static int launch_gemm_2sm(const uvx_gemm_args* a, cudaStream_t stream) {
-  using L = Smem2<BN>;
+  using L = Smem2<BNH, NH, EPW>;
+  constexpr int BN = NH * BNH;
   CUtensorMap tmA, tmW;
   {
     uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->a_rows, (uint64_t)a->a_batch};
@@ -912,7 +1227,7 @@ static int launch_gemm_2sm(const uvx_gemm_args* a, cudaStream_t stream) {
   {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     uint64_t st[1] = {(uint64_t)a->w_row_stride * 2};
-    uint32_t box[2] = {kBK, (uint32_t)(BN / 2)};
+    uint32_t box[2] = {kBK, (uint32_t)(BNH / 2)};
     int rc = encode_map(&tmW, a->W, 2, dims, st, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     if (rc) return rc;
   }
@@ -935,22 +1250,22 @@ static int launch_gemm_2sm(const uvx_gemm_args* a, cudaStream_t stream) {
   p.act = a->act;
   p.out_f32 = a->out_dtype == UVX_DT_F32;
   p.m_tiles = (int)((a->a_rows + 2 * kBM - 1) / (2 * kBM));
-  p.n_tiles = (int)(a->N / BN);
+  p.n_tiles = (int)((a->N + BN - 1) / BN);
   p.num_tiles = p.m_tiles * (int)a->a_batch * p.n_tiles;
   p.splits = 1;
   p.kb_per_split = (int)((a->K + kBK - 1) / kBK);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2sm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2sm_kernel<BNH, NH, EPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(gemm_tc2sm_kernel<%d>, smem %d): %s", BN, L::kTotal, cudaGetErrorString(e));
+      set_error("cudaFuncSetAttribute(gemm_tc2sm_kernel<%d,%d>, smem %d): %s", BNH, NH, kSmemTotal, cudaGetErrorString(e));
       return UVX_ERR_CUDA;
     }
     attr_set = true;
   }
   const int max_pairs = num_sms() / 2;
   const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
-  launch_k(gemm_tc2sm_kernel<BN>, dim3((unsigned)(2 * pairs)), dim3(kThreads), L::kTotal, stream, tmA, tmW, p);
+  launch_k(gemm_tc2sm_kernel<BNH, NH, EPW>, dim3((unsigned)(2 * pairs)), dim3(L::kThreads), kSmemTotal, stream, tmA, tmW, p);
   int rc = check_launch("gemm_tc2sm_kernel");
   if (rc || !(a->norm_w && a->norm_out)) return rc;
   return uvx_rmsnorm(a->C, a->norm_w, a->norm_out, a->a_batch * a->a_rows, a->N, a->c_row_stride, 0, 0, 0, a->norm_eps, stream);
@@ -959,12 +1274,25 @@ static int launch_gemm_2sm(const uvx_gemm_args* a, cudaStream_t stream) {
 }  // namespace uvx
 
 // Tile / split selection.  cfg = MT*1000 + BN; UVX_GEMM_CFG / UVX_GEMM_SPLITS (env, tuning only) override the heuristic.
-static int forced = -1, forced_splits = -1;
+static int forced = -1, forced_splits = -1, forced_cm = 0, forced_cn = 0;
 
 // tuning hook (scripts/gemm_sweep.py): force a tile config (MT*1000+BN, 0 = heuristic) and a split count (0 = heuristic)
 extern "C" int uvx_debug_gemm_override(int cfg, int splits) {
   forced = cfg;
   forced_splits = splits;
+  return UVX_OK;
+}
+
+// tuning hook: 1 = run the 1-SM kernel without its MMAs, 2 = without its TMA loads (results are garbage; timing only)
+extern "C" int uvx_debug_gemm_mode(int mode) {
+  uvx::g_gemm_dbg = mode;
+  return UVX_OK;
+}
+
+// tuning hook: force the thread-block cluster shape (cm row tiles x cn column tiles, 0 = heuristic)
+extern "C" int uvx_debug_gemm_cluster(int cm, int cn) {
+  forced_cm = cm;
+  forced_cn = cn;
   return UVX_OK;
 }
 
@@ -996,7 +1324,7 @@ static void pick_cfg(int64_t rows, int64_t batch, int64_t N, int64_t K, int* cfg
     if (N % 256 == 0 && m_tiles * (N / 256) >= (sms * 4) / 3) bn = 256;
     else bn = (N % 128 == 0 && m_tiles * (N / 128) >= sms / 2) ? 128 : 64;
   }
-  if (forced > 0 && (N % (forced % 1000) == 0 || forced % 1000 == 208)) {
+  if (forced > 0 && (N % (forced % 1000) == 0 || forced % 1000 == 208 || forced / 1000 == 5)) {
     mt = forced / 1000;
     bn = forced % 1000;
   }
@@ -1031,19 +1359,25 @@ extern "C" int uvx_gemm_bf16(const uvx_gemm_args* a, uvx_stream_t stream_) {
   UVX_REQUIRE(!(a->norm_w && a->norm_out) || (a->out_dtype == UVX_DT_BF16 && !a->c_row_map && a->c_row_offset == 0 &&
                                               (a->a_batch == 1 || a->c_batch_rows == a->a_rows)),
               "uvx_gemm_bf16: fused RMSNorm needs a plain bf16 output");
-  int cfg, splits;
+  int cfg, splits, cm = 1, cn = 1;
   pick_cfg(a->a_rows, a->a_batch, a->N, a->K, &cfg, &splits);
+  if (forced_cm > 0 && forced_cn > 0) {
+    cm = forced_cm;
+    cn = forced_cn;
+  }
   switch (cfg) {
-    case 1064: return launch_gemm<1, 64>(a, splits, stream);
-    case 1128: return launch_gemm<1, 128>(a, splits, stream);
-    case 1256: return launch_gemm<1, 256>(a, splits, stream);
-    case 2064: return launch_gemm<2, 64>(a, splits, stream);
-    case 2128: return launch_gemm<2, 128>(a, splits, stream);
-    case 2256: return launch_gemm<2, 256>(a, splits, stream);
-    case 1208: return launch_gemm<1, 208>(a, splits, stream);
-    case 2208: return launch_gemm<2, 208>(a, splits, stream);
-    case 4128: return launch_gemm_2sm<128>(a, stream);
-    case 4256: return launch_gemm_2sm<256>(a, stream);
-    default: return launch_gemm<1, 64>(a, splits, stream);
+    case 1064: return launch_gemm<1, 64>(a, splits, cm, cn, stream);
+    case 1128: return launch_gemm<1, 128>(a, splits, cm, cn, stream);
+    case 1256: return launch_gemm<1, 256>(a, splits, cm, cn, stream);
+    case 2064: return launch_gemm<2, 64>(a, splits, cm, cn, stream);
+    case 2128: return launch_gemm<2, 128>(a, splits, cm, cn, stream);
+    case 2256: return launch_gemm<2, 256>(a, splits, cm, cn, stream);
+    case 1208: return launch_gemm<1, 208>(a, splits, cm, cn, stream);
+    case 2208: return launch_gemm<2, 208>(a, splits, cm, cn, stream);
+    case 4128: return launch_gemm_2sm<128, 1, 4>(a, stream);
+    case 4256: return launch_gemm_2sm<256, 1, 4>(a, stream);
+    case 5416: return launch_gemm_2sm<208, 2, 4>(a, stream);   // 256 x 416 pair tiles (weight-streaming regime)
+    case 5512: return launch_gemm_2sm<256, 2, 8>(a, stream);   // 256 x 512 pair tiles (tensor-bound regime)
+    default: return launch_gemm<1, 64>(a, splits, cm, cn, stream);
   }
 }

@@ -55,6 +55,27 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
+
+// launch with a thread-block cluster of `cluster_x` CTAs along x (grid.x must be a multiple of it)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, unsigned cluster_x,
+                                    Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_x;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 #endif
 
 // ---- small device helpers --------------------------------------------------------------------
@@ -113,12 +134,14 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // bf16 result): one rcp + one ex2 + 8 FMA instead of erff's two divergent branches - the fc1 epilogue is issue-bound.
 __device__ __forceinline__ float gelu_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t, ex;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));   // 1 ulp-class, argument in [1, inf)
   float pl = fmaf(1.061405429f, t, -1.453152027f);
   pl = fmaf(pl, t, 1.421413741f);
   pl = fmaf(pl, t, -0.284496736f);
   pl = fmaf(pl, t, 0.254829592f);
-  const float half_erfc = 0.5f * pl * t * exp2f(-1.4426950408889634f * z * z);  // 0.5 * erfc(|x| / sqrt 2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-1.4426950408889634f * z * z));
+  const float half_erfc = 0.5f * pl * t * ex;  // 0.5 * erfc(|x| / sqrt 2)
   return x * (x >= 0.f ? 1.0f - half_erfc : half_erfc);
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
