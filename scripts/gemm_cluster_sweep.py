@@ -10,13 +10,13 @@ LLM_CL = [(1, 1), (1, 2), (1, 4)]
 ENC_CL = [(1, 1), (2, 1), (1, 2), (2, 2), (4, 1), (1, 4)]
 PLAN = [
     ("llm_gate_up", 201, 28672, 4096, [(2208, 1), (2256, 1), (4256, 1), (5416, 1), (5512, 1)], LLM_CL),
-    ("llm_qkv", 201, 6144, 4096, [(1128, 1), (2128, 1), (2128, 2), (2064, 1), (2208, 1)], LLM_CL + [(2, 1), (2, 2)]),
+    ("llm_qkv", 201, 6144, 4096, [(1128, 1), (2128, 1), (2128, 2), (2064, 1), (2208, 1), (4128, 1), (4256, 1)], LLM_CL + [(2, 1), (2, 2)]),
     ("llm_o", 201, 4096, 4096, [(2128, 4), (2128, 2), (2064, 2), (2064, 1), (2256, 4)], LLM_CL),
     ("llm_down", 201, 4096, 14336, [(2128, 4), (2128, 2), (2064, 2), (2256, 4), (2256, 8)], LLM_CL),
     ("enc_qkv", 1500, 3840, 1280, [(1128, 1), (1256, 1), (4256, 1), (5512, 1)], ENC_CL),
-    ("enc_out", 1500, 1280, 1280, [(1128, 1), (1064, 1)], ENC_CL),
+    ("enc_out", 1500, 1280, 1280, [(1128, 1), (1064, 1), (4128, 1)], ENC_CL),
     ("enc_fc1", 1500, 5120, 1280, [(1128, 1), (1256, 1), (4256, 1), (5512, 1)], ENC_CL),
-    ("enc_fc2", 1500, 1280, 5120, [(1128, 1), (1256, 1)], ENC_CL),
+    ("enc_fc2", 1500, 1280, 5120, [(1128, 1), (1256, 1), (4128, 1), (4256, 1)], ENC_CL),
 ]
 only = sys.argv[1:] or None
 if os.environ.get("BASEONLY"):

@@ -148,6 +148,60 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
                "h"(mask)
                : "memory");
 }
+// Warp-convergent issue forms: the WHOLE warp executes the statement and elect.sync picks the one lane that issues.  Under an
+// `if (lane == 0)` branch the compiler wraps every uniform-datapath instruction (UTCHMMA / UTCBAR / UTMALDG / SYNCS) in an
+// elect-and-retry loop plus register->uniform moves, which triples the instruction count of the single-thread producer / MMA
+// loops - and those loops are the critical path of the kernel (about 575 cycles per k-block regardless of N <= 128).
+__device__ __forceinline__ void umma_f16_e(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_e(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_e(uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_e(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+      "}\n" ::"r"(smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_e(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+      "}\n" ::"r"(smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -328,9 +382,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   pdl_wait();  // set-up above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    // ---- TMA producer: all 32 lanes run the loop (convergent), elect.sync issues
+    {
+      if (lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+      }
+      __syncwarp();
       int s = 0;           // ring slot and its phase: the ring runs ahead across tile boundaries
       uint32_t ph = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
@@ -350,15 +408,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int kb = kb_begin + (i + rot < nk ? i + rot : i + rot - nk);
           mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* sa = smem + s * p.stage_bytes;
-          mbar_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
-          tma_load_3d(sa, &tmA, kb * kBK, m0, b, &full_bar[s]);
-          tma_load_2d(sa + p.a_box_bytes, &tmW, kb * kBK, n0, &full_bar[s]);
+          mbar_expect_tx_e(&full_bar[s], (uint32_t)p.stage_bytes);
+          tma_load_3d_e(sa, &tmA, kb * kBK, m0, b, &full_bar[s]);
+          tma_load_2d_e(sa + p.a_box_bytes, &tmW, kb * kBK, n0, &full_bar[s]);
           if (++s == stages) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // ---- MMA issuer: convergent warp, elect.sync issues
+    {
       constexpr uint32_t idesc = make_idesc(BN);
       int s = 0;
       uint32_t ph = 0, tcount = 0;
@@ -384,13 +443,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {
               // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-              umma_f16(d_tmem + mt * L::kBNT, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+              umma_f16_e(d_tmem + mt * L::kBNT, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
             }
           }
-          umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+          umma_commit_e(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
           if (++s == stages) { s = 0; ph ^= 1u; }
         }
-        umma_commit(&tmem_full[acc]);  // accumulators of this tile complete
+        umma_commit_e(&tmem_full[acc]);  // accumulators of this tile complete
       }
     }
   } else {
@@ -740,6 +799,57 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
 // Pair tile = 256 rows x (NH * BNH) columns: NH tcgen05.mma (N = BNH) per k-step into NH accumulators.  NH = 2 doubles the
 // columns a row tile of A is used for (A is re-read once per column tile, and the GEMMs are bound by bytes delivered from
 // L2): 256 x 416 for the Llama gate/up projection at M = 201, 256 x 512 for the encoder fc1 / qkv.
+__device__ __forceinline__ void tma2_load_2d_e(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+      "}\n" ::"r"(smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d_e(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+      "}\n" ::"r"(smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader_e(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q mbarrier.arrive.shared::cluster.b64 _, [%0];\n"
+      "}\n" ::"r"(smem_u32(bar) & kPeerMask)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_f16_e(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc_e(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
 template <int BNH, int NH, int EPW>
 struct Smem2 {
   static constexpr int kThreads = 64 + 32 * EPW;
@@ -806,9 +916,12 @@ gemm_tc2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   pdl_wait();  // set-up above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    {  // convergent producer warp, elect.sync issues (see umma_f16_e)
+      if (lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+      }
+      __syncwarp();
       uint32_t it = 0;
       for (int tile = pair; tile < p.num_tiles; tile += num_pairs) {
         const int tm_idx = tile % tiles_m_total;
@@ -823,17 +936,17 @@ gemm_tc2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t ph = (it / kStages) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* sa = smem + s * L::kStageBytes;
-          tma2_load_3d(sa, &tmA, kb * kBK, m0, b, &full_bar[s]);
+          tma2_load_3d_e(sa, &tmA, kb * kBK, m0, b, &full_bar[s]);
 #pragma unroll
           for (int h = 0; h < NH; ++h)
-            tma2_load_2d(sa + L::kABytes + h * L::kWHalfBytes, &tmW, kb * kBK, n0 + h * BNH, &full_bar[s]);
-          if (leader) mbar_expect_tx(&full_bar[s], (uint32_t)(2 * L::kStageBytes));
-          else mbar_arrive_leader(&full_bar[s]);
+            tma2_load_2d_e(sa + L::kABytes + h * L::kWHalfBytes, &tmW, kb * kBK, n0 + h * BNH, &full_bar[s]);
+          if (leader) mbar_expect_tx_e(&full_bar[s], (uint32_t)(2 * L::kStageBytes));
+          else mbar_arrive_leader_e(&full_bar[s]);
         }
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader) {  // convergent MMA warp of the leader CTA
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BNH >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       uint32_t it = 0, tcount = 0;
       for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++tcount) {
@@ -854,11 +967,11 @@ gemm_tc2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint64_t dw = make_smem_desc(sa + L::kABytes + h * L::kWHalfBytes);
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k)
-              umma2_f16(d_tmem + h * L::kBNT, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma2_f16_e(d_tmem + h * L::kBNT, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma2_commit_mc(&empty_bar[s]);
+          umma2_commit_mc_e(&empty_bar[s]);
         }
-        umma2_commit_mc(&tmem_full[acc]);
+        umma2_commit_mc_e(&tmem_full[acc]);
       }
       // keep the leader's barriers alive until the last epilogue arrivals from the peer have landed
       if (tcount > 0) {
