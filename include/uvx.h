@@ -140,6 +140,8 @@ typedef struct uvx_attn_args {
   int32_t block;                    /* >0: block-causal, query i sees keys j with j/block <= i/block */
   float scale;
   float* lse;                       /* optional [B, Hq, Sq] fp32: log-sum-exp of the scaled scores (training) */
+  const int32_t* kv_start;          /* optional [B]: keys j < kv_start[b] are masked - left-padded batches              */
+                                    /* (ref collator ultravox_processing.py:53-63; hf masking_utils padding mask)       */
 } uvx_attn_args;
 int uvx_attention(const uvx_attn_args* args, uvx_stream_t stream);
 /* Whisper-encoder specialisation on tcgen05 tensor cores (head_dim 64, Sq == Skv, non-causal + key-length / block-causal

@@ -139,12 +139,58 @@ def test_text_only_and_right_padding_and_errors():
     out = model(ids.cuda(), attention_mask=am.cuda())
     ref = om.llama_forward(sd, sh, sd["language_model.model.embed_tokens.weight"][ids], attention_mask=am)
     assert rel(out.logits[0], ref[0]) < 2e-2 and rel(out.logits[1, :13], ref[1, :13]) < 2e-2
+    hole = am.clone()
+    hole[0, 5] = 0                                     # interior hole: not a padding pattern
     with pytest.raises(NotImplementedError):
-        model(ids.cuda(), attention_mask=am.flip(1).cuda())
+        model(ids.cuda(), attention_mask=hole.cuda())
     with pytest.raises(AssertionError):
         model(ids.cuda(), audio_values=torch.zeros(1, 80, 100).cuda())
     with pytest.raises(ValueError):
         model.encode_audio(torch.zeros(1, 3003, 80, dtype=torch.bfloat16, device="cuda"), None)
+
+
+def test_left_padded_batch_forward_and_generate():
+    """left-padded batches (the reference batches inference prompts with padding_side="left", ref
+    infer.py:155-180, ultravox_processing.py:53-63).  forward: keys in the padding are masked (oracle = HF Llama with the
+    same attention_mask, arange positions, hf:modeling_llama.py:394-397); generate: mask-derived position_ids
+    (hf:generation/utils.py:707-729), so every row must continue exactly like its own unpadded prompt."""
+    from oracle import model as om
+    cfg, model, sd, sh = build()
+    g = torch.Generator().manual_seed(3)
+    S, pads = 21, [0, 6, 13]
+    ids = torch.randint(0, cfg.vocab_size, (3, S), generator=g)
+    am = torch.ones(3, S, dtype=torch.long)
+    for b, pd in enumerate(pads):
+        am[b, :pd] = 0
+    table = sd["language_model.model.embed_tokens.weight"]
+    out = model(ids.cuda(), attention_mask=am.cuda())
+    ref = om.llama_forward(sd, sh, table[ids], attention_mask=am)
+    for b, pd in enumerate(pads):
+        assert rel(out.logits[b, pd:], ref[b, pd:]) < 2e-2
+    # mask-derived positions: row b of the padded batch == the unpadded prompt on its own (oracle and CUDA path)
+    pos = (am.cumsum(-1) - 1).clamp_min(0)
+    out_p = model(ids.cuda(), attention_mask=am.cuda(), position_ids=pos.cuda())
+    ref_p = om.llama_forward(sd, sh, table[ids], attention_mask=am, position_ids=pos)
+    for b, pd in enumerate(pads):
+        assert rel(out_p.logits[b, pd:], ref_p[b, pd:]) < 2e-2
+        solo = om.llama_forward(sd, sh, table[ids[b:b + 1, pd:]])
+        assert rel(out_p.logits[b, pd:], solo[0]) < 2e-2
+    # generation: batch of left-padded prompts vs each prompt alone (same kernels) - logits of every step must agree;
+    # tokens may only differ where the top-2 margin is inside bf16 noise, so compare through teacher forcing
+    seq = model.generate(ids.cuda(), attention_mask=am.cuda(), max_new_tokens=5)
+    assert seq.shape == (3, S + 5) and torch.equal(seq[:, :S].cpu(), ids)
+    for b, pd in enumerate(pads):
+        full = seq[b:b + 1, pd:]                                   # the row's own tokens, padding stripped
+        lg = model(full).logits[0].float()                         # one unpadded re-forward of the generated sequence
+        for t in range(5):
+            row = lg[S - pd - 1 + t]
+            top = row.topk(5).indices.tolist()
+            assert int(seq[b, S + t]) in top, (b, t)
+        single = model.generate(ids[b:b + 1, pd:].cuda(), max_new_tokens=5)
+        agree = (single[0, S - pd:] == seq[b, S:]).float().mean().item()
+        assert agree >= 0.6, (b, agree)
+    with pytest.raises(NotImplementedError):
+        model.generate(ids.cuda(), attention_mask=am.flip(1).cuda(), max_new_tokens=2)
 
 
 def test_generate_greedy_matches_stepwise_oracle():

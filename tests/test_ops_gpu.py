@@ -225,6 +225,23 @@ def test_attention(ops, B, Hq, Hkv, S, D, causal, block, ragged):
     assert rel(out, ref) < 3e-3  # P is rounded to bf16 before PV (as in every flash kernel)
 
 
+@pytest.mark.parametrize("B,Hq,Hkv,S,D", [(3, 8, 2, 201, 128), (2, 4, 4, 77, 64)])
+def test_attention_left_padding(ops, B, Hq, Hkv, S, D):
+    """kv_start: keys in the left padding are masked; rows in the padding see nothing and come out as zeros."""
+    W = (Hq + 2 * Hkv) * D
+    qkv = rnd(B * S, W, seed=5)
+    start = torch.tensor([0, 70, S - 3][:B], dtype=torch.int32).cuda()
+    out = ops.attention_fused_qkv(qkv, B, S, Hq, Hkv, D, D ** -0.5, True, None, 0, kv_start=start).view(B, S, Hq * D)
+    t = qkv.view(B, S, Hq + 2 * Hkv, D).permute(0, 2, 1, 3)
+    for b in range(B):
+        p0 = int(start[b])
+        sub = t[b:b + 1, :, p0:]                       # the unpadded sequence on its own
+        ref = _attn_ref(sub[:, :Hq], sub[:, Hq:Hq + Hkv], sub[:, Hq + Hkv:], D ** -0.5, True)
+        ref = ref.permute(0, 2, 1, 3).reshape(S - p0, Hq * D)
+        assert rel(out[b, p0:], ref) < 3e-3
+        assert torch.count_nonzero(out[b, :p0]) == 0
+
+
 @pytest.mark.parametrize("B,H,S,block,ragged", [(1, 2, 128, 0, False), (1, 3, 256, 0, False), (2, 6, 50, 0, True),
                                                  (1, 20, 1500, 0, False), (2, 4, 300, 100, True), (3, 2, 700, 0, True)])
 def test_attention_encoder_tcgen05(ops, B, H, S, block, ragged):

@@ -30,7 +30,7 @@ class AttnArgs(C.Structure):
     _fields_ = [("q", c_vp), ("k", c_vp), ("v", c_vp), ("o", c_vp), ("B", c_i64), ("Hq", c_i64), ("Hkv", c_i64),
                 ("Sq", c_i64), ("Skv", c_i64), ("D", c_i64), ("q_rs", c_i64), ("q_bs", c_i64), ("k_rs", c_i64),
                 ("k_bs", c_i64), ("v_rs", c_i64), ("v_bs", c_i64), ("o_rs", c_i64), ("o_bs", c_i64), ("kv_len", c_vp),
-                ("causal", c_i32), ("block", c_i32), ("scale", c_f32), ("lse", c_vp)]
+                ("causal", c_i32), ("block", c_i32), ("scale", c_f32), ("lse", c_vp), ("kv_start", c_vp)]
 
 
 # name -> (restype, argtypes); must list every symbol include/uvx.h declares (tests check this)

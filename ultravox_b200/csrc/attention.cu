@@ -18,6 +18,7 @@ struct AttnParams {
   bf16* o;
   int64_t q_rs, q_bs, k_rs, k_bs, v_rs, v_bs, o_rs, o_bs;
   const int32_t* kv_len;
+  const int32_t* kv_start;  // optional [B]: keys before it are masked (left-padded batches)
   float* lse;  // optional [B, Hq, Sq]: natural-log sum-exp of the scaled scores (for the backward)
   int Sq, Skv, group, Hq;  // group = Hq / Hkv
   int causal, block;
@@ -80,6 +81,8 @@ __global__ void __launch_bounds__(kAThreads) attn_fwd_kernel(const AttnParams p)
   const int last_q = min(m0 + kAM, p.Sq) - 1;
   if (p.causal) kv_end = min(kv_end, last_q + shift + 1);
   if (p.block > 0) kv_end = min(kv_end, (last_q / p.block + 1) * p.block);
+  const int kv_begin = p.kv_start ? min(max(p.kv_start[b], 0), kv_end) : 0;
+  const int tile0 = kv_begin / kAN;  // tiles entirely in the left padding are skipped
   const int n_tiles = (kv_end + kAN - 1) / kAN;
 
   constexpr int CH = D / 8;  // 16-byte chunks per row
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(kAThreads) attn_fwd_kernel(const AttnParams p)
   };
 
   load_q();
-  if (n_tiles > 0) load_kv(0, 0);
+  if (n_tiles > tile0) load_kv(tile0, 0);
   cp_async_commit();
 
   float o_acc[D / 8][4];
@@ -114,13 +117,13 @@ __global__ void __launch_bounds__(kAThreads) attn_fwd_kernel(const AttnParams p)
   uint32_t qf[D / 16][4];
   const int qrow0 = m0 + warp * 16 + g;  // this thread's rows: qrow0 and qrow0 + 8
 
-  for (int tile = 0; tile < n_tiles; ++tile) {
-    const int stage = tile & 1;
+  for (int tile = tile0; tile < n_tiles; ++tile) {
+    const int stage = (tile - tile0) & 1;
     if (tile + 1 < n_tiles) load_kv(tile + 1, stage ^ 1);
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
-    if (tile == 0) {
+    if (tile == tile0) {
 #pragma unroll
       for (int kk = 0; kk < D / 16; ++kk)
         ldsm_x4(qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], sQ + (warp * 16 + (lane & 15)) * LD + kk * 16 + (lane >> 4) * 8);
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(kAThreads) attn_fwd_kernel(const AttnParams p)
       for (int e = 0; e < 4; ++e) {
         const int key = n0 + nb * 8 + t4 * 2 + (e & 1);
         const int qr = qrow0 + (e >> 1) * 8;
-        bool ok = key < kv_end;
+        bool ok = key < kv_end && key >= kv_begin;
         if (p.causal) ok = ok && (key <= qr + shift);
         if (p.block > 0) ok = ok && (key / p.block <= qr / p.block);
         if (!ok) s[nb][e] = -INFINITY;
@@ -255,6 +258,7 @@ static int launch_attn(const uvx_attn_args* a, cudaStream_t st) {
   p.q_rs = a->q_rs; p.q_bs = a->q_bs; p.k_rs = a->k_rs; p.k_bs = a->k_bs;
   p.v_rs = a->v_rs; p.v_bs = a->v_bs; p.o_rs = a->o_rs; p.o_bs = a->o_bs;
   p.kv_len = a->kv_len;
+  p.kv_start = a->kv_start;
   p.lse = a->lse;
   p.Hq = (int)a->Hq;
   p.Sq = (int)a->Sq;

@@ -408,6 +408,7 @@ extern "C" int uvx_attention_bwd(const uvx_attn_args* a, const void* o, const vo
                                  float* delta_ws, uvx_stream_t stream) {
   using namespace uvx;
   UVX_REQUIRE(a && a->q && a->k && a->v && o && dout && dq && dk && dv && a->lse && delta_ws, "uvx_attention_bwd: null pointer");
+  UVX_REQUIRE(!a->kv_start, "uvx_attention_bwd: left-padded batches (kv_start) are a forward-only feature");
   UVX_REQUIRE(a->D == 64 || a->D == 128, "uvx_attention_bwd: head_dim must be 64 or 128");
   UVX_REQUIRE(a->Hq % a->Hkv == 0 && a->B >= 1 && a->B < 65536 && a->Hq < 65536, "uvx_attention_bwd: bad shape");
   UVX_REQUIRE(a->q_rs % 8 == 0 && a->k_rs % 8 == 0 && a->v_rs % 8 == 0 && a->o_rs % 8 == 0 && dq_rs % 2 == 0 && dk_rs % 2 == 0 &&

@@ -373,9 +373,12 @@ class UltravoxModel(nn.Module):
 
     # -- llama ---------------------------------------------------------------------------------------
     def llama_hidden(self, inputs_embeds: torch.Tensor, cache: Optional[KVCache] = None,
-                     kv_len: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     kv_len: Optional[torch.Tensor] = None, kv_start: Optional[torch.Tensor] = None,
+                     positions: Optional[torch.Tensor] = None) -> torch.Tensor:
         """All decoder layers + final RMSNorm (hf:models/llama/modeling_llama.py:355-426).  ``inputs_embeds`` [B,S,D]
-        is consumed in place (it becomes the residual stream).  ``kv_len`` [B] int32 masks right padding."""
+        is consumed in place (it becomes the residual stream).  ``kv_len`` / ``kv_start`` [B] int32 bound each sequence's visible
+        keys to [kv_start, kv_len) (right / left padding, hf:masking_utils padding mask); ``positions`` [B*S] int32 overrides
+        the RoPE position of every row (mask-derived ``position_ids`` of left-padded generation, hf:generation/utils.py:707-729)."""
         lm, tc = self.language_model, self.config.text_config
         B, S, Dm = inputs_embeds.shape
         nq, nkv, hd = tc.num_attention_heads, tc.num_key_value_heads, lm.head_dim
@@ -396,9 +399,9 @@ class UltravoxModel(nn.Module):
         for li, layer in enumerate(layers):
             sa, mlp = layer.self_attn, layer.mlp
             ops.linear(x, sa.qkv_w, out=qkv)
-            ops.rope_(qkv, nq, nkv, hd, cos, sin, rows_per_seq=S, pos_offset=past)
+            ops.rope_(qkv, nq, nkv, hd, cos, sin, rows_per_seq=S, pos_offset=past, positions=positions)
             if cache is None:
-                ops.attention_fused_qkv(qkv, B, S, nq, nkv, hd, hd ** -0.5, True, kv_len, 0, out=att)
+                ops.attention_fused_qkv(qkv, B, S, nq, nkv, hd, hd ** -0.5, True, kv_len, 0, out=att, kv_start=kv_start)
             else:
                 kc, vc = cache.k[li], cache.v[li]            # [B, S_max, Hkv, D]
                 kc[:, past:past + S].copy_(qkv.view(B, S, -1)[:, :, nq * hd:(nq + nkv) * hd].view(B, S, nkv, hd))
@@ -406,7 +409,7 @@ class UltravoxModel(nn.Module):
                 smax = kc.shape[1]
                 ops.attention(qkv.data_ptr(), kc.data_ptr(), vc.data_ptr(), att, B, nq, nkv, S, past + S, hd,
                               (rs, S * rs, nkv * hd, smax * nkv * hd, nkv * hd, smax * nkv * hd, nq * hd, S * nq * hd),
-                              hd ** -0.5, True, kv_len, 0)
+                              hd ** -0.5, True, kv_len, 0, kv_start)
             # o_proj / down_proj write the residual stream AND the RMSNorm the next block reads (fused into split-K's pass 2)
             ops.linear(att, sa.o_proj.weight, residual=h, out=h, norm=(layer.post_attention_layernorm.weight, eps, x) if FUSE_NORM else None)
             if not FUSE_NORM:
@@ -427,19 +430,25 @@ class UltravoxModel(nn.Module):
         return KVCache(torch.empty(shape, dtype=BF16, device=self.device), torch.empty(shape, dtype=BF16, device=self.device))
 
     @staticmethod
-    def _right_pad_lengths(attention_mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
-        """attention_mask [B,S] of 1s then 0s -> kv_len int32; None if all ones; left padding is not built yet."""
+    def _pad_bounds(attention_mask: Optional[torch.Tensor]):
+        """attention_mask [B,S] with one contiguous run of ones per row -> (kv_start, kv_len) int32 [B] (None where the
+        bound is trivial).  Right padding (training collator, ref ultravox_processing.py:43-51) gives kv_len, left padding
+        (inference collator / ``tokenizer.padding_side = "left"``, ref :53-63, infer.py:155-180) gives kv_start."""
         if attention_mask is None:
-            return None
+            return None, None
         m = attention_mask.to(torch.bool)
         if bool(m.all()):
-            return None
-        lens = m.sum(-1)
-        ar = torch.arange(m.shape[1], device=m.device)[None, :]
-        if not torch.equal(m, ar < lens[:, None]):
-            raise NotImplementedError("left / interior padding in attention_mask (SURVEY.md 8f rank 2) is not built yet; "
-                                      "use right padding or unpadded batches")
-        return lens.to(torch.int32)
+            return None, None
+        S = m.shape[1]
+        ar = torch.arange(S, device=m.device)[None, :]
+        n = m.sum(-1)
+        start = torch.where(n > 0, m.to(torch.int64).argmax(-1), torch.zeros_like(n))
+        end = start + n
+        if not torch.equal(m, (ar >= start[:, None]) & (ar < end[:, None])):
+            raise NotImplementedError("attention_mask rows must be one contiguous run of ones (left and/or right padding)")
+        kv_start = start.to(torch.int32) if bool((start > 0).any()) else None
+        kv_len = end.to(torch.int32) if bool((end < S).any()) else None
+        return kv_start, kv_len
 
     # -- forward / generate --------------------------------------------------------------------------
     def forward(self, input_ids: torch.Tensor, audio_values: Optional[torch.Tensor] = None,
@@ -468,8 +477,10 @@ class UltravoxModel(nn.Module):
             inputs_embeds = inputs_embeds.clone()
         if self.training and self.loss_config.loss_function not in (LossFunction.CrossEntropy, LossFunction.KL_Divergence):
             raise ValueError(f"Unsupported loss function: {self.loss_config.loss_function}")
-        kv_len = self._right_pad_lengths(attention_mask.to(dev) if attention_mask is not None else None)
-        hidden = self.llama_hidden(inputs_embeds, past_key_values, kv_len)
+        kv_start, kv_len = self._pad_bounds(attention_mask.to(dev) if attention_mask is not None else None)
+        position_ids = kwargs.get("position_ids")
+        positions = position_ids.to(dev, torch.int32).reshape(-1).contiguous() if position_ids is not None else None
+        hidden = self.llama_hidden(inputs_embeds, past_key_values, kv_len, kv_start, positions)
         B, S, Dm = hidden.shape
         lm_w = self.language_model.lm_head.weight
         if logits_to_keep == 1:
@@ -512,11 +523,21 @@ class UltravoxModel(nn.Module):
         dev = self.device
         input_ids = input_ids.to(dev)
         B, S = input_ids.shape
+        # left-padded batches (ref infer.py:155-180 batches prompts with padding_side="left"): keys in the padding are masked
+        # for the whole generation and RoPE positions count real tokens only (hf:generation/utils.py:707-729)
+        kv_start = None
+        position_ids = None
+        pad = torch.zeros(B, dtype=torch.int64, device=dev)
         if attention_mask is not None and not bool(attention_mask.to(torch.bool).all()):
-            raise NotImplementedError("padded batches in generate() are not built yet (SURVEY.md 8f rank 2)")
+            am = attention_mask.to(dev)
+            kv_start, kv_len = self._pad_bounds(am)
+            if kv_len is not None:
+                raise NotImplementedError("generate() needs left padding (or none); right-padded prompts cannot be continued")
+            pad = kv_start.to(torch.int64)
+            position_ids = (am.to(torch.int64).cumsum(-1) - 1).clamp_min(0)
         cache = self.new_cache(B, S + max_new_tokens)
-        out = self.forward(input_ids, audio_values, inputs_embeds, None, None, audio_token_start_idx, audio_lens,
-                           audio_token_len, audio_batch_size, cache, logits_to_keep=1)
+        out = self.forward(input_ids, audio_values, inputs_embeds, None, attention_mask, audio_token_start_idx, audio_lens,
+                           audio_token_len, audio_batch_size, cache, logits_to_keep=1, position_ids=position_ids)
         eos = set([eos_token_id] if isinstance(eos_token_id, int) else (eos_token_id or []))
         seq = [input_ids]
         done = torch.zeros(B, dtype=torch.bool, device=dev)
@@ -530,7 +551,8 @@ class UltravoxModel(nn.Module):
             if step == max_new_tokens - 1:
                 break
             emb = ops.embed_splice(tok.view(B, 1), self.language_model.model.embed_tokens.weight, None, None)
-            hidden = self.llama_hidden(emb, cache)
+            positions = (S + step - pad).to(torch.int32) if kv_start is not None else None
+            hidden = self.llama_hidden(emb, cache, None, kv_start, positions)
             tok = ops.argmax(ops.lm_head(hidden[:, -1, :], self.language_model.lm_head.weight))
         return torch.cat(seq, dim=1)
 

@@ -188,14 +188,16 @@ def stack_rmsnorm(enc: torch.Tensor, w: torch.Tensor, stack: int, eps: float = 1
 # ------------------------------------------------------------------------------------------ attention
 def attention(q_ptr: int, k_ptr: int, v_ptr: int, out: torch.Tensor, B: int, Hq: int, Hkv: int, Sq: int,
               Skv: int, D: int, strides: tuple, scale: float, causal: bool = False,
-              kv_len: Optional[torch.Tensor] = None, block: int = 0) -> torch.Tensor:
+              kv_len: Optional[torch.Tensor] = None, block: int = 0, kv_start: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Raw strided interface: strides = (q_rs, q_bs, k_rs, k_bs, v_rs, v_bs, o_rs, o_bs) in elements; the three
-    pointers address element [b=0, i=0, h=0, 0] of q / k / v."""
+    pointers address element [b=0, i=0, h=0, 0] of q / k / v.  ``kv_len`` / ``kv_start`` [B] int32 bound the visible keys
+    of each sequence to [kv_start, kv_len) (right / left padding)."""
     a = AttnArgs()
     a.q, a.k, a.v, a.o = q_ptr, k_ptr, v_ptr, out.data_ptr()
     a.B, a.Hq, a.Hkv, a.Sq, a.Skv, a.D = B, Hq, Hkv, Sq, Skv, D
     (a.q_rs, a.q_bs, a.k_rs, a.k_bs, a.v_rs, a.v_bs, a.o_rs, a.o_bs) = strides
     a.kv_len = _p(kv_len)
+    a.kv_start = _p(kv_start)
     a.causal, a.block, a.scale = int(causal), int(block), float(scale)
     check(lib().uvx_attention(C.byref(a), _stream()), "uvx_attention")
     return out
@@ -203,7 +205,7 @@ def attention(q_ptr: int, k_ptr: int, v_ptr: int, out: torch.Tensor, B: int, Hq:
 
 def attention_fused_qkv(qkv: torch.Tensor, B: int, S: int, Hq: int, Hkv: int, D: int, scale: float, causal: bool,
                         kv_len: Optional[torch.Tensor] = None, block: int = 0,
-                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                        out: Optional[torch.Tensor] = None, kv_start: Optional[torch.Tensor] = None) -> torch.Tensor:
     """qkv [B*S, (Hq + 2*Hkv) * D] (q | k | v sections) -> out [B*S, Hq*D]."""
     _cuda(qkv, BF16, "qkv")
     assert qkv.shape[-1] == (Hq + 2 * Hkv) * D and qkv.stride(-1) == 1
@@ -212,7 +214,7 @@ def attention_fused_qkv(qkv: torch.Tensor, B: int, S: int, Hq: int, Hkv: int, D:
         out = torch.empty(B * S, Hq * D, dtype=BF16, device=qkv.device)
     base = qkv.data_ptr()
     return attention(base, base + 2 * Hq * D, base + 2 * (Hq + Hkv) * D, out, B, Hq, Hkv, S, S, D,
-                     (rs, S * rs, rs, S * rs, rs, S * rs, Hq * D, S * Hq * D), scale, causal, kv_len, block)
+                     (rs, S * rs, rs, S * rs, rs, S * rs, Hq * D, S * Hq * D), scale, causal, kv_len, block, kv_start)
 
 
 def attention_encoder_tc(qkv: torch.Tensor, B: int, S: int, H: int, scale: float, kv_len: Optional[torch.Tensor] = None,
