@@ -10,6 +10,10 @@ What runs verbatim from /root/reference (it cannot travel to the GPU box, so the
     UltravoxModel._prepare_audio_embeds  (float path; `accelerate` / `peft` are absent, so two empty stand-in modules
     are put in sys.modules AFTER importing transformers - none of the executed code touches them).
   * transformers' WhisperFeatureExtractor (third-party arithmetic of the path) on seeded waveforms -> log-mel goldens.
+  * ultravox.model.ultravox_data_proc.UltravoxDataproc._process / _compute_loss_mask_len  (host feed) with the
+    reference's real VoiceSample (ultravox.data.data_sample; `librosa` / `soundfile` are only touched by its file loaders,
+    so empty stand-in modules suffice).  The package `ultravox.data` itself needs simple_parsing / datasets / streaming, so
+    a stand-in module exposing the real VoiceSample and a restated 10-line `Dataproc` base is registered under that name.
 """
 import json
 import os
@@ -214,8 +218,79 @@ def mask_goldens():
     print("mask golden", tuple(m.shape))
 
 
+CHAT_MESSAGES = [
+    ("audio_qa", [{"role": "user", "content": "Listen to <|audio|> and answer briefly"},
+                  {"role": "assistant", "content": "it says hello world again and again"}], 16000, "hello world"),
+    ("system_audio", [{"role": "system", "content": "you are helpful"}, {"role": "user", "content": "Transcribe <|audio|>"},
+                      {"role": "assistant", "content": "one two three four five six seven eight nine ten"}], 5 * 16000 + 123,
+     "one two three"),
+    ("text_only", [{"role": "user", "content": "What is two plus two"}, {"role": "assistant", "content": "four of course"}], 0, None),
+    ("long_clip", [{"role": "user", "content": "<|audio|> summarise"}, {"role": "assistant", "content": "a b c d e f"}],
+     35 * 16000, "long transcript words here"),
+]
+
+
+def dataproc_goldens():
+    for name in ("librosa", "soundfile"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ultravox_data_sample_real", os.path.join(REF, "ultravox/data/data_sample.py"))
+    ds = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ds)
+
+    class _Base:                                   # stand-in for ultravox.data.Dataproc (ref datasets.py:592-616)
+        def __init__(self, dataset):
+            self._dataset = dataset
+
+    fake = types.ModuleType("ultravox.data")
+    fake.Dataproc, fake.VoiceSample = _Base, ds.VoiceSample
+    fake.SizedIterableDataset, fake.Augmentation = object, object
+    sys.modules["ultravox.data"] = fake
+    import ultravox
+    ultravox.data = fake
+    from ultravox.model import ultravox_data_proc
+
+    def chat(messages, tokenize=False, chat_template=None):
+        return " ".join(f"<|start|> {m['role']} <|sep|> {m['content']} <|eot_id|>" for m in messages)
+
+    proc = make_processor(80)
+    proc.tokenizer.apply_chat_template = chat
+    out = []
+    for cname, messages, n, transcript in CHAT_MESSAGES:
+        for mask in ("last_assistant", "after_audio", "all"):
+            if mask == "after_audio" and n == 0:
+                continue
+            for alt, cap, infer in ((False, None, False), (True, None, False), (True, 3, False), (False, None, True)):
+                audio = wave(7, n) if n else None
+                if audio is not None and cname == "system_audio":
+                    audio = (audio * 1000).astype(np.int16)          # exercises VoiceSample's integer normalisation
+                sample = ds.VoiceSample([dict(m) for m in messages], audio, audio_transcript=transcript)
+                dp = ultravox_data_proc.UltravoxDataproc(None, proc, ultravox_config.LossMaskType(mask), inference_mode=infer,
+                                                         include_alt_fields=alt, max_response_tokens=cap)
+                try:
+                    r = dp._process(sample)
+                except ValueError as e:               # e.g. inference_mode + last_assistant drops the turn that holds the audio
+                    out.append({"name": cname, "n_samples": n, "int16": cname == "system_audio" and n > 0, "loss_mask_type": mask,
+                                "include_alt_fields": alt, "max_response_tokens": cap, "inference_mode": infer,
+                                "transcript": transcript, "raises": "ValueError", "msg": str(e)})
+                    continue
+                d = {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in r.items() if k != "audio_values"}
+                if "audio_values" in r:
+                    d["audio_values_shape"] = list(r["audio_values"].shape)
+                out.append({"name": cname, "n_samples": n, "int16": cname == "system_audio" and n > 0, "loss_mask_type": mask,
+                            "include_alt_fields": alt, "max_response_tokens": cap, "inference_mode": infer,
+                            "transcript": transcript, "out": d})
+    json.dump({"messages": {c[0]: c[1] for c in CHAT_MESSAGES}, "cases": out}, open(os.path.join(OUT, "dataproc_cases.json"), "w"),
+              indent=0)
+    print("dataproc cases:", len(out))
+
+
 if __name__ == "__main__":
+    if "--dataproc-only" in sys.argv:
+        dataproc_goldens()
+        sys.exit(0)
     processor_cases()
     logmel_goldens()
     projector_goldens()
     mask_goldens()
+    dataproc_goldens()
