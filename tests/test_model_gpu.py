@@ -193,6 +193,36 @@ def test_left_padded_batch_forward_and_generate():
         model.generate(ids.cuda(), attention_mask=am.flip(1).cuda(), max_new_tokens=2)
 
 
+def test_conversation_kv_reuse_two_turns():
+    """SURVEY 8f rank 2 (conversation mode, ref infer.py:126-148): turn 2 passes the cache returned by turn 1 and only the
+    new suffix is prefilled; the continuation must match a cache-less generation over the whole conversation."""
+    from ultravox_b200 import ops
+    cfg, model, sd, sh = build()
+    padded, batch = make_batch(cfg, [16000])
+    mel = ops.logmel(torch.from_numpy(padded).cuda(), sh.n_mels)
+    kw = {k: v.cuda() for k, v in batch.items()}
+    out1 = model.generate(audio_values=mel, max_new_tokens=4, return_dict_in_generate=True, **kw)
+    S1 = batch["input_ids"].shape[1]
+    cache = out1.past_key_values
+    assert out1.sequences.shape == (1, S1 + 4) and cache.length == S1 + 3      # the last new token is not in the cache yet
+    g = torch.Generator().manual_seed(9)
+    turn2 = torch.randint(0, cfg.vocab_size, (1, 6), generator=g).cuda()
+    ids2 = torch.cat([out1.sequences, turn2], dim=1)
+    kw2 = dict(kw, input_ids=ids2)
+    out2 = model.generate(audio_values=mel, max_new_tokens=5, past_key_values=cache, return_dict_in_generate=True, **kw2)
+    S2 = ids2.shape[1]
+    assert out2.sequences.shape == (1, S2 + 5) and torch.equal(out2.sequences[:, :S2], ids2)
+    assert out2.past_key_values.length == S2 + 4 and out2.past_key_values.capacity >= S2 + 5
+    # cache-less reference over the whole conversation (same kernels): teacher-forced logits must rank every token on top
+    full = model(out2.sequences[:, :-1], audio_values=mel, **{k: v for k, v in kw.items() if k != "input_ids"}).logits[0].float()
+    for t in range(5):
+        assert int(out2.sequences[0, S2 + t]) in full[S2 - 1 + t].topk(5).indices.tolist(), t
+    fresh = model.generate(audio_values=mel, max_new_tokens=5, **kw2)
+    assert (fresh[0, S2:] == out2.sequences[0, S2:]).float().mean().item() >= 0.6
+    with pytest.raises(ValueError):
+        model.generate(audio_values=mel, max_new_tokens=2, past_key_values=out2.past_key_values, **kw)   # prompt shorter than cache
+
+
 def test_generate_greedy_matches_stepwise_oracle():
     from oracle import logmel as ol, model as om
     from ultravox_b200 import ops

@@ -175,6 +175,28 @@ class KVCache:
     def get_seq_length(self) -> int:
         return self.length
 
+    @property
+    def capacity(self) -> int:
+        return int(self.k.shape[2])
+
+    def grown(self, max_len: int) -> "KVCache":
+        """A cache with room for ``max_len`` positions holding the same ``length`` entries (conversation turns grow it)."""
+        if max_len <= self.capacity:
+            return self
+        shape = list(self.k.shape)
+        shape[2] = max_len
+        k, v = self.k.new_empty(shape), self.v.new_empty(shape)
+        k[:, :, :self.length].copy_(self.k[:, :, :self.length])
+        v[:, :, :self.length].copy_(self.v[:, :, :self.length])
+        return KVCache(k, v, self.length)
+
+
+@dataclasses.dataclass
+class GenerateOutput:
+    """``return_dict_in_generate=True`` result: what the reference's conversation mode reads (ref infer.py:131-148)."""
+    sequences: torch.Tensor
+    past_key_values: KVCache
+
 
 # ------------------------------------------------------------------------------------------------ the model
 class UltravoxModel(nn.Module):
@@ -517,9 +539,14 @@ class UltravoxModel(nn.Module):
     def generate(self, input_ids: torch.Tensor, audio_values: Optional[torch.Tensor] = None,
                  inputs_embeds: Optional[torch.Tensor] = None, audio_token_start_idx=None, audio_lens=None,
                  audio_token_len=None, audio_batch_size=None, max_new_tokens: int = 20, eos_token_id=None,
-                 attention_mask: Optional[torch.Tensor] = None, **kwargs) -> torch.Tensor:
+                 attention_mask: Optional[torch.Tensor] = None, past_key_values: Optional[KVCache] = None,
+                 return_dict_in_generate: bool = False, **kwargs):
         """Greedy decoding (the reference's default: temperature None/0, ref infer.py:319-328).  Returns prompt ids
-        followed by the new tokens, like ``GenerationMixin.generate`` (ref :398-426)."""
+        followed by the new tokens, like ``GenerationMixin.generate`` (ref :398-426).
+
+        ``past_key_values``: conversation KV reuse (ref infer.py:126-148): the cache already holds the first
+        ``past_key_values.length`` positions of ``input_ids`` (earlier turns incl. the reply), so only the new suffix is
+        embedded, spliced and prefilled; ``return_dict_in_generate=True`` hands the cache back for the next turn."""
         dev = self.device
         input_ids = input_ids.to(dev)
         B, S = input_ids.shape
@@ -533,11 +560,27 @@ class UltravoxModel(nn.Module):
             kv_start, kv_len = self._pad_bounds(am)
             if kv_len is not None:
                 raise NotImplementedError("generate() needs left padding (or none); right-padded prompts cannot be continued")
+            if past_key_values is not None:
+                raise NotImplementedError("conversation KV reuse with padded batches (the reference has none either, infer.py:155)")
             pad = kv_start.to(torch.int64)
             position_ids = (am.to(torch.int64).cumsum(-1) - 1).clamp_min(0)
-        cache = self.new_cache(B, S + max_new_tokens)
-        out = self.forward(input_ids, audio_values, inputs_embeds, None, attention_mask, audio_token_start_idx, audio_lens,
-                           audio_token_len, audio_batch_size, cache, logits_to_keep=1, position_ids=position_ids)
+        if past_key_values is None:
+            cache = self.new_cache(B, S + max_new_tokens)
+            out = self.forward(input_ids, audio_values, inputs_embeds, None, attention_mask, audio_token_start_idx, audio_lens,
+                               audio_token_len, audio_batch_size, cache, logits_to_keep=1, position_ids=position_ids)
+        else:
+            P = past_key_values.length
+            if not (0 <= P < S) or past_key_values.k.shape[1] != B:
+                raise ValueError(f"past_key_values holds {P} positions for batch {past_key_values.k.shape[1]}; the prompt has "
+                                 f"{S} tokens for batch {B} - it must extend the cached prefix")
+            cache = past_key_values.grown(S + max_new_tokens)
+            if inputs_embeds is None:                       # embed + splice the whole prompt, prefill only the new suffix
+                if audio_values is not None and len(audio_values) > 0:
+                    inputs_embeds = self._prepare_audio_embeds(input_ids, audio_values, audio_token_start_idx, audio_lens,
+                                                               audio_token_len, audio_batch_size)
+                else:
+                    inputs_embeds = ops.embed_splice(input_ids, self.language_model.model.embed_tokens.weight, None, None)
+            out = self.forward(input_ids[:, P:], None, inputs_embeds[:, P:].contiguous(), past_key_values=cache, logits_to_keep=1)
         eos = set([eos_token_id] if isinstance(eos_token_id, int) else (eos_token_id or []))
         seq = [input_ids]
         done = torch.zeros(B, dtype=torch.bool, device=dev)
@@ -554,7 +597,8 @@ class UltravoxModel(nn.Module):
             positions = (S + step - pad).to(torch.int32) if kv_start is not None else None
             hidden = self.llama_hidden(emb, cache, None, kv_start, positions)
             tok = ops.argmax(ops.lm_head(hidden[:, -1, :], self.language_model.lm_head.weight))
-        return torch.cat(seq, dim=1)
+        sequences = torch.cat(seq, dim=1)
+        return GenerateOutput(sequences, cache) if return_dict_in_generate else sequences
 
 
 def _sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> torch.Tensor:
