@@ -251,3 +251,82 @@ def test_pad_bounds_from_attention_mask():
     assert ks.tolist() == [1, 0] and kl.tolist() == [3, 0]
     with pytest.raises(NotImplementedError):
         f(torch.tensor([[1, 0, 1, 1, 1]]))
+
+
+def test_lora_checkpoint_names_and_merge():
+    """SURVEY 8b state-dict row / 8f rank 3: PEFT-wrapped checkpoint names (base_model.model. / .base_layer. infixes,
+    lora_A / lora_B) are folded into plain weights, W' = W + (alpha / r) B A, and the renaming round-trips."""
+    import torch
+    from ultravox_b200 import lora
+    g = torch.Generator().manual_seed(0)
+    d, r, alpha = 16, 4, 8.0
+    plain = {"audio_tower.layers.0.self_attn.q_proj.weight": torch.randn(d, d, generator=g),
+             "audio_tower.layers.0.self_attn.q_proj.bias": torch.randn(d, generator=g),
+             "audio_tower.layers.0.self_attn.k_proj.weight": torch.randn(d, d, generator=g),
+             "audio_tower.layers.0.self_attn.v_proj.weight": torch.randn(d, d, generator=g),
+             "audio_tower.layer_norm.weight": torch.ones(d),
+             "multi_modal_projector.linear_1.weight": torch.randn(8, d, generator=g)}
+    wrapped = lora.to_lora_names(plain, "audio_tower", ["k_proj", "q_proj", "linear_k", "linear_q"])
+    assert "audio_tower.base_model.model.layers.0.self_attn.q_proj.base_layer.weight" in wrapped
+    assert "audio_tower.base_model.model.layers.0.self_attn.q_proj.base_layer.bias" in wrapped
+    assert "audio_tower.base_model.model.layers.0.self_attn.v_proj.weight" in wrapped           # not a target module
+    assert "audio_tower.base_model.model.layer_norm.weight" in wrapped and "multi_modal_projector.linear_1.weight" in wrapped
+    assert lora.to_lora_names(wrapped, "audio_tower", ["q_proj"]) == wrapped                     # already wrapped: untouched
+    assert not lora.has_lora_keys(plain) and lora.has_lora_keys(wrapped)
+    A = {m: torch.randn(r, d, generator=g) for m in ("q_proj", "k_proj")}
+    B = {m: torch.randn(d, r, generator=g) for m in ("q_proj", "k_proj")}
+    for m in A:
+        stem = f"audio_tower.base_model.model.layers.0.self_attn.{m}"
+        wrapped[f"{stem}.lora_A.default.weight"], wrapped[f"{stem}.lora_B.default.weight"] = A[m], B[m]
+    scal = {"audio_tower": lora.lora_scaling({"r": r, "lora_alpha": alpha}), "language_model": lora.lora_scaling({"r": 0})}
+    assert scal == {"audio_tower": 2.0, "language_model": 0.0}
+    merged = lora.merge_lora_state_dict(wrapped, scal)
+    assert set(merged) == set(plain)
+    x = torch.randn(5, d, generator=g)
+    for m in A:
+        k = f"audio_tower.layers.0.self_attn.{m}.weight"
+        want = x @ plain[k].T + (alpha / r) * (x @ A[m].T) @ B[m].T      # peft LoRA forward: base(x) + scaling * B(A(x))
+        assert torch.allclose(x @ merged[k].T, want, atol=1e-4)
+    assert torch.equal(merged["audio_tower.layers.0.self_attn.v_proj.weight"], plain["audio_tower.layers.0.self_attn.v_proj.weight"])
+    assert torch.equal(merged["audio_tower.layers.0.self_attn.q_proj.bias"], plain["audio_tower.layers.0.self_attn.q_proj.bias"])
+    with pytest.raises(ValueError):
+        lora.merge_lora_state_dict(wrapped, {"audio_tower": 0.0})
+    broken = dict(wrapped)
+    del broken["audio_tower.base_model.model.layers.0.self_attn.q_proj.lora_B.default.weight"]
+    with pytest.raises(KeyError):
+        lora.merge_lora_state_dict(broken, scal)
+
+
+def test_model_loads_lora_wrapped_checkpoint():
+    """``UltravoxModel.load_state_dict`` takes a PEFT-named checkpoint (LoRA r=4 on the Whisper q/k projections) and
+    ends up with merged weights in the fused q|k|v storage the GEMM reads (no GPU needed: parameter containers only)."""
+    import torch
+    from ultravox_b200 import lora
+    from ultravox_b200.config import preset
+    from ultravox_b200.model import UltravoxModel
+    cfg = preset("micro")
+    cfg.audio_model_lora_config = {"r": 4, "lora_alpha": 8, "target_modules": ["k_proj", "q_proj"]}
+    m = UltravoxModel(cfg, device="cpu")
+    g = torch.Generator().manual_seed(0)
+    sd = {k: (torch.randn(v.shape, generator=g) * 0.02).to(v.dtype) for k, v in m.state_dict().items()}
+    wrapped = lora.to_lora_names(sd, "audio_tower", ["k_proj", "q_proj"])
+    d = sd["audio_tower.layers.0.self_attn.q_proj.weight"].shape[0]
+    ab = {}
+    for layer in range(cfg.audio_config.encoder_layers):
+        for mod in ("q_proj", "k_proj"):
+            stem = f"audio_tower.base_model.model.layers.{layer}.self_attn.{mod}"
+            ab[stem] = (torch.randn(4, d, generator=g).to(torch.bfloat16), torch.randn(d, 4, generator=g).to(torch.bfloat16))
+            wrapped[stem + ".lora_A.default.weight"], wrapped[stem + ".lora_B.default.weight"] = ab[stem]
+    res = m.load_state_dict(wrapped)
+    assert not res.missing_keys and not res.unexpected_keys
+    now = m.state_dict()
+    for stem, (a, b) in ab.items():
+        k = lora.plain_name(stem + ".base_layer.weight")
+        want = sd[k].float() + 2.0 * (b.float() @ a.float())
+        assert ((now[k].float() - want).norm() / want.norm()).item() < 4e-3          # one bf16 rounding of the merged weight
+    att = m.audio_tower.layers[0].self_attn
+    assert torch.equal(att.qkv_w[:d], now["audio_tower.layers.0.self_attn.q_proj.weight"])   # views of the fused GEMM operand
+    assert torch.equal(now["audio_tower.layers.0.self_attn.v_proj.weight"], sd["audio_tower.layers.0.self_attn.v_proj.weight"])
+    cfg0 = preset("micro")
+    with pytest.raises(ValueError):                                                    # LoRA weights but r = 0 in the config
+        UltravoxModel(cfg0, device="cpu").load_state_dict(wrapped)

@@ -446,6 +446,16 @@ class UltravoxModel(nn.Module):
             cache.length = past + S
         return x.view(B, S, Dm)
 
+    def load_state_dict(self, state_dict, strict: bool = True, **kwargs):
+        """Accepts the reference's checkpoints as they are saved: plain names, or PEFT-wrapped names with LoRA adapters on the
+        encoder / LLM projections (ref training/model_types.py:300-333) - the adapters are folded into the base weights."""
+        from . import lora
+        if lora.has_lora_keys(state_dict):
+            scaling = {"audio_tower": lora.lora_scaling(self.config.audio_model_lora_config),
+                       "language_model": lora.lora_scaling(self.config.text_model_lora_config)}
+            state_dict = lora.merge_lora_state_dict(state_dict, scaling)
+        return super().load_state_dict(state_dict, strict=strict, **kwargs)
+
     def new_cache(self, batch: int, max_len: int) -> KVCache:
         tc, lm = self.config.text_config, self.language_model
         shape = (tc.num_hidden_layers, batch, max_len, tc.num_key_value_heads, lm.head_dim)
