@@ -360,3 +360,99 @@ def test_gemv_matches_gemm():
         ref = x.float() @ w.float().T + r.float()
         assert rel(ops.gemv(x, w, residual=r), ref.to(torch.bfloat16)) < 1e-3
         assert rel(ops.gemv(x, w, out_dtype=torch.float32), x.float() @ w.float().T) < 1e-5
+
+
+class _ChatTok(_Tok):
+    """_Tok + what LocalInference needs: chat template, decode, left padding, eos-string splitting."""
+    padding_side = "left"
+    pad_token_id = 1000
+    added_tokens_encoder = {"<|eot_id|>": 1000}
+
+    def convert_tokens_to_ids(self, t):
+        return self.added_tokens_encoder[t]
+
+    def __call__(self, parts, add_special_tokens=False, **kw):
+        out = []
+        for p in parts:
+            words = p.replace(self.eos_token, f" {self.eos_token} ").split()
+            out.append([self.eos_token_id if w == self.eos_token else (sum(map(ord, w)) * 31 + len(w)) % 1000 for w in words])
+        return {"input_ids": out}
+
+    def apply_chat_template(self, messages, add_generation_prompt=True, tokenize=False, chat_template=None, **kw):
+        text = " ".join(f"<s> {m['role']} : {m['content']} {self.eos_token}" for m in messages)
+        return text + (" <s> assistant :" if add_generation_prompt else "")
+
+    def decode(self, ids, skip_special_tokens=True):
+        ids = [int(i) for i in (ids.tolist() if hasattr(ids, "tolist") else ids)]
+        return " ".join(f"t{i}" for i in ids if not (skip_special_tokens and i == self.eos_token_id))
+
+    def pad(self, features, padding=True, max_length=None, pad_to_multiple_of=None, return_tensors=None, **kw):
+        import transformers
+        L = max(len(f["input_ids"]) for f in features)
+        out = {"input_ids": [], "attention_mask": []}
+        for f in features:
+            ids = list(map(int, f["input_ids"]))
+            n = L - len(ids)
+            out["input_ids"].append([self.pad_token_id] * n + ids)
+            out["attention_mask"].append([0] * n + [1] * len(ids))
+        out.update({k: [f[k] for f in features] for k in features[0] if k not in ("input_ids", "attention_mask")})
+        return transformers.BatchFeature(out, tensor_type=return_tensors)
+
+
+def test_local_inference_single_batch_stream_conversation():
+    """the reference's LocalInference surface (ref inference/infer.py:20-342) over the B200 model:
+    infer == infer_stream (same tokens, chunked), infer_batch (left-padded collate) agrees with per-sample infer,
+    conversation mode re-uses the returned KV cache and prefills only the new turn, 48 kHz input is resampled."""
+    from ultravox_b200.data_proc import VoiceSample
+    from ultravox_b200.inference import InferenceChunk, InferenceStats, LocalInference
+    from ultravox_b200.processing import MelSpec, UltravoxProcessor
+    cfg, model, sd, sh = build()
+    tok = _ChatTok()
+    proc = UltravoxProcessor(MelSpec(feature_size=80), tok, mel_device="cuda")
+    inf = LocalInference(model, proc, tok, conversation_mode=False)
+    s1 = VoiceSample.from_prompt_and_raw("Listen to <|audio|> and answer", wave(1, 16000), 16000)
+    s2 = VoiceSample.from_prompt_and_raw("<|audio|> what", (wave(2, 48000 * 2) * 3000).astype(np.int16), 48000)   # 2 s @ 48 kHz
+    s3 = VoiceSample.from_prompt("plain text question without audio")
+    o1 = inf.infer(s1, max_tokens=6)
+    assert o1.output_tokens <= 6 and o1.input_tokens > 7 and o1.text.startswith("t")
+    feats2 = inf._dataproc(s2)
+    assert feats2["audio_lens"].tolist() == [200] and feats2["audio_token_len"].tolist() == [13]    # 2 s -> 200 frames -> 13 tokens
+    # streaming: same tokens as infer, delivered as text deltas + final stats
+    msgs = list(inf.infer_stream(s1, max_tokens=6))
+    assert isinstance(msgs[-1], InferenceStats) and all(isinstance(m, InferenceChunk) for m in msgs[:-1])
+    assert "".join(m.text for m in msgs[:-1]) == o1.text and msgs[-1].output_tokens == o1.output_tokens
+    # batch (left padding; audio rows together, text-only rows together - the reference collator cannot mix them) vs one by one
+    s4 = VoiceSample.from_prompt("another much longer plain text question to force left padding in the batch")
+    first, rest = [], []
+    for group in ([s1, s2], [s3, s4]):
+        singles = [inf.infer(s, max_tokens=5) for s in group]
+        batch = inf.infer_batch(group, max_tokens=5)
+        assert len(batch) == 2 and all(b.input_tokens == max(s.input_tokens for s in singles) for b in batch)
+        for sg, bt in zip(singles, batch):
+            a, b = sg.text.split(), bt.text.split()
+            first.append(a[0] == b[0])
+            rest += [x == y for x, y in zip(a, b)]
+    # random-init weights have near-tied logits, and a greedy sequence diverges for good after one flipped token: the strict
+    # checks of the padded path are teacher-forced (test_left_padded_batch_forward_and_generate); here the first tokens
+    # (pure prefill) must agree and the continuations mostly
+    assert np.mean(first) >= 0.75 and np.mean(rest) >= 0.4, (first, np.mean(rest))
+    with pytest.raises(NotImplementedError):
+        inf.infer(s3, max_tokens=2, temperature=0.7)
+    # conversation mode: turn 2 only prefills its own suffix on top of the cache from turn 1
+    conv = LocalInference(model, proc, tok, conversation_mode=True)
+    c1 = conv.infer(s1, max_tokens=4)
+    cache = conv.past_key_values
+    assert cache is not None and cache.length == c1.input_tokens + c1.output_tokens - 1
+    assert conv.past_messages[-1] == {"role": "assistant", "content": c1.text}
+    assert conv.past_messages[0]["content"].count(tok.eos_token) == 7 and "<|audio|>" not in conv.past_messages[0]["content"]
+    seen = []
+    orig = model.llama_hidden
+    model.llama_hidden = lambda emb, *a, **k: (seen.append(emb.shape[1]), orig(emb, *a, **k))[1]
+    try:
+        c2 = conv.infer(VoiceSample.from_prompt("and then what happened"), max_tokens=4)
+    finally:
+        model.llama_hidden = orig
+    assert c2.input_tokens > c1.input_tokens + c1.output_tokens and seen[0] == c2.input_tokens - cache.length   # suffix only
+    assert conv.past_key_values.length == c2.input_tokens + c2.output_tokens - 1 and len(conv.past_messages) == 4
+    with pytest.raises(AssertionError):
+        conv.infer_batch([s1])

@@ -550,13 +550,15 @@ class UltravoxModel(nn.Module):
                  inputs_embeds: Optional[torch.Tensor] = None, audio_token_start_idx=None, audio_lens=None,
                  audio_token_len=None, audio_batch_size=None, max_new_tokens: int = 20, eos_token_id=None,
                  attention_mask: Optional[torch.Tensor] = None, past_key_values: Optional[KVCache] = None,
-                 return_dict_in_generate: bool = False, **kwargs):
+                 return_dict_in_generate: bool = False, streamer=None, pad_token_id: Optional[int] = None, **kwargs):
         """Greedy decoding (the reference's default: temperature None/0, ref infer.py:319-328).  Returns prompt ids
         followed by the new tokens, like ``GenerationMixin.generate`` (ref :398-426).
 
         ``past_key_values``: conversation KV reuse (ref infer.py:126-148): the cache already holds the first
         ``past_key_values.length`` positions of ``input_ids`` (earlier turns incl. the reply), so only the new suffix is
-        embedded, spliced and prefilled; ``return_dict_in_generate=True`` hands the cache back for the next turn."""
+        embedded, spliced and prefilled; ``return_dict_in_generate=True`` hands the cache back for the next turn.
+        ``streamer``: object with ``put(tensor)`` / ``end()`` (transformers' streamer protocol: the prompt first, then one
+        call per new token).  Rows that have produced an EOS keep emitting ``pad_token_id`` (default: the first EOS id)."""
         dev = self.device
         input_ids = input_ids.to(dev)
         B, S = input_ids.shape
@@ -592,13 +594,21 @@ class UltravoxModel(nn.Module):
                     inputs_embeds = ops.embed_splice(input_ids, self.language_model.model.embed_tokens.weight, None, None)
             out = self.forward(input_ids[:, P:], None, inputs_embeds[:, P:].contiguous(), past_key_values=cache, logits_to_keep=1)
         eos = set([eos_token_id] if isinstance(eos_token_id, int) else (eos_token_id or []))
+        eos_t = torch.tensor(sorted(eos), device=dev) if eos else None
+        pad_id = pad_token_id if pad_token_id is not None else (min(eos) if eos else 0)
         seq = [input_ids]
+        if streamer is not None:
+            streamer.put(input_ids)
         done = torch.zeros(B, dtype=torch.bool, device=dev)
         tok = ops.argmax(out.logits.view(B, -1))
         for step in range(max_new_tokens):
-            seq.append(tok.view(B, 1))
             if eos:
-                done |= torch.isin(tok, torch.tensor(sorted(eos), device=dev))
+                tok = torch.where(done, torch.full_like(tok, pad_id), tok)      # finished rows emit padding (HF semantics)
+            seq.append(tok.view(B, 1))
+            if streamer is not None:
+                streamer.put(tok)
+            if eos:
+                done |= torch.isin(tok, eos_t)
                 if bool(done.all()):
                     break
             if step == max_new_tokens - 1:
@@ -607,6 +617,8 @@ class UltravoxModel(nn.Module):
             positions = (S + step - pad).to(torch.int32) if kv_start is not None else None
             hidden = self.llama_hidden(emb, cache, None, kv_start, positions)
             tok = ops.argmax(ops.lm_head(hidden[:, -1, :], self.language_model.lm_head.weight))
+        if streamer is not None:
+            streamer.end()
         sequences = torch.cat(seq, dim=1)
         return GenerateOutput(sequences, cache) if return_dict_in_generate else sequences
 
