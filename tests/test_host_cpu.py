@@ -330,3 +330,73 @@ def test_model_loads_lora_wrapped_checkpoint():
     cfg0 = preset("micro")
     with pytest.raises(ValueError):                                                    # LoRA weights but r = 0 in the config
         UltravoxModel(cfg0, device="cpu").load_state_dict(wrapped)
+
+
+def test_local_inference_host_logic():
+    """Host half of the LocalInference mirror (ref inference/infer.py:52-124, base.py): conversation bookkeeping, thinking
+    post-processing, resampling length, the token queue; generation itself is covered by the GPU tests."""
+    import torch
+    from ultravox_b200.data_proc import VoiceSample
+    from ultravox_b200.inference import (InferenceChunk, InferenceStats, LocalInference, VoiceInference, VoiceOutput, _TokenQueue,
+                                         resample_to_16k)
+
+    class FakeModel:
+        device = torch.device("cpu")
+
+        def eval(self):
+            return self
+
+    tok = StubTokenizer()
+    tok.padding_side = "left"
+    inf = LocalInference(FakeModel(), object(), tok, conversation_mode=True)
+    with pytest.raises(ValueError):
+        inf._get_sample_with_past(None)                               # nothing to continue from
+    msgs = [{"role": "user", "content": "hear <|audio|> now"}]
+    past = inf._build_past_messages(msgs, 3, "fine")
+    assert past == [{"role": "user", "content": "hear " + tok.eos_token * 3 + " now"}, {"role": "assistant", "content": "fine"}]
+    assert msgs[0]["content"] == "hear <|audio|> now"                  # the query itself is not edited in place
+    with pytest.raises(ValueError):
+        inf._build_past_messages([{"role": "user", "content": "<|audio|> <|audio|>"}], 3, "x")
+    assert inf._build_past_messages([{"role": "user", "content": "text only"}], 0, "ok")[-1]["content"] == "ok"
+    inf.update_conversation(past, "cache")
+    s = inf._get_sample_with_past(VoiceSample.from_prompt("next"))
+    assert [m["role"] for m in s.messages] == ["user", "assistant", "user"] and inf.past_key_values == "cache"
+    assert inf._get_sample_with_past(None).messages == past
+    inf.update_conversation()
+    assert inf.past_messages == [] and inf.past_key_values is None
+    # thinking post-processing
+    assert inf._postprocess_response("plain") == ("plain", None)
+    th = LocalInference(FakeModel(), object(), tok, enable_thinking=True, thinking_regex=r"<think>(.*?)</think>")
+    assert th._postprocess_response("<think> a b </think> answer") == ("answer", "a b")
+    with pytest.raises(ValueError):
+        th._postprocess_response("no thoughts here")
+    with pytest.raises(ValueError):
+        LocalInference(FakeModel(), object(), tok, enable_thinking=True)._postprocess_response("x")
+    with pytest.raises(ValueError):
+        LocalInference(FakeModel(), object(), tok, dtype=torch.float16)
+    tok_r = StubTokenizer()                                            # padding_side "right" is refused like the reference
+    with pytest.raises(AssertionError):
+        LocalInference(FakeModel(), object(), tok_r)
+    # resampling: 48 kHz -> 16 kHz keeps duration (ref infer_test.py:112-132 pins the resulting frame count)
+    x = np.sin(2 * np.pi * 440 * np.arange(48000) / 48000).astype(np.float32)
+    y = resample_to_16k(x, 48000)
+    assert y.dtype == np.float32 and len(y) == 16000
+    ref = np.sin(2 * np.pi * 440 * np.arange(16000) / 16000)
+    assert np.abs(y[200:-200] - ref[200:-200]).max() < 2e-3
+    assert resample_to_16k(x[:16000], 16000) is not None and len(resample_to_16k(x[:44100], 44100)) == 16000
+    # streamer protocol: the prompt is skipped, tokens flow, end() terminates the iterator
+    q = _TokenQueue()
+    q.put(torch.tensor([[1, 2, 3]]))
+    q.put(torch.tensor([7]))
+    q.put(torch.tensor([9]))
+    q.end()
+    assert list(q) == [7, 9]
+
+    class Once(VoiceInference):                                        # base-class fallbacks
+        def infer(self, sample, max_tokens=None, temperature=None):
+            return VoiceOutput("hi", 3, 1)
+
+    o = Once()
+    assert [v.text for v in o.infer_batch([None, None])] == ["hi", "hi"]
+    out = list(o.infer_stream(None))
+    assert out == [InferenceChunk("hi"), InferenceStats(3, 1)]
