@@ -400,3 +400,70 @@ def test_local_inference_host_logic():
     assert [v.text for v in o.infer_batch([None, None])] == ["hi", "hi"]
     out = list(o.infer_stream(None))
     assert out == [InferenceChunk("hi"), InferenceStats(3, 1)]
+
+
+def test_transformers_registration_and_repetition_penalty():
+    """SURVEY 8b registration row (ref ultravox_model.py:997-1003, ultravox_processing.py:385-387, ultravox_pipeline.py:128-133)
+    and the pipeline's default logits processor (hf RepetitionPenaltyLogitsProcessor) - bit-exact on CPU."""
+    import torch
+    import transformers
+    from transformers.activations import ACT2FN
+    from transformers.generation.logits_process import RepetitionPenaltyLogitsProcessor
+    from transformers.models.auto.modeling_auto import MODEL_MAPPING
+    from transformers.models.auto.processing_auto import PROCESSOR_MAPPING
+    from ultravox_b200 import model, pipeline
+    from ultravox_b200.config import UltravoxConfig
+    assert isinstance(transformers.AutoConfig.for_model("ultravox"), UltravoxConfig)
+    assert MODEL_MAPPING[UltravoxConfig] is model.UltravoxModel
+    assert PROCESSOR_MAPPING[UltravoxConfig] is UltravoxProcessor
+    assert isinstance(ACT2FN["swiglu"], model.SwiGLU)
+    task = transformers.pipelines.PIPELINE_REGISTRY.check_task("ultravox-pipeline")
+    assert task[1]["impl"] is pipeline.UltravoxPipeline
+    g = torch.Generator().manual_seed(0)
+    for pen in (1.0, 1.1, 2.5):
+        lg, seq = torch.randn(3, 50, generator=g), torch.randint(0, 50, (3, 9), generator=g)
+        assert torch.equal(model.apply_repetition_penalty(lg.clone(), seq, pen), RepetitionPenaltyLogitsProcessor(pen)(seq, lg.clone())
+                           if pen != 1.0 else lg)
+
+
+def test_pipeline_host_stages():
+    """ref ultravox_pipeline.py:52-126: parameter split, audio dtype normalisation, prompt / turns handling, terminators, slicing."""
+    import torch
+    from ultravox_b200.pipeline import UltravoxPipeline
+
+    def chat(turns, add_generation_prompt=True, tokenize=False, **kw):
+        return " ".join(f"<s> {m['role']} : {m['content']}" for m in turns) + (" <s> assistant :" if add_generation_prompt else "")
+
+    tok = StubTokenizer()
+    tok.pad_token_id = tok.eos_token_id
+    tok.apply_chat_template = chat
+    tok.added_tokens_encoder = {"<|eot_id|>": 128009}
+    tok.convert_tokens_to_ids = lambda t: tok.added_tokens_encoder[t]
+    tok.decode = lambda ids, skip_special_tokens=True: " ".join(str(int(i)) for i in ids)
+    calls = {}
+
+    class FakeModel:
+        device = torch.device("cpu")
+
+        def generate(self, **kw):
+            calls.update(kw)
+            return torch.cat([kw["input_ids"], torch.tensor([[11, 12, 13]])], dim=1)
+
+    proc = UltravoxProcessor(MelSpec(feature_size=80), tok, defer_mel=True)
+    pipe = UltravoxPipeline(FakeModel(), tokenizer=tok, processor=proc)
+    assert pipe._sanitize_parameters(temperature=0.5, max_new_tokens=7, foo=1) == ({}, {"temperature": 0.5, "max_new_tokens": 7}, {})
+    a16 = (wave(0, 16000) * 2000).astype(np.int16)
+    out = pipe.preprocess({"audio": a16, "sampling_rate": 16000})
+    assert out["audio_token_len"].tolist() == [7] and out["audio_waveforms"].dtype == torch.float32
+    assert float(out["audio_waveforms"].abs().max()) <= 1.0                                  # int16 / 32768
+    turns = [{"role": "system", "content": "be brief"}]
+    out2 = pipe.preprocess({"audio": wave(0, 16000).astype(np.float64), "turns": turns, "prompt": "what is said", "sampling_rate": 16000})
+    assert turns[-1] == {"role": "user", "content": "what is said <|audio|>"} and out2["audio_token_len"].tolist() == [7]
+    keep = [{"role": "user", "content": "about <|audio|> please"}]
+    pipe.preprocess({"audio": wave(1, 32000), "turns": keep, "sampling_rate": 16000})
+    assert len(keep) == 1                                                                    # the last turn is the user's: used as is
+    text = pipe({"audio": wave(0, 16000), "sampling_rate": 16000}, max_new_tokens=3)
+    assert text == "11 12 13" and calls["repetition_penalty"] == 1.1 and calls["do_sample"] is False
+    assert calls["eos_token_id"] == [128009, 128009] and calls["max_new_tokens"] == 3
+    with pytest.raises(ValueError):
+        UltravoxPipeline(FakeModel())

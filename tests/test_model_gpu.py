@@ -456,3 +456,28 @@ def test_local_inference_single_batch_stream_conversation():
     assert conv.past_key_values.length == c2.input_tokens + c2.output_tokens - 1 and len(conv.past_messages) == 4
     with pytest.raises(AssertionError):
         conv.infer_batch([s1])
+
+
+def test_pipeline_end_to_end_and_repetition_penalty():
+    """ref ultravox_pipeline.py: one call from raw audio to text; penalty 1.0 == plain greedy generate, the default 1.1 goes
+    through the HF-exact logits processor (unit-tested on CPU) on the device logits of every step."""
+    from ultravox_b200.data_proc import VoiceSample
+    from ultravox_b200.inference import LocalInference
+    from ultravox_b200.pipeline import UltravoxPipeline
+    from ultravox_b200.processing import MelSpec, UltravoxProcessor
+    cfg, model, sd, sh = build()
+    tok = _ChatTok()
+    proc = UltravoxProcessor(MelSpec(feature_size=80), tok, mel_device="cuda")
+    pipe = UltravoxPipeline(model, tokenizer=tok, processor=proc)
+    a = wave(4, 16000)
+    plain = pipe({"audio": a, "sampling_rate": 16000, "prompt": "Listen to <|audio|> and answer"}, max_new_tokens=6, repetition_penalty=1.0)
+    inf = LocalInference(model, proc, tok)
+    ref = inf.infer(VoiceSample.from_prompt_and_raw("Listen to <|audio|> and answer", a, 16000), max_tokens=6)
+    assert plain == ref.text
+    pen = pipe({"audio": (a * 20000).astype(np.int16), "sampling_rate": 16000}, max_new_tokens=6)       # default penalty 1.1
+    assert isinstance(pen, str) and 1 <= len(pen.split()) <= 6
+    toks = pen.split()
+    strong = pipe({"audio": a, "sampling_rate": 16000}, max_new_tokens=8, repetition_penalty=50.0).split()
+    assert len(set(strong)) == len(strong)                  # a huge penalty never repeats a token it has already produced
+    with pytest.raises(NotImplementedError):
+        pipe({"audio": a, "sampling_rate": 16000}, temperature=0.7)

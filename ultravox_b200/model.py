@@ -550,7 +550,8 @@ class UltravoxModel(nn.Module):
                  inputs_embeds: Optional[torch.Tensor] = None, audio_token_start_idx=None, audio_lens=None,
                  audio_token_len=None, audio_batch_size=None, max_new_tokens: int = 20, eos_token_id=None,
                  attention_mask: Optional[torch.Tensor] = None, past_key_values: Optional[KVCache] = None,
-                 return_dict_in_generate: bool = False, streamer=None, pad_token_id: Optional[int] = None, **kwargs):
+                 return_dict_in_generate: bool = False, streamer=None, pad_token_id: Optional[int] = None,
+                 repetition_penalty: float = 1.0, temperature: Optional[float] = None, do_sample: bool = False, **kwargs):
         """Greedy decoding (the reference's default: temperature None/0, ref infer.py:319-328).  Returns prompt ids
         followed by the new tokens, like ``GenerationMixin.generate`` (ref :398-426).
 
@@ -559,6 +560,8 @@ class UltravoxModel(nn.Module):
         embedded, spliced and prefilled; ``return_dict_in_generate=True`` hands the cache back for the next turn.
         ``streamer``: object with ``put(tensor)`` / ``end()`` (transformers' streamer protocol: the prompt first, then one
         call per new token).  Rows that have produced an EOS keep emitting ``pad_token_id`` (default: the first EOS id)."""
+        if do_sample or (temperature is not None and temperature > 0):
+            raise NotImplementedError("sampling is not built; greedy decoding only (the reference's default)")
         dev = self.device
         input_ids = input_ids.to(dev)
         B, S = input_ids.shape
@@ -600,7 +603,14 @@ class UltravoxModel(nn.Module):
         if streamer is not None:
             streamer.put(input_ids)
         done = torch.zeros(B, dtype=torch.bool, device=dev)
-        tok = ops.argmax(out.logits.view(B, -1))
+        penalised = repetition_penalty is not None and float(repetition_penalty) != 1.0
+
+        def pick(logits_bv: torch.Tensor) -> torch.Tensor:
+            if penalised:
+                logits_bv = apply_repetition_penalty(logits_bv, torch.cat(seq, dim=1), float(repetition_penalty))
+            return ops.argmax(logits_bv.contiguous())
+
+        tok = pick(out.logits.view(B, -1))
         for step in range(max_new_tokens):
             if eos:
                 tok = torch.where(done, torch.full_like(tok, pad_id), tok)      # finished rows emit padding (HF semantics)
@@ -616,11 +626,30 @@ class UltravoxModel(nn.Module):
             emb = ops.embed_splice(tok.view(B, 1), self.language_model.model.embed_tokens.weight, None, None)
             positions = (S + step - pad).to(torch.int32) if kv_start is not None else None
             hidden = self.llama_hidden(emb, cache, None, kv_start, positions)
-            tok = ops.argmax(ops.lm_head(hidden[:, -1, :], self.language_model.lm_head.weight))
+            tok = pick(ops.lm_head(hidden[:, -1, :], self.language_model.lm_head.weight))
         if streamer is not None:
             streamer.end()
         sequences = torch.cat(seq, dim=1)
         return GenerateOutput(sequences, cache) if return_dict_in_generate else sequences
+
+
+class SwiGLU(nn.Module):
+    """``silu(gate) * x`` with ``x, gate = chunk(2, -1)`` (ref ultravox_model.py:739-742), as the module the reference registers
+    under ``ACT2FN["swiglu"]``; runs ``uvx_swiglu`` (CUDA bf16 only - there is no CPU fallback)."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return ops.swiglu(x, gate_first=False)
+
+
+def apply_repetition_penalty(logits: torch.Tensor, sequences: torch.Tensor, penalty: float) -> torch.Tensor:
+    """CTRL-style penalty on every token already in ``sequences`` ([B, T] ids): positive scores are divided by ``penalty``,
+    negative ones multiplied (hf:generation/logits_process.py ``RepetitionPenaltyLogitsProcessor``, which the reference's
+    pipeline enables with 1.1, ref ultravox_pipeline.py:95-113).  Plain tensor ops on the [B, V] logits of one step."""
+    if penalty == 1.0:
+        return logits
+    seen = torch.gather(logits, 1, sequences)
+    seen = torch.where(seen < 0, seen * penalty, seen / penalty)
+    return logits.scatter(1, sequences, seen)
 
 
 def _sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> torch.Tensor:
@@ -630,3 +659,18 @@ def _sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> to
     inv = torch.exp(-inc * torch.arange(channels // 2))
     t = torch.arange(length).view(-1, 1) * inv.view(1, -1)
     return torch.cat([t.sin(), t.cos()], dim=1)
+
+
+# -- registration with the transformers Auto* machinery, as the reference does at import time (ref ultravox_model.py:997-1003)
+def _register_with_transformers() -> None:
+    import transformers
+    from transformers.activations import ACT2FN
+    transformers.AutoConfig.register("ultravox", UltravoxConfig, exist_ok=True)
+    transformers.AutoModel.register(UltravoxConfig, UltravoxModel, exist_ok=True)
+    try:
+        ACT2FN["swiglu"] = SwiGLU
+    except TypeError:                        # ClassInstantier of older transformers takes (class, kwargs) tuples as well
+        ACT2FN["swiglu"] = (SwiGLU, {})
+
+
+_register_with_transformers()

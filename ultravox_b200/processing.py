@@ -233,3 +233,13 @@ class UltravoxProcessor:
     def model_input_names(self):
         names = list(getattr(self.tokenizer, "model_input_names", ["input_ids", "attention_mask"]))
         return list(set(names + ["input_features"]))
+
+
+def _register_with_transformers() -> None:
+    """``AutoProcessor`` mapping, as the reference registers it at import time (ref ultravox_processing.py:385-387)."""
+    import transformers
+    from .config import UltravoxConfig
+    transformers.AutoProcessor.register(UltravoxConfig, UltravoxProcessor, exist_ok=True)
+
+
+_register_with_transformers()
