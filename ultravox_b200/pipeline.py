@@ -39,27 +39,33 @@ class UltravoxPipeline:
         generation_keys = ["temperature", "max_new_tokens", "repetition_penalty"]
         return {}, {k: kwargs[k] for k in kwargs if k in generation_keys}, {}
 
+    @staticmethod
+    def _as_float_pcm(audio):
+        """float64 -> float32, int16 / int32 -> float32 in [-1, 1); anything else is left to the processor to judge."""
+        if not isinstance(audio, np.ndarray):
+            return audio
+        full_scale = {np.dtype(np.int16): 2.0 ** 15, np.dtype(np.int32): 2.0 ** 31}.get(audio.dtype)
+        if full_scale is not None:
+            return audio.astype(np.float32) / np.float32(full_scale)
+        return audio.astype(np.float32) if audio.dtype == np.float64 else audio
+
     def preprocess(self, inputs: Dict[str, Any]):
+        """``{"audio", "turns", "prompt", "sampling_rate"}`` -> processor features.  A clip without a trailing user turn gets one
+        made from ``prompt`` (default: just the placeholder; the placeholder is appended when the prompt lacks it)."""
         turns: list = inputs.get("turns", [])
-        audio = inputs.get("audio", None)
-        if isinstance(audio, np.ndarray):
-            if audio.dtype == np.float64:
-                audio = audio.astype(np.float32)
-            elif audio.dtype == np.int16:
-                audio = audio.astype(np.float32) / np.float32(32768.0)
-            elif audio.dtype == np.int32:
-                audio = audio.astype(np.float32) / np.float32(2147483648.0)
-        if audio is not None and (len(turns) == 0 or turns[-1]["role"] != "user"):
+        audio = self._as_float_pcm(inputs.get("audio"))
+        needs_user_turn = audio is not None and not (turns and turns[-1]["role"] == "user")
+        if needs_user_turn:
             prompt = inputs.get("prompt", AUDIO_PLACEHOLDER)
             if AUDIO_PLACEHOLDER not in prompt:
                 logging.warning("Prompt does not contain '<|audio|>', appending '<|audio|>' to the end of the prompt.")
-                prompt += " " + AUDIO_PLACEHOLDER
+                prompt = f"{prompt} {AUDIO_PLACEHOLDER}"
             turns.append({"role": "user", "content": prompt})
-        text = self.processor.tokenizer.apply_chat_template(turns, add_generation_prompt=True, tokenize=False)
-        if "sampling_rate" not in inputs and audio is not None:
+        if audio is not None and "sampling_rate" not in inputs:
             logging.warning("No sampling rate provided, using default of 16kHz. We highly recommend providing the correct "
                             "sampling rate.")
-        return self.processor(text=text, audio=audio, sampling_rate=inputs.get("sampling_rate", 16000))
+        rendered = self.processor.tokenizer.apply_chat_template(turns, add_generation_prompt=True, tokenize=False)
+        return self.processor(text=rendered, audio=audio, sampling_rate=inputs.get("sampling_rate", 16000))
 
     def _forward(self, model_inputs: Dict[str, Any], temperature: Optional[float] = None,
                  max_new_tokens: Optional[int] = None, repetition_penalty: float = 1.1) -> List[int]:
