@@ -46,6 +46,36 @@ def test_gemm_plain(ops, M, N, K):
     assert rel(y, ref.to(BF)) < 1e-3, rel(y, ref)
 
 
+def test_gemm_exact_bench_shapes(ops):
+    """The shapes only bench.py exercised in round 1: Llama-3.1-8B prefill at S=201 - fused qkv
+    201x6144x4096, o_proj 201x4096x4096 (+residual, fused RMSNorm), gate|up 201x28672x4096 (ragged 208-wide tiles at full K),
+    down 201x4096x14336 (split-K + residual + fused RMSNorm) - and the encoder GEMMs at T=1500 (qkv+bias, fc1+bias+GELU,
+    fc2+bias+residual).  fp32 math on the same bf16 inputs (torch fp32 matmul on the GPU, TF32 off), rounded once."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    M = 201
+    x = rnd(M, 4096, seed=1)
+    for N, K, seed in ((6144, 4096, 2), (28672, 4096, 3)):
+        w = rnd(N, K, scale=0.02, seed=seed)
+        y = ops.linear(x, w)
+        assert rel(y, x.float() @ w.float().T) < 1e-3, (N, K)
+    for N, K, seed in ((4096, 4096, 4), (4096, 14336, 5)):
+        xa, w = rnd(M, K, seed=seed), rnd(N, K, scale=0.02, seed=seed + 10)
+        r, nw = rnd(M, N, seed=seed + 20), rnd(N, seed=seed + 30)
+        h, xn = r.clone(), torch.empty(M, N, dtype=BF, device="cuda")
+        ops.linear(xa, w, residual=h, out=h, norm=(nw, 1e-5, xn))
+        assert rel(h, xa.float() @ w.float().T + r.float()) < 1e-3, (N, K)
+        assert torch.equal(xn, ops.rmsnorm(h, nw, 1e-5)), (N, K)
+    T = 1500
+    xe = rnd(T, 1280, seed=6)
+    wq, bq = rnd(3840, 1280, scale=0.02, seed=7), rnd(3840, seed=8)
+    assert rel(ops.linear(xe, wq, bias=bq), xe.float() @ wq.float().T + bq.float()) < 1e-3
+    w1, b1 = rnd(5120, 1280, scale=0.02, seed=9), rnd(5120, seed=10)
+    f1 = ops.linear(xe, w1, bias=b1, act=ops.ACT_GELU)
+    assert rel(f1, F.gelu(xe.float() @ w1.float().T + b1.float())) < 1e-3
+    w2, b2, r2 = rnd(1280, 5120, scale=0.02, seed=11), rnd(1280, seed=12), rnd(T, 1280, seed=13)
+    assert rel(ops.linear(f1, w2, bias=b2, residual=r2), f1.float() @ w2.float().T + b2.float() + r2.float()) < 1e-3
+
+
 @pytest.mark.parametrize("cfg,splits", [(2128, 4), (2256, 3), (1128, 5), (1064, 2), (2064, 7), (1256, 2), (2208, 1), (1208, 1)])
 def test_gemm_forced_configs_and_split_k(ops, cfg, splits):
     from ultravox_b200 import _lib
@@ -148,7 +178,7 @@ def test_gemm_row_map(ops):
 
 
 @pytest.mark.parametrize("stride,Cin,Cout,T,N", [(1, 80, 128, 100, 2), (2, 128, 128, 100, 2), (2, 128, 256, 37, 3),
-                                                 (1, 128, 1280, 3000, 1)])
+                                                 (1, 128, 1280, 3000, 1), (2, 1280, 1280, 3000, 1)])
 def test_conv_implicit_gemm(ops, stride, Cin, Cout, T, N):
     x = rnd(N, Cin, T, seed=5).float()           # [N, C, T] "mel"
     w = rnd(Cout, Cin, 3, scale=0.05, seed=6)
