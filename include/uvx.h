@@ -194,6 +194,30 @@ int uvx_kv_append(const void* qkv, int64_t row_stride, int64_t k_col, int64_t v_
                   void* v_cache, int64_t cache_batch_stride, const int32_t* positions, int64_t B, uvx_stream_t stream);
 /* a[i] += delta (and b[i] += delta when b != NULL): advances the device-side positions / lengths after each step     */
 int uvx_add_i32(int32_t* a, int32_t* b, int64_t n, int32_t delta, uvx_stream_t stream);
+/* prefill counterpart of uvx_kv_append: rows b*S + s of the fused projection -> cache[b, past + s] (k and v sections),
+ * what DynamicCache.update does for the prompt (hf:cache_utils.py; call site hf:modeling_llama.py:262-273)           */
+int uvx_kv_write(const void* qkv, int64_t row_stride, int64_t k_col, int64_t v_col, int64_t kv_width, void* k_cache,
+                 void* v_cache, int64_t cache_batch_stride, int64_t B, int64_t S, int64_t past, uvx_stream_t stream);
+
+/* The rest of one `GenerationMixin` step (ref:ultravox/model/ultravox_model.py:398-426 -> hf:generation/utils.py _sample),
+ * with every per-step scalar read from DEVICE memory so that a whole decode step replays from one CUDA graph:
+ * uvx_repetition_penalty  scores of tokens already in seq[b, 0:cur_len[0]] are divided (positive) / multiplied (negative)
+ *                         by `penalty`, each distinct token once (hf:generation/logits_process.py
+ *                         RepetitionPenaltyLogitsProcessor; the reference pipeline enables 1.1, ref ultravox_pipeline.py:95-113);
+ *                         scratch: [B, seq_stride] fp32.
+ * uvx_sample              out[b] ~ softmax(logits[b] / temperature) restricted to the top_k largest logits (top_k <= 0: all),
+ *                         by inverse CDF on the uniform u[step_idx[0] * u_stride + b] (step_idx NULL = 0): the do_sample branch of
+ *                         ref:ultravox/inference/infer.py:319-328.  Deterministic given u.
+ * uvx_token_finish        tok[b] = done[b] ? pad_id : tok[b]; seq[b, cur_len[0]] = tok[b]; done[b] |= tok[b] in eos_ids;
+ *                         cur_len[0]++, step_idx[0]++ (if given), bump{0,1,2}[b]++ (if given: cache slot / visible keys / RoPE
+ *                         position); all_done[0] = all(done).                                                                 */
+int uvx_repetition_penalty(float* logits, int64_t B, int64_t V, const int64_t* seq, int64_t seq_stride, const int32_t* cur_len,
+                           float penalty, float* scratch, uvx_stream_t stream);
+int uvx_sample(const float* logits, int64_t B, int64_t V, float temperature, int32_t top_k, const float* u, const int32_t* step_idx,
+               int64_t u_stride, int64_t* out_idx, uvx_stream_t stream);
+int uvx_token_finish(int64_t* tok, int32_t* done, const int64_t* eos_ids, int32_t n_eos, int64_t pad_id, int64_t* seq,
+                     int64_t seq_stride, int32_t* cur_len, int32_t* step_idx, int32_t* bump0, int32_t* bump1, int32_t* bump2,
+                     int32_t* all_done, int64_t B, uvx_stream_t stream);
 
 /* Shifted causal-LM cross entropy (hf:loss/loss_utils.py:28-67; called through LlamaForCausalLM.forward(labels=)
  * from ref:ultravox/model/ultravox_model.py:328-334).  logits [B*S, V] fp32 (row_stride elements), labels [B, S]

@@ -130,6 +130,31 @@ def test_collator_left_padding_displacement(cases):
         assert list(got["audio_values"].shape) == exp["audio_values_shape"]
 
 
+def test_collator_deferred_mel_layout(cases):
+    """the deferred-mel samples (the DataLoader-safe mode) go through the collator as they are: same index vectors as
+    the reference fixtures, waveforms flattened per clip and zero-padded to the batch-longest multiple of the hop, each clip's
+    own padded width recorded (``audio_pad_frames``), nothing left behind for ``tokenizer.pad`` to choke on."""
+    sr = 16000
+    for c in cases["collator"]:
+        tok = StubTokenizer()
+        tok.padding_side = c["padding_side"]
+        p = UltravoxProcessor(MelSpec(feature_size=80), tok, defer_mel=True)
+        samples = []
+        for text, n, i in (("Test with <|audio|>", sr, 0), ("Other longer text with <|audio|> more", 35 * sr, 1)):
+            s = dict(p(text, audio=wave(i, n), sampling_rate=sr))
+            s["input_ids"], s["attention_mask"] = s["input_ids"][0], s["attention_mask"][0]
+            samples.append(s)
+        got = DataCollatorForSeq2SeqWithAudio(tok)(samples)
+        exp = c["out"]
+        for key in ("input_ids", "attention_mask", "audio_lens", "audio_token_len", "audio_token_start_idx", "audio_batch_size"):
+            assert got[key].tolist() == exp[key], (c["padding_side"], key)
+        assert "audio_values" not in got
+        assert tuple(got["audio_waveforms"].shape) == (2, 35 * sr) and got["audio_waveforms"].dtype == torch.float32
+        assert got["audio_num_frames"].tolist() == [100, 3500] and got["audio_pad_frames"].tolist() == [100, 3500]
+        assert float(got["audio_waveforms"][0, sr:].abs().sum()) == 0.0
+        assert np.array_equal(got["audio_waveforms"][0, :sr].numpy(), wave(0, sr))
+
+
 def test_config_surface_round_trip(tmp_path):
     cfg = preset("micro", audio_latency_block_size=100)
     assert cfg.model_type == "ultravox" and cfg.stack_factor == 8 and cfg.projector_ln_mid is True

@@ -271,6 +271,66 @@ def test_generate_cache_decode_matches_cacheless_reforward():
         cur = torch.cat([cur, table[tok][None]], dim=1)
 
 
+def test_decode_engine_ignores_cache_tail_contents():
+    """the static KV cache is torch.empty; rows past a stream's length must never reach the P.V product
+    (a masked probability of 0 times NaN is NaN).  Same tokens with the cache pre-filled with NaN."""
+    from ultravox_b200 import ops
+    from ultravox_b200.engine import DecodeEngine
+    cfg, model, sd, sh = build()
+    padded, batch = make_batch(cfg, [16000])
+    mel = ops.logmel(torch.from_numpy(padded).cuda(), sh.n_mels)
+    emb = model._prepare_audio_embeds(batch["input_ids"].cuda(), mel, batch["audio_token_start_idx"], batch["audio_lens"],
+                                      batch["audio_token_len"], batch["audio_batch_size"])
+    runs = []
+    for poison in (False, True):
+        de = DecodeEngine(model, 1, 150)
+        de.cache.k.fill_(float("nan") if poison else 0.0)
+        de.cache.v.fill_(float("nan") if poison else 0.0)
+        toks = [int(de.prefill(emb.clone())[0])]
+        for _ in range(5):
+            toks.append(int(de.step().view(-1)[0]))
+        assert bool(torch.isfinite(de.logits).all())
+        runs.append(toks)
+    assert runs[0] == runs[1]
+
+
+def test_generate_sampling_eos_and_deferred_waveforms():
+    from ultravox_b200 import ops
+    cfg, model, sd, sh = build()
+    padded, batch = make_batch(cfg, [16000])
+    mel = ops.logmel(torch.from_numpy(padded).cuda(), sh.n_mels)
+    kw = {k: v.cuda() for k, v in batch.items()}
+    S = batch["input_ids"].shape[1]
+    greedy = model.generate(audio_values=mel, max_new_tokens=12, **kw)
+    # (1) sampling: reproducible for a seeded generator, every token inside the top-k of the teacher-forced distribution
+    g = torch.Generator(device="cuda").manual_seed(11)
+    s1 = model.generate(audio_values=mel, max_new_tokens=12, do_sample=True, temperature=0.9, top_k=20, generator=g, **kw)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    s2 = model.generate(audio_values=mel, max_new_tokens=12, do_sample=True, temperature=0.9, top_k=20, generator=g, **kw)
+    assert torch.equal(s1, s2) and s1.shape == (1, S + 12)
+    full = model(s1[:, :-1], audio_values=mel, **{k: v for k, v in kw.items() if k != "input_ids"}).logits[0].float()
+    for t in range(12):
+        assert int(s1[0, S + t]) in full[S - 1 + t].topk(24).indices.tolist(), t
+    g3 = torch.Generator(device="cuda").manual_seed(12)
+    s3 = model.generate(audio_values=mel, max_new_tokens=12, do_sample=True, temperature=0.9, top_k=20, generator=g3, **kw)
+    assert not torch.equal(s1, s3) or not torch.equal(s1, greedy)
+    # (2) EOS: generation stops right after the step at which the row finished (HF semantics), without a streamer
+    eos = int(greedy[0, S + 2])
+    first = (greedy[0, S:] == eos).nonzero()[0].item()
+    out = model.generate(audio_values=mel, max_new_tokens=12, eos_token_id=[eos], **kw)
+    assert out.shape == (1, S + first + 1) and torch.equal(out[0], greedy[0, :S + first + 1])
+    # (3) deferred mel: raw waveform in, same tokens as the precomputed mel
+    wv = torch.from_numpy(padded)
+    out_w = model.generate(max_new_tokens=6, audio_waveforms=wv, audio_num_frames=torch.tensor([100]), **kw)
+    assert torch.equal(out_w, greedy[:, :S + 6])
+    with pytest.raises(TypeError):
+        model.generate(audio_values=mel, max_new_tokens=2, audio_wavforms=wv, **kw)          # misspelt tensor kwarg is not swallowed
+    # (4) repetition penalty through the graph == eager step-by-step application of the HF rule
+    pen = model.generate(audio_values=mel, max_new_tokens=8, repetition_penalty=1.3, **kw)
+    pen_eager = model.generate(audio_values=mel, max_new_tokens=8, repetition_penalty=1.3, use_graph=False, **kw)
+    assert torch.equal(pen, pen_eager)
+
+
 def test_prefill_engine_graph_matches_eager():
     from ultravox_b200.engine import PrefillEngine
     cfg, model, sd, sh = build()

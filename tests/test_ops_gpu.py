@@ -370,3 +370,82 @@ def test_logmel(ops, n_mels, secs, B):
     assert torch.count_nonzero(tm[:, 0]) == 0 and torch.count_nonzero(tm[:, T + 1]) == 0
     av = ops.mel_to_timemajor(torch.from_numpy(got).cuda())
     assert torch.equal(av, tm)
+
+
+# ------------------------------------------------------------------------------------------ decode-loop helpers (generate.cu)
+def test_repetition_penalty_matches_hf_processor(ops):
+    from transformers.generation.logits_process import RepetitionPenaltyLogitsProcessor
+    g = torch.Generator().manual_seed(3)
+    B, V, cap = 3, 1000, 40
+    logits = torch.randn(B, V, generator=g)
+    seq = torch.randint(0, V, (B, cap), generator=g)
+    seq[0, 5] = seq[0, 2]                                   # duplicates are penalised once (gather - rescale - scatter)
+    seq[1, :7] = 11
+    n = 23
+    ref = RepetitionPenaltyLogitsProcessor(1.1)(seq[:, :n], logits.clone())
+    got = logits.clone().cuda()
+    ops.repetition_penalty_(got, seq.cuda(), torch.tensor([n], dtype=torch.int32).cuda(), 1.1,
+                            torch.empty(B, cap, dtype=torch.float32, device="cuda"))
+    assert torch.equal(got.cpu(), ref)
+
+
+def test_sample_matches_softmax_distribution_and_top_k(ops):
+    g = torch.Generator().manual_seed(5)
+    V, n = 64, 40000
+    logits = (torch.randn(1, V, generator=g) * 2).cuda()
+    big = logits.expand(n, V).contiguous()
+    u = torch.rand(n, generator=g).cuda()
+    T = 0.7
+    picks = ops.sample(big, T, 0, u)
+    p = torch.softmax(logits[0].double() / T, -1).cpu()
+    hist = torch.bincount(picks.cpu(), minlength=V).double() / n
+    assert float((hist - p).abs().max()) < 0.01
+    assert torch.equal(picks, ops.sample(big, T, 0, u))                 # deterministic given u
+    k = 5
+    picks_k = ops.sample(big, T, k, u)
+    topk = set(logits[0].topk(k).indices.tolist())
+    assert set(picks_k.unique().tolist()) <= topk
+    pk = torch.zeros(V, dtype=torch.double)
+    idx = logits[0].topk(k).indices.cpu()
+    pk[idx] = torch.softmax(logits[0, idx.cuda()].double().cpu() / T, -1)
+    hist_k = torch.bincount(picks_k.cpu(), minlength=V).double() / n
+    assert float((hist_k - pk).abs().max()) < 0.01
+    # inverse CDF ends: u = 0 -> the first entry with mass, u -> 1 -> the last
+    ends = ops.sample(logits.expand(2, V).contiguous(), T, 0, torch.tensor([0.0, 0.9999999], device="cuda"))
+    assert ends.tolist() == [0, V - 1]
+    # vocabulary-sized rows: valid ids inside the top-k set, step-indexed uniforms
+    Vb = 128256
+    lg = torch.randn(4, Vb, generator=g).cuda()
+    uu = torch.rand(3, 4, generator=g).cuda()
+    step = torch.tensor([2], dtype=torch.int32).cuda()
+    out = ops.sample(lg, 1.0, 50, uu, step)
+    top = lg.topk(50, -1).indices
+    assert all(int(out[b]) in top[b].tolist() for b in range(4))
+    assert torch.equal(out, ops.sample(lg, 1.0, 50, uu[2].contiguous()))
+
+
+def test_kv_write_and_token_finish(ops):
+    B, S, Hq, Hkv, D, smax, past = 2, 5, 4, 2, 64, 16, 3
+    qkv = rnd(B * S, (Hq + 2 * Hkv) * D, seed=1)
+    kc = torch.zeros(B, smax, Hkv, D, dtype=BF, device="cuda")
+    vc = torch.zeros_like(kc)
+    ops.kv_write(qkv, kc, vc, B, S, past, Hq, Hkv, D)
+    q3 = qkv.view(B, S, -1)
+    assert torch.equal(kc[:, past:past + S].reshape(B, S, -1), q3[:, :, Hq * D:(Hq + Hkv) * D])
+    assert torch.equal(vc[:, past:past + S].reshape(B, S, -1), q3[:, :, (Hq + Hkv) * D:])
+    assert torch.count_nonzero(kc[:, :past]) == 0 and torch.count_nonzero(kc[:, past + S:]) == 0
+    tok = torch.tensor([7, 9, 4], dtype=torch.int64, device="cuda")
+    done = torch.tensor([0, 1, 0], dtype=torch.int32, device="cuda")
+    eos = torch.tensor([4, 100], dtype=torch.int64, device="cuda")
+    seq = torch.zeros(3, 10, dtype=torch.int64, device="cuda")
+    cur = torch.tensor([6], dtype=torch.int32, device="cuda")
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    pos = torch.tensor([5, 5, 5], dtype=torch.int32, device="cuda")
+    lens = pos + 1
+    alld = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops.token_finish(tok, done, eos, 55, seq, cur, step, (pos, lens), alld)
+    assert tok.tolist() == [7, 55, 4] and done.tolist() == [0, 1, 1] and seq[:, 6].tolist() == [7, 55, 4]
+    assert int(cur) == 7 and int(step) == 1 and pos.tolist() == [6, 6, 6] and lens.tolist() == [7, 7, 7] and int(alld) == 0
+    tok.copy_(torch.tensor([100, 1, 2]))
+    ops.token_finish(tok, done, eos, 55, seq, cur, step, (pos, lens), alld)
+    assert tok.tolist() == [100, 55, 55] and done.tolist() == [1, 1, 1] and int(alld) == 1 and int(cur) == 8

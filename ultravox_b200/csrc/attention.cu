@@ -99,7 +99,9 @@ __global__ void __launch_bounds__(kAThreads) attn_fwd_kernel(const AttnParams p)
     bf16* dv = sV + stage * kAN * LD;
     for (int i = tid; i < kAN * CH; i += kAThreads) {
       const int r = i / CH, c = i % CH;
-      const bool ok = (n0 + r) < p.Skv;
+      // rows outside [kv_begin, kv_end) are zero-filled, never read: the cache tail past a sequence's length may hold
+      // anything (torch.empty), and a masked probability of 0 times a NaN/Inf V row would still poison P.V
+      const bool ok = (n0 + r) < kv_end && (n0 + r) >= kv_begin;
       const int64_t row = ok ? n0 + r : 0;
       cp_async16(dk + r * LD + c * 8, kb + row * p.k_rs + c * 8, ok);
       cp_async16(dv + r * LD + c * 8, vb + row * p.v_rs + c * 8, ok);

@@ -92,38 +92,92 @@ class PrefillEngine:
 
 
 class DecodeEngine:
-    """Greedy decode after a prefill, one token per stream per step, the whole step (embedding -> 32/80 layers -> lm head
-    -> argmax -> position bump) captured ONCE in a CUDA graph and replayed per token: positions, KV lengths and the
-    current token live on the device, so nothing in the graph changes between steps.  Linear layers are weight-streaming
-    matrix-vector kernels (uvx_gemv_bf16).  This is the serving loop of ``LocalInference._generate`` with
-    ``temperature in {None, 0}`` (ref:ultravox/inference/infer.py:309-342)."""
+    """Token-by-token decoding after a prefill, the whole step (embedding -> 32/80 layers -> lm head -> logits processing ->
+    greedy / sampled pick -> EOS + sequence bookkeeping -> position bump) captured ONCE in a CUDA graph and replayed per token:
+    positions, KV lengths, the current token, the output sequence and the step counter all live on the device, so nothing in
+    the graph changes between steps and the host never has to synchronise inside the loop.  Linear layers are weight-streaming
+    matrix-vector kernels (uvx_gemv_bf16, slabs of 8 streams).  This is the serving loop of ``LocalInference._generate``
+    (ref:ultravox/inference/infer.py:309-342 -> ``GenerationMixin.generate``): greedy when ``temperature in {None, 0}``,
+    multinomial sampling otherwise; repetition penalty as the reference pipeline sets it (ref ultravox_pipeline.py:95-113);
+    left-padded batches (``kv_start`` + mask-derived RoPE positions, hf:generation/utils.py:707-729)."""
 
-    def __init__(self, model: UltravoxModel, batch: int, max_len: int, use_graph: bool = True):
-        if batch > 8:
-            raise ValueError("DecodeEngine handles up to 8 streams per GPU (uvx_gemv_bf16)")
-        self.model, self.B, self.max_len = model, batch, max_len
+    def __init__(self, model: UltravoxModel, batch: int, max_len: int, use_graph: bool = True, cache=None,
+                 eos_token_ids=None, pad_token_id: int = 0, temperature: float = 0.0, top_k: int = 0,
+                 repetition_penalty: float = 1.0, generator: Optional[torch.Generator] = None):
+        self.model, self.B = model, batch
         dev = model.device
-        tc, lm = model.config.text_config, model.language_model
-        self.cache = model.new_cache(batch, max_len)
-        self.pos = torch.zeros(batch, dtype=torch.int32, device=dev)       # position of the token being fed
-        self.lens = torch.zeros(batch, dtype=torch.int32, device=dev)      # keys visible to it (= pos + 1)
+        self.cache = cache if cache is not None else model.new_cache(batch, max_len)
+        self.max_len = self.cache.capacity
+        self.pos = torch.zeros(batch, dtype=torch.int32, device=dev)        # cache slot of the token being fed
+        self.lens = torch.zeros(batch, dtype=torch.int32, device=dev)       # keys visible to it (= pos + 1)
+        self.rope_pos = torch.zeros(batch, dtype=torch.int32, device=dev)   # its RoPE position (= pos - left padding)
+        self.kv_start: Optional[torch.Tensor] = None
         self.token = torch.zeros(batch, 1, dtype=torch.int64, device=dev)
-        self.cos, self.sin = model._rope_tables(max_len)
+        self.seq = torch.zeros(batch, self.max_len + 1, dtype=torch.int64, device=dev)
+        self.cur_len = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.step_idx = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.done = torch.zeros(batch, dtype=torch.int32, device=dev)
+        self.all_done = torch.zeros(1, dtype=torch.int32, device=dev)
+        eos = sorted(set([eos_token_ids] if isinstance(eos_token_ids, int) else (eos_token_ids or [])))
+        self.eos = torch.tensor(eos, dtype=torch.int64, device=dev) if eos else None
+        self.pad_id = int(pad_token_id)
+        self.temperature, self.top_k = float(temperature or 0.0), int(top_k or 0)
+        self.penalty = float(repetition_penalty or 1.0)
+        self.u = None
+        if self.temperature > 0:
+            # one uniform per (step, stream), drawn up front from the caller's (seedable) generator: the graph reads row step_idx
+            self.u = torch.rand(self.max_len + 1, batch, device=dev, dtype=torch.float32, generator=generator)
+        self.scratch = torch.empty(batch, self.max_len + 1, dtype=torch.float32, device=dev) if self.penalty != 1.0 else None
+        self.cos, self.sin = model._rope_tables(self.max_len + 1)
         self.graph = None
         self.use_graph = use_graph
         self.launches_per_step = 0
+        self.logits = None
+
+    # -- state ---------------------------------------------------------------------------------------------
+    def begin(self, input_ids: torch.Tensor, first_logits: torch.Tensor, kv_start: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """After the prompt has been prefilled into ``self.cache`` (S = input_ids.shape[1] positions): seeds the sequence buffer
+        and the counters, picks the first new token from ``first_logits`` [B, V] fp32.  Returns the device token tensor [B]."""
+        B, S = input_ids.shape
+        if S + 1 > self.max_len + 1:
+            raise ValueError("prompt longer than the KV cache")
+        self.seq[:, :S].copy_(input_ids)
+        self.cur_len.fill_(S)
+        self.step_idx.zero_()
+        self.done.zero_()
+        self.all_done.zero_()
+        self.kv_start = kv_start
+        pad = kv_start if kv_start is not None else torch.zeros(B, dtype=torch.int32, device=self.pos.device)
+        # the pick's token_finish bumps all three by one: the first new token sits at slot S, sees S + 1 keys, RoPE S - pad
+        self.pos.fill_(S - 1)
+        self.lens.fill_(S)
+        self.rope_pos.copy_((S - 1) - pad.to(torch.int32))
+        self._pick(first_logits.contiguous())
+        return self.token.view(-1)
 
     def prefill(self, inputs_embeds: torch.Tensor) -> torch.Tensor:
-        """Runs the prompt through the LLM, fills the cache, returns the first generated token [B]."""
+        """Runs the prompt through the LLM, fills the cache, returns the first generated token [B] (greedy or sampled)."""
         m = self.model
         B, S, _ = inputs_embeds.shape
         self.cache.length = 0
         hid = m.llama_hidden(inputs_embeds, self.cache)
-        tok = ops.argmax(ops.lm_head(hid[:, -1, :], m.language_model.lm_head.weight))
-        self.token.copy_(tok.view(B, 1))
-        self.pos.fill_(S)
-        self.lens.fill_(S + 1)
-        return tok
+        logits = ops.lm_head(hid[:, -1, :], m.language_model.lm_head.weight)
+        self.seq[:, :S].zero_()
+        return self.begin(self.seq[:, :S], logits).clone()
+
+    # -- one step ------------------------------------------------------------------------------------------
+    def _pick(self, logits: torch.Tensor):
+        """logits [B, V] fp32 -> self.token (+ sequence / EOS / counter bookkeeping), all on the device."""
+        self.logits = logits
+        if self.penalty != 1.0:
+            ops.repetition_penalty_(logits, self.seq, self.cur_len, self.penalty, self.scratch)
+        tok = self.token.view(-1)
+        if self.temperature > 0:
+            ops.sample(logits, self.temperature, self.top_k, self.u, self.step_idx, out=tok)
+        else:
+            ops.argmax(logits, out=tok)
+        ops.token_finish(tok, self.done, self.eos, self.pad_id, self.seq, self.cur_len, self.step_idx,
+                         (self.pos, self.lens, self.rope_pos), self.all_done)
 
     def _step(self):
         m = self.model
@@ -136,22 +190,20 @@ class DecodeEngine:
             sa, mlp = layer.self_attn, layer.mlp
             x = ops.rmsnorm(h, layer.input_layernorm.weight, tc.rms_norm_eps)
             qkv = ops.gemv(x, sa.qkv_w)
-            ops.rope_(qkv, nq, nkv, hd, self.cos, self.sin, rows_per_seq=1, positions=self.pos)
+            ops.rope_(qkv, nq, nkv, hd, self.cos, self.sin, rows_per_seq=1, positions=self.rope_pos)
             kc, vc = self.cache.k[li], self.cache.v[li]
             ops.kv_append(qkv, kc, vc, self.pos, nq, nkv, hd)
             att = torch.empty(B, nq * hd, dtype=torch.bfloat16, device=h.device)
             rs = qkv.stride(0)
             ops.attention(qkv.data_ptr(), kc.data_ptr(), vc.data_ptr(), att, B, nq, nkv, 1, smax, hd,
                           (rs, rs, nkv * hd, smax * nkv * hd, nkv * hd, smax * nkv * hd, nq * hd, nq * hd), hd ** -0.5, False,
-                          self.lens, 0)
+                          self.lens, 0, self.kv_start)
             h = ops.gemv(att, sa.o_proj.weight, residual=h)
             x = ops.rmsnorm(h, layer.post_attention_layernorm.weight, tc.rms_norm_eps)
             act = ops.swiglu(ops.gemv(x, mlp.gate_up_w), gate_first=True)
             h = ops.gemv(act, mlp.down_proj.weight, residual=h)
         hn = ops.rmsnorm(h, lm.model.norm.weight, tc.rms_norm_eps)
-        logits = ops.lm_head(hn, lm.lm_head.weight)
-        ops.argmax(logits, out=self.token.view(-1))
-        ops.add_i32_(self.pos, self.lens, 1)
+        self._pick(ops.lm_head(hn, lm.lm_head.weight))
 
     def step(self) -> torch.Tensor:
         """Feeds ``self.token`` (the previous output), writes the next token into it; returns the device tensor."""
@@ -163,17 +215,23 @@ class DecodeEngine:
             self._step()
         return self.token
 
+    def _state(self):
+        return [self.pos, self.lens, self.rope_pos, self.token, self.cur_len, self.step_idx, self.done, self.all_done]
+
     def _step_warm(self):
-        # warm-up on a scratch copy of the state, then capture; the state is restored so no token is lost
-        pos, lens, tok = self.pos.clone(), self.lens.clone(), self.token.clone()
+        # warm-up on a scratch copy of the state, then capture; the state is restored so no token is lost (the cache row and the
+        # sequence column the two trial steps write are rewritten with the same values by the first real step)
+        saved = [t.clone() for t in self._state()]
         self._step()
         torch.cuda.synchronize()
-        self.pos.copy_(pos), self.lens.copy_(lens), self.token.copy_(tok)
+        for t, s0 in zip(self._state(), saved):
+            t.copy_(s0)
         before = _lib.launch_count()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             self._step()
         self.launches_per_step = _lib.launch_count() - before
-        self.pos.copy_(pos), self.lens.copy_(lens), self.token.copy_(tok)
+        for t, s0 in zip(self._state(), saved):
+            t.copy_(s0)
         torch.cuda.synchronize()
         self.graph = g

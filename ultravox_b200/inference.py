@@ -4,8 +4,8 @@ Mirrors ``ultravox/inference/base.py`` (``VoiceOutput``, ``InferenceChunk``, ``I
 ``ultravox/inference/infer.py:20-342`` (``LocalInference``: single / batch / streaming generation, conversation mode with
 KV-cache reuse), same constructor arguments, method names and result types.  What differs, and why:
 
-* decoding is greedy only (the reference's default, ``temperature`` None / 0, ref infer.py:319-328); a positive
-  temperature raises ``NotImplementedError`` instead of silently changing the distribution;
+* decoding follows ref infer.py:319-328: greedy for ``temperature`` None / 0, multinomial sampling at a positive
+  temperature (``do_sample=True``; top-k 50 like HF's ``GenerationConfig`` default), through the graph-captured decode engine;
 * resampling to 16 kHz uses ``scipy.signal.resample_poly`` (``librosa`` - soxr_hq - is not in this image; the reference
   only pins the resulting frame / token counts, ref infer_test.py:112-132);
 * ``infer_stream`` pushes tokens through a queue as the decode loop produces them (one ``InferenceChunk`` per decoded
@@ -188,14 +188,15 @@ class LocalInference(VoiceInference):
     def _generate(self, inputs: Dict[str, torch.Tensor], max_new_tokens: Optional[int] = None,
                   temperature: Optional[float] = None, streamer=None, past_key_values=None,
                   return_dict_in_generate: bool = True):
-        if temperature is not None and temperature > 0:
-            raise NotImplementedError("sampling (temperature > 0) is not built; the reference default is greedy decoding")
+        # ref infer.py:319-328: temperature None -> model default (greedy here), 0 -> greedy, > 0 -> sample
+        do_sample = temperature is not None and temperature > 0
         terminators = [self.tokenizer.eos_token_id]
         extra = getattr(self.tokenizer, "added_tokens_encoder", {})
         if "<|eot_id|>" in extra:
             terminators.append(self.tokenizer.convert_tokens_to_ids("<|eot_id|>"))
         return self.model.generate(**inputs, max_new_tokens=max_new_tokens or MAX_NEW_TOKENS, eos_token_id=terminators,
-                                   streamer=streamer, past_key_values=past_key_values,
+                                   streamer=streamer, past_key_values=past_key_values, do_sample=do_sample,
+                                   temperature=temperature if do_sample else None,
                                    return_dict_in_generate=return_dict_in_generate)
 
     # -- the three entry points ---------------------------------------------------------------------------------------

@@ -288,8 +288,14 @@ class UltravoxModel(nn.Module):
         return self
 
     def _rope_tables(self, need: int):
-        if self._rope is None or self._rope[0].shape[0] < need:
-            n = max(need, 4096)
+        """cos/sin [n, D/2] fp32; grown geometrically (long conversations with KV reuse decode one position at a time - growing
+        to exactly ``need`` would rebuild the table on every step past the initial size)."""
+        have = 0 if self._rope is None else self._rope[0].shape[0]
+        if have < need:
+            cap = int(getattr(self.config.text_config, "max_position_embeddings", 0) or 0)
+            n = max(need, 4096, 2 * have)
+            if cap >= need:
+                n = min(n, cap)
             self._rope = ops.rope_tables(self._inv_freq, n, self.device)
         return self._rope
 
@@ -351,7 +357,7 @@ class UltravoxModel(nn.Module):
         return a
 
     def mel_chunks_from_waveforms(self, audio_waveforms: torch.Tensor, audio_num_frames: torch.Tensor,
-                                  context: int = 3000) -> torch.Tensor:
+                                  context: int = 3000, audio_pad_frames: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Zero-padded waveforms [B, L] (what ``UltravoxProcessor(defer_mel=True)`` hands over) -> time-major mel chunks
         [N, T+2, n_mels] bf16 with guard rows, chunked exactly like ``_chunk_and_pad_audio`` (ref processing :153-215):
         the log-mel (with its per-CLIP max) is computed once per clip on the GPU, then cut into <= ``context``-frame pieces;
@@ -362,6 +368,14 @@ class UltravoxModel(nn.Module):
         n_mels = self.audio_tower.n_mels
         tm = ops.logmel(waves, n_mels, want_f32=False, want_tm=True)            # [B, Tfull+2, n_mels]
         t_full = tm.shape[1] - 2
+        if audio_pad_frames is not None:
+            # collated batches (``DataCollatorForSeq2SeqWithAudio`` over deferred-mel samples): inside its own sample a clip was
+            # zero-padded as a WAVEFORM to ``audio_pad_frames`` frames (those frames hold the log-mel of silence, hf
+            # feature_extraction_whisper.py:296-303); beyond that the reference collator pads the MEL with literal 0.0
+            # (ref ultravox_processing.py:49-52).  Padding content is observable through the conv stem.
+            lim = audio_pad_frames.to(dev).view(-1, 1) + 1                      # +1: guard row
+            keep = torch.arange(t_full + 2, device=dev).view(1, -1) < lim
+            tm = tm * keep.unsqueeze(-1).to(tm.dtype)
         plan, _ = frame_chunks(audio_num_frames.tolist(), context)
         if len(plan) == tm.shape[0] and t_full <= context:
             return tm                                                             # one chunk per clip: nothing to cut
@@ -426,8 +440,7 @@ class UltravoxModel(nn.Module):
                 ops.attention_fused_qkv(qkv, B, S, nq, nkv, hd, hd ** -0.5, True, kv_len, 0, out=att, kv_start=kv_start)
             else:
                 kc, vc = cache.k[li], cache.v[li]            # [B, S_max, Hkv, D]
-                kc[:, past:past + S].copy_(qkv.view(B, S, -1)[:, :, nq * hd:(nq + nkv) * hd].view(B, S, nkv, hd))
-                vc[:, past:past + S].copy_(qkv.view(B, S, -1)[:, :, (nq + nkv) * hd:].view(B, S, nkv, hd))
+                ops.kv_write(qkv, kc, vc, B, S, past, nq, nkv, hd)
                 smax = kc.shape[1]
                 ops.attention(qkv.data_ptr(), kc.data_ptr(), vc.data_ptr(), att, B, nq, nkv, S, past + S, hd,
                               (rs, S * rs, nkv * hd, smax * nkv * hd, nkv * hd, smax * nkv * hd, nq * hd, S * nq * hd),
@@ -490,14 +503,14 @@ class UltravoxModel(nn.Module):
                 audio_batch_size: Optional[torch.Tensor] = None, past_key_values: Optional[KVCache] = None,
                 alt_input_ids=None, alt_attention_mask=None, alt_labels=None, logits_to_keep: int = 0,
                 audio_waveforms: Optional[torch.Tensor] = None, audio_num_frames: Optional[torch.Tensor] = None,
-                **kwargs) -> CausalLMOutputWithPast:
+                audio_pad_frames: Optional[torch.Tensor] = None, **kwargs) -> CausalLMOutputWithPast:
         """Same signature and semantics as the reference ``forward`` (ref :277-352).  ``logits_to_keep=1`` computes
         only the last position's logits (the TTFT path, hf:modeling_llama.py:485-491)."""
         dev = self.device
         input_ids = input_ids.to(dev)
         if inputs_embeds is None:
             if audio_waveforms is not None and len(audio_waveforms) > 0:
-                tm = self.mel_chunks_from_waveforms(audio_waveforms, audio_num_frames)
+                tm = self.mel_chunks_from_waveforms(audio_waveforms, audio_num_frames, audio_pad_frames=audio_pad_frames)
                 inputs_embeds = self._prepare_audio_embeds(input_ids, None, audio_token_start_idx, audio_lens,
                                                            audio_token_len, audio_batch_size, audio_tm=tm)
             elif audio_values is not None and len(audio_values) > 0:
@@ -551,17 +564,34 @@ class UltravoxModel(nn.Module):
                  audio_token_len=None, audio_batch_size=None, max_new_tokens: int = 20, eos_token_id=None,
                  attention_mask: Optional[torch.Tensor] = None, past_key_values: Optional[KVCache] = None,
                  return_dict_in_generate: bool = False, streamer=None, pad_token_id: Optional[int] = None,
-                 repetition_penalty: float = 1.0, temperature: Optional[float] = None, do_sample: bool = False, **kwargs):
-        """Greedy decoding (the reference's default: temperature None/0, ref infer.py:319-328).  Returns prompt ids
-        followed by the new tokens, like ``GenerationMixin.generate`` (ref :398-426).
+                 repetition_penalty: float = 1.0, temperature: Optional[float] = None, do_sample: bool = False,
+                 top_k: Optional[int] = None, top_p: Optional[float] = None, generator: Optional[torch.Generator] = None,
+                 audio_waveforms: Optional[torch.Tensor] = None, audio_num_frames: Optional[torch.Tensor] = None,
+                 audio_pad_frames: Optional[torch.Tensor] = None, use_graph: bool = True, **kwargs):
+        """``GenerationMixin.generate`` for this model (ref :398-426; arguments as ``LocalInference._generate`` passes them, ref
+        infer.py:309-342).  Returns prompt ids followed by the new tokens.
 
+        Greedy when ``do_sample`` is false (the reference's default: temperature None / 0, ref infer.py:319-328); with
+        ``do_sample=True`` tokens are drawn from softmax(logits / temperature) over the ``top_k`` largest logits (HF
+        ``GenerationConfig`` defaults: temperature 1.0, top_k 50), reproducibly for a seeded ``generator``.
         ``past_key_values``: conversation KV reuse (ref infer.py:126-148): the cache already holds the first
         ``past_key_values.length`` positions of ``input_ids`` (earlier turns incl. the reply), so only the new suffix is
         embedded, spliced and prefilled; ``return_dict_in_generate=True`` hands the cache back for the next turn.
         ``streamer``: object with ``put(tensor)`` / ``end()`` (transformers' streamer protocol: the prompt first, then one
-        call per new token).  Rows that have produced an EOS keep emitting ``pad_token_id`` (default: the first EOS id)."""
-        if do_sample or (temperature is not None and temperature > 0):
-            raise NotImplementedError("sampling is not built; greedy decoding only (the reference's default)")
+        call per new token).  Rows that have produced an EOS keep emitting ``pad_token_id`` (default: the first EOS id).
+
+        The prompt is prefilled by the tensor-core path; every later token is one replay of a CUDA graph holding the whole
+        decode step (``engine.DecodeEngine``: GEMV linears, device-side positions / EOS / sequence bookkeeping), so the loop
+        has no per-token host synchronisation unless a streamer asks for the token."""
+        from .engine import DecodeEngine
+        unknown = [k for k, v in kwargs.items() if isinstance(v, torch.Tensor)]
+        if unknown:
+            raise TypeError(f"generate() got unexpected tensor arguments {unknown}")
+        if top_p is not None and float(top_p) < 1.0:
+            raise NotImplementedError("top_p (nucleus) filtering is not built; use top_k")
+        sampling = bool(do_sample) and (temperature is None or float(temperature) > 0)
+        temp = (1.0 if temperature is None else float(temperature)) if sampling else 0.0
+        k_top = (50 if top_k is None else int(top_k)) if sampling else 0
         dev = self.device
         input_ids = input_ids.to(dev)
         B, S = input_ids.shape
@@ -569,7 +599,6 @@ class UltravoxModel(nn.Module):
         # for the whole generation and RoPE positions count real tokens only (hf:generation/utils.py:707-729)
         kv_start = None
         position_ids = None
-        pad = torch.zeros(B, dtype=torch.int64, device=dev)
         if attention_mask is not None and not bool(attention_mask.to(torch.bool).all()):
             am = attention_mask.to(dev)
             kv_start, kv_len = self._pad_bounds(am)
@@ -577,12 +606,14 @@ class UltravoxModel(nn.Module):
                 raise NotImplementedError("generate() needs left padding (or none); right-padded prompts cannot be continued")
             if past_key_values is not None:
                 raise NotImplementedError("conversation KV reuse with padded batches (the reference has none either, infer.py:155)")
-            pad = kv_start.to(torch.int64)
             position_ids = (am.to(torch.int64).cumsum(-1) - 1).clamp_min(0)
+        has_wave = audio_waveforms is not None and len(audio_waveforms) > 0
+        has_mel = audio_values is not None and len(audio_values) > 0
         if past_key_values is None:
             cache = self.new_cache(B, S + max_new_tokens)
             out = self.forward(input_ids, audio_values, inputs_embeds, None, attention_mask, audio_token_start_idx, audio_lens,
-                               audio_token_len, audio_batch_size, cache, logits_to_keep=1, position_ids=position_ids)
+                               audio_token_len, audio_batch_size, cache, logits_to_keep=1, position_ids=position_ids,
+                               audio_waveforms=audio_waveforms, audio_num_frames=audio_num_frames, audio_pad_frames=audio_pad_frames)
         else:
             P = past_key_values.length
             if not (0 <= P < S) or past_key_values.k.shape[1] != B:
@@ -590,46 +621,46 @@ class UltravoxModel(nn.Module):
                                  f"{S} tokens for batch {B} - it must extend the cached prefix")
             cache = past_key_values.grown(S + max_new_tokens)
             if inputs_embeds is None:                       # embed + splice the whole prompt, prefill only the new suffix
-                if audio_values is not None and len(audio_values) > 0:
+                if has_wave:
+                    tm = self.mel_chunks_from_waveforms(audio_waveforms, audio_num_frames, audio_pad_frames=audio_pad_frames)
+                    inputs_embeds = self._prepare_audio_embeds(input_ids, None, audio_token_start_idx, audio_lens,
+                                                               audio_token_len, audio_batch_size, audio_tm=tm)
+                elif has_mel:
                     inputs_embeds = self._prepare_audio_embeds(input_ids, audio_values, audio_token_start_idx, audio_lens,
                                                                audio_token_len, audio_batch_size)
                 else:
                     inputs_embeds = ops.embed_splice(input_ids, self.language_model.model.embed_tokens.weight, None, None)
             out = self.forward(input_ids[:, P:], None, inputs_embeds[:, P:].contiguous(), past_key_values=cache, logits_to_keep=1)
-        eos = set([eos_token_id] if isinstance(eos_token_id, int) else (eos_token_id or []))
-        eos_t = torch.tensor(sorted(eos), device=dev) if eos else None
+        eos = sorted(set([eos_token_id] if isinstance(eos_token_id, int) else (eos_token_id or [])))
         pad_id = pad_token_id if pad_token_id is not None else (min(eos) if eos else 0)
-        seq = [input_ids]
+        eng = DecodeEngine(self, B, cache.capacity, use_graph=use_graph, cache=cache, eos_token_ids=eos, pad_token_id=pad_id,
+                           temperature=temp, top_k=k_top, repetition_penalty=repetition_penalty or 1.0, generator=generator)
         if streamer is not None:
             streamer.put(input_ids)
-        done = torch.zeros(B, dtype=torch.bool, device=dev)
-        penalised = repetition_penalty is not None and float(repetition_penalty) != 1.0
-
-        def pick(logits_bv: torch.Tensor) -> torch.Tensor:
-            if penalised:
-                logits_bv = apply_repetition_penalty(logits_bv, torch.cat(seq, dim=1), float(repetition_penalty))
-            return ops.argmax(logits_bv.contiguous())
-
-        tok = pick(out.logits.view(B, -1))
-        for step in range(max_new_tokens):
-            if eos:
-                tok = torch.where(done, torch.full_like(tok, pad_id), tok)      # finished rows emit padding (HF semantics)
-            seq.append(tok.view(B, 1))
+        tok = eng.begin(input_ids, out.logits.view(B, -1), kv_start)
+        n_new = 1
+        sync_every = 8          # without a streamer the host looks at the all-done flag every few tokens only
+        while True:
             if streamer is not None:
-                streamer.put(tok)
-            if eos:
-                done |= torch.isin(tok, eos_t)
-                if bool(done.all()):
-                    break
-            if step == max_new_tokens - 1:
+                streamer.put(tok.clone())
+            stop = n_new >= max_new_tokens
+            if not stop and eos and (streamer is not None or n_new % sync_every == 0):
+                stop = bool(int(eng.all_done))
+            if stop:
                 break
-            emb = ops.embed_splice(tok.view(B, 1), self.language_model.model.embed_tokens.weight, None, None)
-            positions = (S + step - pad).to(torch.int32) if kv_start is not None else None
-            hidden = self.llama_hidden(emb, cache, None, kv_start, positions)
-            tok = pick(ops.lm_head(hidden[:, -1, :], self.language_model.lm_head.weight))
+            eng.step()
+            n_new += 1
         if streamer is not None:
             streamer.end()
-        sequences = torch.cat(seq, dim=1)
+        new = eng.seq[:, S:S + n_new]
+        if eos and streamer is None and n_new > 1:
+            # the loop may have run a few tokens past the step at which every row had finished: HF stops right there
+            hit = torch.isin(new, eng.eos)
+            first = torch.where(hit.any(-1), hit.to(torch.int32).argmax(-1), torch.full((B,), n_new, device=dev))
+            n_new = min(n_new, int(first.max()) + 1)
+            new = new[:, :n_new]
+        cache.length = S + n_new - 1                        # the last new token has not been fed yet
+        sequences = torch.cat([input_ids, new], dim=1)
         return GenerateOutput(sequences, cache) if return_dict_in_generate else sequences
 
 

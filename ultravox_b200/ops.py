@@ -452,3 +452,41 @@ def kv_append(qkv: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, p
 
 def add_i32_(a: torch.Tensor, b: Optional[torch.Tensor], delta: int) -> None:
     check(lib().uvx_add_i32(a.data_ptr(), _p(b), a.numel(), delta, _stream()), "uvx_add_i32")
+
+
+def kv_write(qkv: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, B: int, S: int, past: int, Hq: int, Hkv: int,
+             D: int) -> None:
+    """Prefill rows [B*S, (Hq+2Hkv)*D] -> k_cache / v_cache [B, S_max, Hkv, D] at positions past .. past+S-1."""
+    check(lib().uvx_kv_write(qkv.data_ptr(), qkv.stride(0), Hq * D, (Hq + Hkv) * D, Hkv * D, k_cache.data_ptr(), v_cache.data_ptr(),
+                             k_cache.stride(0), B, S, past, _stream()), "uvx_kv_write")
+
+
+def repetition_penalty_(logits: torch.Tensor, seq: torch.Tensor, cur_len: torch.Tensor, penalty: float,
+                        scratch: torch.Tensor) -> torch.Tensor:
+    _cuda(logits, torch.float32, "logits"), _cuda(seq, torch.int64, "seq"), _cuda(cur_len, torch.int32, "cur_len")
+    B, V = logits.shape
+    check(lib().uvx_repetition_penalty(logits.data_ptr(), B, V, seq.data_ptr(), seq.stride(0), cur_len.data_ptr(), float(penalty),
+                                       scratch.data_ptr(), _stream()), "uvx_repetition_penalty")
+    return logits
+
+
+def sample(logits: torch.Tensor, temperature: float, top_k: int, u: torch.Tensor, step_idx: Optional[torch.Tensor] = None,
+           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """logits [B, V] fp32, u [steps, B] (or [B]) uniforms in [0, 1) -> sampled ids [B] int64."""
+    _cuda(logits, torch.float32, "logits"), _cuda(u, torch.float32, "u")
+    B, V = logits.shape
+    if out is None:
+        out = torch.empty(B, dtype=torch.int64, device=logits.device)
+    check(lib().uvx_sample(logits.data_ptr(), B, V, float(temperature), int(top_k or 0), u.data_ptr(), _p(step_idx),
+                           u.stride(0) if u.dim() == 2 else 0, out.data_ptr(), _stream()), "uvx_sample")
+    return out
+
+
+def token_finish(tok: torch.Tensor, done: torch.Tensor, eos_ids: Optional[torch.Tensor], pad_id: int, seq: Optional[torch.Tensor],
+                 cur_len: torch.Tensor, step_idx: Optional[torch.Tensor] = None, bumps: tuple = (),
+                 all_done: Optional[torch.Tensor] = None) -> None:
+    _cuda(tok, torch.int64, "tok"), _cuda(done, torch.int32, "done")
+    b = list(bumps) + [None] * (3 - len(bumps))
+    check(lib().uvx_token_finish(tok.data_ptr(), done.data_ptr(), _p(eos_ids), 0 if eos_ids is None else eos_ids.numel(), int(pad_id),
+                                 _p(seq), seq.stride(0) if seq is not None else 0, cur_len.data_ptr(), _p(step_idx), _p(b[0]), _p(b[1]),
+                                 _p(b[2]), _p(all_done), tok.numel(), _stream()), "uvx_token_finish")

@@ -68,6 +68,12 @@ class DataCollatorForSeq2SeqWithAudio(transformers.DataCollatorForSeq2Seq):
     def __call__(self, features, *args, **kwargs):
         def flat(key):
             return [x for f in features for x in f.pop(key, [])]
+        # deferred-mel samples (``UltravoxProcessor(defer_mel=True)``, the mode that is safe in forked DataLoader workers) carry
+        # zero-padded waveforms instead of a mel: clips are flattened across samples and padded (as waveforms, to a multiple
+        # of the hop) to the batch-longest; ``audio_pad_frames`` remembers each clip's own padded width so the model can
+        # reproduce the reference's padding content frame for frame (see UltravoxModel.mel_chunks_from_waveforms)
+        waves = [w for f in features for w in f.pop("audio_waveforms", [])]
+        n_frames = [n for f in features for n in f.pop("audio_num_frames", [])]
         vals, lens = flat("audio_values"), flat("audio_lens")
         tok_len, starts = flat("audio_token_len"), flat("audio_token_start_idx")
         alt = None
@@ -79,12 +85,20 @@ class DataCollatorForSeq2SeqWithAudio(transformers.DataCollatorForSeq2Seq):
             ab = super().__call__(alt, *args, **kwargs)
             for k in ("input_ids", "attention_mask", "labels"):
                 batch["alt_" + k] = ab[k]
-        if vals and len(vals) > 0 and len(vals[0]) > 0:
+        has_mel = bool(vals) and len(vals[0]) > 0
+        if has_mel or waves:
             batch["audio_token_start_idx"] = torch.stack(starts)
             batch["audio_lens"] = torch.stack(lens)
             batch["audio_token_len"] = torch.stack(tok_len)
-            width = max(v.shape[-1] for v in vals)
-            batch["audio_values"] = torch.stack([F.pad(v, (0, width - v.shape[-1])) for v in vals])
+            if has_mel:
+                width = max(v.shape[-1] for v in vals)
+                batch["audio_values"] = torch.stack([F.pad(v, (0, width - v.shape[-1])) for v in vals])
+            else:
+                waves = [torch.as_tensor(w) for w in waves]
+                width = max(w.shape[-1] for w in waves)
+                batch["audio_waveforms"] = torch.stack([F.pad(w, (0, width - w.shape[-1])) for w in waves])
+                batch["audio_num_frames"] = torch.stack([torch.as_tensor(n) for n in n_frames]).to(torch.int64)
+                batch["audio_pad_frames"] = torch.tensor([w.shape[-1] // 160 for w in waves], dtype=torch.int64)
             if self.tokenizer.padding_side == "left":
                 own = torch.LongTensor([f["input_ids"].shape[-1] for f in features])
                 shift = (batch["input_ids"].shape[-1] - own).repeat_interleave(

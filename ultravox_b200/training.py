@@ -59,7 +59,8 @@ class AdapterTrainer:
     # -- forward + backward --------------------------------------------------------------------------
     def forward_backward(self, input_ids, audio_values, audio_token_start_idx, audio_lens, audio_token_len,
                          audio_batch_size, labels, audio_tm: Optional[torch.Tensor] = None, alt_input_ids=None,
-                         alt_labels=None, alt_attention_mask=None) -> torch.Tensor:
+                         alt_labels=None, alt_attention_mask=None, attention_mask=None, audio_waveforms=None,
+                         audio_num_frames=None, audio_pad_frames=None, **_) -> torch.Tensor:
         """Accumulates d(loss)/d(projector) into ``self.grad`` (zeroed first) and returns the loss (device scalar).
         Unpadded batches of equal length (the cfg3 synthetic workload); labels follow the HF convention."""
         m, cfg = self.model, self.model.config
@@ -73,6 +74,11 @@ class AdapterTrainer:
         self.grad.zero_()
 
         # ---- forward: audio tower (frozen, nothing kept) + projector (kept)
+        if attention_mask is not None and not bool(torch.as_tensor(attention_mask).to(torch.bool).all()):
+            raise NotImplementedError("AdapterTrainer.forward_backward takes unpadded batches of equal length (cfg3 workload); "
+                                      "use model(**batch).loss.backward() for padded batches")
+        if audio_tm is None and audio_waveforms is not None:
+            audio_tm = m.mel_chunks_from_waveforms(audio_waveforms, audio_num_frames, audio_pad_frames=audio_pad_frames)
         if audio_tm is None:
             audio_tm = ops.mel_to_timemajor(audio_values.to(dev, torch.float32))
         enc = m.encode_audio(audio_tm, audio_lens).clone()                 # [N, T2, d]
