@@ -267,3 +267,95 @@ def test_kl_training_step_and_forward_loss_match_oracle():
     out = model(audio_values=mel, alt_input_ids=alt_ids, alt_labels=alt_labels, **{k: v for k, v in batch.items()})
     model.eval()
     assert abs(float(out.loss) - float(loss)) < 1e-2 * max(1e-3, abs(float(loss))) + 1e-4
+
+
+def test_autograd_door_matches_adapter_trainer_and_hf_trainer_usage():
+    """VERDICT r1 item 5 (north_star: autograd.Functions): the HF-Trainer door - ``model.train(); out = model(**batch);
+    out.loss.backward()`` - fills ``multi_modal_projector.*.grad`` with the same gradients the explicit AdapterTrainer computes
+    (same kernels, fp32 accumulation, one bf16 rounding at the autograd boundary), loss scaling included; right-padded batches
+    go through the same path."""
+    from ultravox_b200 import ops
+    from ultravox_b200.training import AdapterTrainer
+    cfg, model, padded, batch = _setup([16000 * 2, 16000 + 77])
+    mel = ops.logmel(torch.from_numpy(padded).cuda(), cfg.audio_config.num_mel_bins)
+    tr = AdapterTrainer(model, lr=1e-3)
+    loss_t = float(tr.forward_backward(audio_values=mel, **batch))
+    model.train()
+    model.zero_grad(set_to_none=True)
+    out = model(audio_values=mel, **{k: v.cuda() for k, v in batch.items()})
+    assert out.loss.requires_grad and out.logits.shape == (2, batch["input_ids"].shape[1], cfg.vocab_size) and not out.logits.requires_grad
+    assert abs(float(out.loss) - loss_t) < 1e-5 * max(1.0, abs(loss_t))
+    (out.loss * 0.5).backward()                           # gradient accumulation scales the loss (hf Trainer.training_step)
+    pj = model.multi_modal_projector
+    for n in ("ln_pre", "linear_1", "ln_mid", "linear_2"):
+        g = getattr(pj, n).weight.grad
+        assert g is not None and g.dtype == BF and g.shape == getattr(pj, n).weight.shape
+        want = (0.5 * tr.grad_view(n)).to(BF)
+        assert rel(g, want) < 1.5e-2, (n, rel(g, want))
+    for name, p_ in model.named_parameters():
+        if not name.startswith("multi_modal_projector."):
+            assert p_.grad is None, name
+    # eval / no_grad: the plain path, no graph
+    model.eval()
+    with torch.no_grad():
+        out2 = model(audio_values=mel, **{k: v.cuda() for k, v in batch.items()})
+    assert not out2.loss.requires_grad and abs(float(out2.loss) - loss_t) < 2e-3 * max(1.0, abs(loss_t))
+    # right-padded batch (training collator): the padded tail changes nothing for the real rows' loss
+    model.train()
+    S = batch["input_ids"].shape[1]
+    pad = 7
+    ids_p = torch.cat([batch["input_ids"], torch.zeros(2, pad, dtype=torch.int64)], 1)
+    lab_p = torch.cat([batch["labels"], torch.full((2, pad), -100)], 1)
+    am = torch.cat([torch.ones(2, S, dtype=torch.int64), torch.zeros(2, pad, dtype=torch.int64)], 1)
+    model.zero_grad(set_to_none=True)
+    kw = {k: v.cuda() for k, v in batch.items() if k not in ("input_ids", "labels")}
+    out3 = model(ids_p.cuda(), audio_values=mel, labels=lab_p.cuda(), attention_mask=am.cuda(), **kw)
+    assert abs(float(out3.loss) - loss_t) < 2e-3 * max(1.0, abs(loss_t))
+    out3.loss.backward()
+    assert rel(pj.linear_2.weight.grad, tr.grad_view("linear_2").to(BF)) < 2e-2
+
+
+def test_save_and_from_pretrained_round_trip(tmp_path):
+    """ref:ultravox/model/ultravox_model_test.py:71-111 style: save_pretrained writes config + the diff checkpoint (projector
+    only), from_pretrained restores it on top of separately loaded towers; resize_token_embeddings / merge_and_unload surface."""
+    import os
+    from safetensors.torch import load_file, save_file
+    from ultravox_b200.config import preset
+    from ultravox_b200.model import UltravoxModel
+    cfg = preset("micro")
+    model = UltravoxModel(cfg, device="cuda").init_random_(seed=3)
+    d = tmp_path / "ckpt"
+    model.save_pretrained(str(d))
+    saved = load_file(os.path.join(d, "model.safetensors"))
+    assert set(saved) == {k for k in model.state_dict() if k.startswith("multi_modal_projector.")}
+    # towers from their "own checkpoints": an LLM directory and a Whisper directory named by the config ids
+    llm_dir, enc_dir = tmp_path / "llm", tmp_path / "whisper"
+    os.makedirs(llm_dir), os.makedirs(enc_dir)
+    sd = model.state_dict()
+    save_file({k[len("language_model."):]: v.cpu().contiguous().clone() for k, v in sd.items() if k.startswith("language_model.")},
+              str(llm_dir / "model.safetensors"))
+    save_file({"model.encoder." + k[len("audio_tower."):]: v.cpu().contiguous().clone() for k, v in sd.items() if k.startswith("audio_tower.")},
+              str(enc_dir / "model.safetensors"))
+    cfg2 = UltravoxModel.config_class.from_pretrained(str(d))
+    cfg2.text_model_id, cfg2.audio_model_id = str(llm_dir), str(enc_dir)
+    back = UltravoxModel.from_pretrained(str(d), config=cfg2)
+    for k, v in model.state_dict().items():
+        assert torch.equal(back.state_dict()[k], v), k
+    assert {k for k in back.keep_params} == set(saved)                       # towers' keys are not re-saved
+    assert set(back.diff_state_dict()) == set(saved)
+    # a diff checkpoint alone loads into a model (strict): the missing tower keys are ignorable, typos are not
+    m3 = UltravoxModel(cfg, device="cuda")
+    res = m3.load_state_dict(saved)
+    assert not res.missing_keys and not res.unexpected_keys
+    with pytest.raises(RuntimeError):
+        m3.load_state_dict({"multi_modal_projector.linear_3.weight": torch.zeros(1)})
+    # resize_token_embeddings keeps old rows, updates the three vocab fields, and forward still runs
+    V0 = cfg.vocab_size
+    emb = back.resize_token_embeddings(V0 + 3, pad_to_multiple_of=64)
+    V1 = -(-(V0 + 3) // 64) * 64
+    assert emb.num_embeddings == V1 == back.config.vocab_size == back.config.text_config.vocab_size == back.vocab_size
+    assert torch.equal(back.get_input_embeddings().weight[:V0], model.get_input_embeddings().weight)
+    out = back(torch.randint(0, V1, (1, 9)).cuda())
+    assert out.logits.shape == (1, 9, V1) and bool(torch.isfinite(out.logits).all())
+    back.merge_and_unload()
+    assert not hasattr(back.config, "text_model_lora_config")

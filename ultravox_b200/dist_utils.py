@@ -27,6 +27,15 @@ def shard_indices(n_items: int, shard: int, n_shards: int) -> list[int]:
     return [i for i in range(n_items) if i % n_shards == shard]
 
 
+def allreduce_sum_(flat: torch.Tensor, group=None) -> float:
+    """In-place SUM over the data-parallel group; returns 1 / world for the caller to fold into its next kernel (the optimizer
+    step reads the gradient anyway: a separate x 1/world pass over the flat buffer is a wasted HBM round trip)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        return 1.0 / dist.get_world_size(group)
+    return 1.0
+
+
 def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
     """In-place mean over the data-parallel group (sum all-reduce, then 1/world)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

@@ -45,6 +45,18 @@ class _P(nn.Module):
             self.bias = None
 
 
+class _Embed(_P):
+    """Token-embedding leaf: ``weight`` plus the two attributes callers read off ``nn.Embedding`` (ref :144-156)."""
+
+    @property
+    def num_embeddings(self) -> int:
+        return int(self.weight.shape[0])
+
+    @property
+    def embedding_dim(self) -> int:
+        return int(self.weight.shape[1])
+
+
 def _empty(*shape, device, dtype=BF16):
     return torch.empty(*shape, device=device, dtype=dtype)
 
@@ -145,7 +157,7 @@ class _LlamaLayer(nn.Module):
 class _LlamaInner(nn.Module):
     def __init__(self, tc, hd, device):
         super().__init__()
-        self.embed_tokens = _P(_empty(tc.vocab_size, tc.hidden_size, device=device))
+        self.embed_tokens = _Embed(_empty(tc.vocab_size, tc.hidden_size, device=device))
         self.layers = nn.ModuleList([_LlamaLayer(tc, hd, device) for _ in range(tc.num_hidden_layers)])
         self.norm = _P(_empty(tc.hidden_size, device=device))
 
@@ -157,12 +169,20 @@ class LanguageModel(nn.Module):
         self.model = _LlamaInner(tc, self.head_dim, device)
         self.tied = bool(getattr(tc, "tie_word_embeddings", False))
         if self.tied:
-            self.lm_head = _P(self.model.embed_tokens.weight.data)
+            self.lm_head = _Embed(self.model.embed_tokens.weight.data)
         else:
-            self.lm_head = _P(_empty(tc.vocab_size, tc.hidden_size, device=device))
+            self.lm_head = _Embed(_empty(tc.vocab_size, tc.hidden_size, device=device))
 
     def get_input_embeddings(self):
         return self.model.embed_tokens
+
+    def get_output_embeddings(self):
+        return self.lm_head
+
+    def tie_weights(self):
+        """Tied checkpoints (Llama-3.2-1B): lm_head shares the embedding storage (hf:modeling_utils.py tie_weights)."""
+        if self.tied:
+            self.lm_head.weight = nn.Parameter(self.model.embed_tokens.weight.data, requires_grad=False)
 
 
 @dataclasses.dataclass
@@ -227,8 +247,146 @@ class UltravoxModel(nn.Module):
     def get_input_embeddings(self):
         return self.language_model.get_input_embeddings()
 
+    def set_input_embeddings(self, value):
+        """ref :115-116.  ``value``: anything with a ``weight`` [V, D] (an ``nn.Embedding`` in the reference)."""
+        w = value.weight if hasattr(value, "weight") else value
+        emb = self.language_model.model.embed_tokens
+        emb.weight = nn.Parameter(w.detach().to(self.device, BF16).contiguous(), requires_grad=False)
+        self.language_model.tie_weights()
+
+    def get_output_embeddings(self):
+        return self.language_model.get_output_embeddings()
+
+    def set_output_embeddings(self, new_embeddings):
+        w = new_embeddings.weight if hasattr(new_embeddings, "weight") else new_embeddings
+        self.language_model.lm_head.weight = nn.Parameter(w.detach().to(self.device, BF16).contiguous(), requires_grad=False)
+
+    def get_decoder(self):
+        return self.language_model.model
+
+    def tie_weights(self, **_):
+        return self.language_model.tie_weights()
+
     def set_loss_config(self, loss_config: LossConfig):
         self.loss_config = loss_config
+
+    @torch.no_grad()
+    def resize_token_embeddings(self, new_num_tokens: Optional[int] = None, pad_to_multiple_of: Optional[int] = None):
+        """ref :144-156 (-> hf:modeling_utils.py resize_token_embeddings): grows / shrinks ``embed_tokens`` and ``lm_head`` and
+        updates the three vocab-size fields.  New rows are set to the mean of the existing rows (HF's ``mean_resizing`` default
+        draws them from a Gaussian around that mean)."""
+        emb = self.language_model.model.embed_tokens
+        old = emb.num_embeddings
+        if new_num_tokens is None:
+            return emb
+        if pad_to_multiple_of:
+            new_num_tokens = -(-new_num_tokens // pad_to_multiple_of) * pad_to_multiple_of
+
+        def resized(w):
+            out = torch.empty(new_num_tokens, w.shape[1], dtype=w.dtype, device=w.device)
+            n = min(old, new_num_tokens)
+            out[:n] = w[:n]
+            if new_num_tokens > old:
+                out[old:] = w.float().mean(0, keepdim=True).to(w.dtype)
+            return out
+
+        emb.weight = nn.Parameter(resized(emb.weight.data), requires_grad=False)
+        if self.language_model.tied:
+            self.language_model.tie_weights()
+        else:
+            head = self.language_model.lm_head
+            head.weight = nn.Parameter(resized(head.weight.data), requires_grad=False)
+        self.config.text_config.vocab_size = self.config.vocab_size = self.vocab_size = new_num_tokens
+        self._wT = None                     # transposed lm_head of the training path is rebuilt on demand
+        return emb
+
+    def merge_and_unload(self):
+        """ref :528-559.  LoRA adapters are folded into the fused base weights when a checkpoint is LOADED (``lora.py``), so
+        there is nothing left to merge; what remains is the reference's bookkeeping: the merged towers must be saved with the
+        adapter checkpoint (``keep_params``), their hub ids no longer apply, and the LoRA configs leave the config."""
+        for comp, id_attr, cfg_attr in (("language_model", "text_model_id", "text_model_lora_config"),
+                                        ("audio_tower", "audio_model_id", "audio_model_lora_config")):
+            lc = getattr(self.config, cfg_attr, None) or {}
+            if hasattr(self, comp) and int(lc.get("r", 0) or 0) > 0:
+                setattr(self.config, id_attr, None)
+                self.keep_params.update(f"{comp}.{n}" for n, _ in getattr(self, comp).named_parameters())
+        for cfg_attr in ("text_model_lora_config", "audio_model_lora_config"):
+            if hasattr(self.config, cfg_attr):
+                delattr(self.config, cfg_attr)
+
+    def print_trainable_parameters(self):
+        tr = sum(p.numel() for p in self.parameters() if p.requires_grad)
+        tot = sum(p.numel() for p in self.parameters())
+        print(f"trainable params: {tr:,d} || all params: {tot:,d} || trainable%: {100 * tr / max(tot, 1):.4f}")
+
+    # -- checkpoints (ref :103-110, :565-594) ---------------------------------------------------------
+    def save_pretrained(self, save_directory, state_dict=None, safe_serialization: bool = True, **kwargs):
+        """Writes ``config.json`` + the DIFF checkpoint (trainable and explicitly kept parameters only, ref :565-591) as
+        ``model.safetensors`` - the layout ``from_pretrained`` (here and in the reference) reads back."""
+        import os
+        os.makedirs(save_directory, exist_ok=True)
+        self.config.save_pretrained(save_directory)
+        sd = {k: v.detach().to("cpu").contiguous().clone() for k, v in self.diff_state_dict(state_dict).items()}
+        if safe_serialization:
+            from safetensors.torch import save_file
+            save_file(sd, os.path.join(save_directory, "model.safetensors"), metadata={"format": "pt"})
+        else:
+            torch.save(sd, os.path.join(save_directory, "pytorch_model.bin"))
+
+    @staticmethod
+    def _read_checkpoint_dir(path: str) -> dict:
+        """All tensors of a HF-style checkpoint directory: single / sharded safetensors or ``pytorch_model.bin``."""
+        import glob
+        import json
+        import os
+        from safetensors.torch import load_file
+        idx = os.path.join(path, "model.safetensors.index.json")
+        files = []
+        if os.path.exists(idx):
+            files = sorted({os.path.join(path, f) for f in json.load(open(idx))["weight_map"].values()})
+        elif os.path.exists(os.path.join(path, "model.safetensors")):
+            files = [os.path.join(path, "model.safetensors")]
+        else:
+            files = sorted(glob.glob(os.path.join(path, "*.safetensors")))
+        out = {}
+        for f in files:
+            out.update(load_file(f))
+        if not files and os.path.exists(os.path.join(path, "pytorch_model.bin")):
+            out = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu", weights_only=True)
+        return out
+
+    @staticmethod
+    def _resolve_dir(model_id: str) -> str:
+        import os
+        if os.path.isdir(model_id):
+            return model_id
+        from huggingface_hub import snapshot_download
+        return snapshot_download(model_id, allow_patterns=["*.safetensors", "*.json", "*.bin"])
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, *model_args, config: Optional[UltravoxConfig] = None, device="cuda",
+                        **kwargs):
+        """ref :103-110 -> ``PreTrainedModel.from_pretrained``: (1) the config, (2) the base towers named by ``text_model_id`` /
+        ``audio_model_id`` (their own checkpoints, ref :440-526), (3) the diff checkpoint saved by ``save_pretrained`` (projector,
+        merged / LoRA tower weights) on top, missing tower keys allowed (``_keys_to_ignore_on_load_missing``), (4) derived
+        device buffers.  ``torch_dtype`` / ``device_map`` style kwargs of the HF API are accepted and ignored (bf16, one GPU)."""
+        path = cls._resolve_dir(str(pretrained_model_name_or_path))
+        cfg = config or UltravoxConfig.from_pretrained(path)
+        model = cls(cfg, device=device)
+        if cfg.text_model_id:
+            base = cls._read_checkpoint_dir(cls._resolve_dir(cfg.text_model_id))
+            model.load_state_dict({"language_model." + k: v for k, v in base.items()}, strict=False, _track=False)
+        if cfg.audio_model_id and hasattr(model, "audio_tower"):
+            base = cls._read_checkpoint_dir(cls._resolve_dir(cfg.audio_model_id))
+            enc = {}
+            for k, v in base.items():                      # WhisperModel / WhisperForConditionalGeneration -> encoder only
+                for pre in ("model.encoder.", "encoder."):
+                    if k.startswith(pre):
+                        enc["audio_tower." + k[len(pre):]] = v
+            model.load_state_dict(enc, strict=False, _track=False)
+        model.load_state_dict(cls._read_checkpoint_dir(path), strict=True)
+        model.prepare()
+        return model.eval()
 
     @property
     def device(self):
@@ -459,15 +617,33 @@ class UltravoxModel(nn.Module):
             cache.length = past + S
         return x.view(B, S, Dm)
 
-    def load_state_dict(self, state_dict, strict: bool = True, **kwargs):
-        """Accepts the reference's checkpoints as they are saved: plain names, or PEFT-wrapped names with LoRA adapters on the
-        encoder / LLM projections (ref training/model_types.py:300-333) - the adapters are folded into the base weights."""
+    def load_state_dict(self, state_dict, strict: bool = True, _track: bool = True, **kwargs):
+        """Accepts the reference's checkpoints as they are saved: the diff checkpoint of ``save_pretrained`` (projector + kept
+        keys only - the towers' keys may be missing, ``_keys_to_ignore_on_load_missing``), plain full state dicts, or
+        PEFT-wrapped names with LoRA adapters on the encoder / LLM projections (ref training/model_types.py:300-333) - the
+        adapters are folded into the base weights.  Loaded keys are remembered in ``keep_params`` like the reference's pre-load
+        hook does (ref :593-594), so ``diff_state_dict`` / ``save_pretrained`` write them back out."""
+        import re
         from . import lora
         if lora.has_lora_keys(state_dict):
-            scaling = {"audio_tower": lora.lora_scaling(self.config.audio_model_lora_config),
-                       "language_model": lora.lora_scaling(self.config.text_model_lora_config)}
+            scaling = {"audio_tower": lora.lora_scaling(getattr(self.config, "audio_model_lora_config", None)),
+                       "language_model": lora.lora_scaling(getattr(self.config, "text_model_lora_config", None))}
             state_dict = lora.merge_lora_state_dict(state_dict, scaling)
-        return super().load_state_dict(state_dict, strict=strict, **kwargs)
+        if self.language_model.tied and "language_model.lm_head.weight" not in state_dict \
+                and "language_model.model.embed_tokens.weight" in state_dict:
+            state_dict = dict(state_dict)
+            state_dict["language_model.lm_head.weight"] = state_dict["language_model.model.embed_tokens.weight"]
+        if _track:
+            self.keep_params.update(state_dict.keys())
+        res = super().load_state_dict(state_dict, strict=False, **kwargs)
+        ignorable = [re.compile(p.replace(".", r"\.").replace("*", ".*")) for p in self._keys_to_ignore_on_load_missing]
+        missing = [k for k in res.missing_keys if not any(r.match(k) for r in ignorable)]
+        if strict and (missing or res.unexpected_keys):
+            raise RuntimeError(f"Error(s) in loading state_dict for UltravoxModel: missing keys {missing}, "
+                               f"unexpected keys {list(res.unexpected_keys)}")
+        res.missing_keys[:] = missing
+        self._wT = None
+        return res
 
     def new_cache(self, batch: int, max_len: int) -> KVCache:
         tc, lm = self.config.text_config, self.language_model
@@ -508,7 +684,20 @@ class UltravoxModel(nn.Module):
         only the last position's logits (the TTFT path, hf:modeling_llama.py:485-491)."""
         dev = self.device
         input_ids = input_ids.to(dev)
-        if inputs_embeds is None:
+        has_audio = (audio_waveforms is not None and len(audio_waveforms) > 0) or (audio_values is not None and len(audio_values) > 0)
+        # the training door (HF Trainer: model(**batch) -> loss.backward(), ref train.py:250-330): gradients are enabled, a
+        # projector parameter wants one and the loss depends on it -> the forward is built from autograd.Functions
+        grad_path = (torch.is_grad_enabled() and labels is not None and inputs_embeds is None and has_audio
+                     and past_key_values is None and hasattr(self, "multi_modal_projector")
+                     and any(p.requires_grad for p in self.multi_modal_projector.parameters()))
+        if grad_path:
+            with torch.no_grad():
+                if audio_waveforms is not None and len(audio_waveforms) > 0:
+                    tm = self.mel_chunks_from_waveforms(audio_waveforms, audio_num_frames, audio_pad_frames=audio_pad_frames)
+                else:
+                    tm = ops.mel_to_timemajor(audio_values.to(dev, torch.float32))
+                inputs_embeds = self.encode_audio(tm, audio_lens).clone()       # encoder output; the towers are frozen
+        elif inputs_embeds is None:
             if audio_waveforms is not None and len(audio_waveforms) > 0:
                 tm = self.mel_chunks_from_waveforms(audio_waveforms, audio_num_frames, audio_pad_frames=audio_pad_frames)
                 inputs_embeds = self._prepare_audio_embeds(input_ids, None, audio_token_start_idx, audio_lens,
@@ -522,6 +711,9 @@ class UltravoxModel(nn.Module):
             inputs_embeds = inputs_embeds.clone()
         if self.training and self.loss_config.loss_function not in (LossFunction.CrossEntropy, LossFunction.KL_Divergence):
             raise ValueError(f"Unsupported loss function: {self.loss_config.loss_function}")
+        if grad_path:
+            return self._forward_with_grad(input_ids, inputs_embeds, labels, attention_mask, audio_token_start_idx,
+                                           audio_token_len, audio_batch_size, alt_input_ids, alt_labels, logits_to_keep)
         kv_start, kv_len = self._pad_bounds(attention_mask.to(dev) if attention_mask is not None else None)
         position_ids = kwargs.get("position_ids")
         positions = position_ids.to(dev, torch.int32).reshape(-1).contiguous() if position_ids is not None else None
@@ -539,6 +731,38 @@ class UltravoxModel(nn.Module):
         if self.training and self.loss_config.loss_function == LossFunction.KL_Divergence:
             loss = self._compute_kl_loss(logits, labels, alt_input_ids, alt_labels)
         return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=past_key_values)
+
+    def _forward_with_grad(self, input_ids, enc, labels, attention_mask, audio_token_start_idx, audio_token_len,
+                           audio_batch_size, alt_input_ids, alt_labels, logits_to_keep) -> CausalLMOutputWithPast:
+        """``forward`` for training: loss carries a grad_fn through ProjectorFn / SpliceFn / LlamaStackFn / HeadLossFn
+        (``autograd.py``), so ``out.loss.backward()`` fills ``multi_modal_projector.*.grad``; logits are returned like the
+        reference does (all rows, fp32, detached - computed outside the graph)."""
+        from . import autograd as ag
+        dev = self.device
+        assert audio_token_start_idx is not None and audio_token_len is not None and audio_batch_size is not None, \
+            "inputs_embeds/audio_values/audio_token_start_idx/audio_token_len/audio_lens/audio_batch_size must be provided."
+        kv_start, kv_len = self._pad_bounds(attention_mask.to(dev) if attention_mask is not None else None)
+        if kv_start is not None:
+            raise NotImplementedError("training batches are right-padded (ref ultravox_processing.py:43-51); left padding is for generation")
+        if self.training and self.loss_config.loss_function == LossFunction.KL_Divergence and (alt_input_ids is None or alt_labels is None):
+            raise ValueError("labels must be provided")
+        kl = self.training and self.loss_config.loss_function == LossFunction.KL_Divergence
+        prev = self.loss_config
+        if not kl and prev.loss_function != LossFunction.CrossEntropy:
+            self.loss_config = LossConfig()               # eval-mode forward with grad enabled: CE, like the reference (:335-338)
+        try:
+            loss, hidden = ag.adapter_loss(self, input_ids, enc, (audio_token_start_idx, audio_token_len, audio_batch_size),
+                                           labels.to(dev), alt_input_ids if kl else None, alt_labels if kl else None, kv_len)
+        finally:
+            self.loss_config = prev
+        B, S, Dm = hidden.shape
+        with torch.no_grad():
+            lm_w = self.language_model.lm_head.weight
+            if logits_to_keep == 1:
+                logits = ops.lm_head(hidden[:, -1, :], lm_w).view(B, 1, -1)
+            else:
+                logits = ops.linear(hidden.reshape(B * S, Dm), lm_w, out_dtype=torch.float32).view(B, S, -1)
+        return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=None)
 
     def _compute_kl_loss(self, logits: torch.Tensor, labels, alt_input_ids, alt_labels) -> torch.Tensor:
         """ref :202-257: teacher = this LLM on the text-only ``alt_*`` twin (no grad), KL at ``kl_temperature`` on the
