@@ -317,10 +317,17 @@ def roofline_pass(model, eng, peaks, reps=20):
             M, N, K, osz, has_r = shape_of(c)
             byt += N * K * 2 + M * K * 2 + M * N * osz + (M * N * 2 if has_r else 0)
             fl += 2.0 * M * N * K
+        # manual capture on a side stream: `with torch.cuda.graph()` empties the allocator cache first, which would unmap the
+        # (already freed, still cached) activation buffers the recorded calls point at
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            g.capture_begin()
             for _, orig, a, k in sel:
                 orig(*a, **k)
+            g.capture_end()
+        torch.cuda.current_stream().wait_stream(side)
         for _ in range(3):
             g.replay()
         torch.cuda.synchronize()
@@ -486,11 +493,20 @@ def main():
                 "ttft_ms_p50_cuda_events": per_ev[len(per_ev) // 2], "ttft_iters": n_tt,
                 "gpu_launches": eng.launches_per_step * K, "launches_per_step": eng.launches_per_step,
                 "clocks": clocks, "token_check": tokens_ok}
+        state = mel_used = None
+        if not args.no_cpu_baseline:
+            try:      # material for the CPU leg, fetched before anything else touches the allocator
+                from ultravox_b200 import ops
+                from oracle import model as om
+                mel_used = ops.logmel(devw[0], model.audio_tower.n_mels).cpu().to(torch.bfloat16).float()
+                state = om.state_dict_fp32(model)
+            except Exception as e:
+                line["cpu_baseline"] = {"error": repr(e)[:300]}
         if not args.no_roofline:
             try:
                 line["roofline"] = roofline_pass(model, eng, peaks)
             except Exception as e:  # never lose the headline number to the diagnostic pass
-                line["roofline"] = {"error": repr(e)}
+                line["roofline"] = {"error": repr(e)[:300]}
         if world == 1 and not args.no_library_baseline:
             try:
                 sys.path.insert(0, os.path.join(ROOT, "scripts"))
@@ -498,13 +514,9 @@ def main():
                 line["gpu_library_baseline"] = hf_gpu_baseline.run(cfg, wl, dev, iters=20, warmup=3)
             except Exception as e:
                 line["gpu_library_baseline"] = {"error": repr(e)[:300]}
-        if not args.no_cpu_baseline:
+        if state is not None:
             # full-depth fp32 CPU oracle on THIS model's weights: the cpu_baseline sample and the check of the GPU output in one
             try:
-                from ultravox_b200 import ops
-                from oracle import model as om
-                mel_used = ops.logmel(devw[0], model.audio_tower.n_mels).cpu().to(torch.bfloat16).float()
-                state = om.state_dict_fp32(model)
                 cb, check = cpu_leg(cfg, wl, args, state=state, gpu_logits=gpu_logits, gpu_token=gpu_token, max_steps=1,
                                     mel_used=mel_used)
                 line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "stage_seconds", "host_cpus")}

@@ -76,7 +76,7 @@ int uvx_mel_to_timemajor(const float* mel, int64_t N, int n_mels, int64_t T, voi
  * positional embedding added after GELU (ref :896-899, r_batch_stride = 0).
  * Requirements: K % 8 == 0, N % 64 == 0, strides % 8 == 0, 16-byte aligned bases.
  * Split-K partial sums are reduced in a fixed order by a second kernel: results are deterministic.  */
-enum { UVX_ACT_NONE = 0, UVX_ACT_GELU = 1 };
+enum { UVX_ACT_NONE = 0, UVX_ACT_GELU = 1, UVX_ACT_SWIGLU = 2 };
 enum { UVX_DT_BF16 = 0, UVX_DT_F32 = 1 };
 
 typedef struct uvx_gemm_args {
@@ -99,11 +99,34 @@ typedef struct uvx_gemm_args {
   const void* norm_w;       /* optional: also emit norm_out[row,:] = norm_w * bf16(C[row,:] * rsqrt(mean(C^2) + eps)),  */
   void* norm_out;           /* the LlamaRMSNorm that follows o_proj / down_proj (hf:modeling_llama.py:53-67, 321-329),  */
   float norm_eps;           /* fused into the split-K reduction when there is one.  bf16 [rows, N], plain row order.    */
+  /* ---- round 2 (all optional, zero = off) -------------------------------------------------------------------------
+   * w_tiled = R (64 / 128 / 208 / 256): W points at the pre-tiled image [ceil(N/R)][K/64][R][64] of the [N, K] weight (rows past
+   *   N zero) instead of the row-major matrix, so every k-block of a tile is ONE contiguous R*128-byte run of DRAM (the weight
+   *   stream of the LLM prefill is HBM-bound; see uvx_tile_weight).  The kernel then uses R-wide tiles.
+   * act = UVX_ACT_SWIGLU (needs w_tiled = 208 and the image built with interleave = 8): rows of the image alternate 8 gate rows
+   *   and the 8 up rows of the same features; the epilogue writes C[row, f] = silu(gate_f) * up_f for the N/2 features
+   *   (LlamaMLP act_fn(gate_proj(x)) * up_proj(x), hf:modeling_llama.py:183) - the [rows, N] intermediate never reaches HBM.
+   * rope_cos/rope_sin [max_pos, 64] fp32 (+ rope_positions / rope_rows_per_seq / rope_pos_offset as in uvx_rope): tiles whose
+   *   first column is < rope_cols (= (Hq + Hkv) * 128) are rotated in the epilogue (hf:modeling_llama.py:124-168, head_dim 128).  */
+  int32_t w_tiled;
+  int32_t rope_cols;
+  const float* rope_cos;
+  const float* rope_sin;
+  const int32_t* rope_positions;
+  int64_t rope_rows_per_seq, rope_pos_offset;
 } uvx_gemm_args;
 
 int uvx_gemm_bf16(const uvx_gemm_args* args, uvx_stream_t stream);
 /* tuning hook: force tile config MT*1000+BN (0 = heuristic) and split-K count (0 = heuristic) for later calls */
 int uvx_debug_gemm_override(int cfg, int splits);
+/* tuning hook: L2 prefetch distance of the weight stream in k-blocks (0 = off; < 0 = default) */
+int uvx_debug_gemm_pf(int pf);
+/* W [N, K] bf16 row-major (row stride w_row_stride) -> the pre-tiled image uvx_gemm_args.w_tiled = R reads:
+ * out[t][kb][r][0:64] = W[row(t, r), kb*64 : kb*64+64], zero where row >= N.  interleave = 0: row(t, r) = t*R + r.
+ * interleave = 8 (fused gate|up, N = 2*F, R % 16 == 0): r = 16*g + j -> gate feature t*R/2 + 8g + j (j < 8) = W row of that
+ * feature, or the up row F + t*R/2 + 8g + (j-8) (j >= 8).  out: ceil(N/R) * (K/64) * R * 64 bf16 elements.               */
+int uvx_tile_weight(const void* W, int64_t N, int64_t K, int64_t w_row_stride, int32_t R, int32_t interleave, void* out,
+                    uvx_stream_t stream);
 /* tuning hook: force the thread-block cluster shape cm x cn (row tiles x column tiles sharing operand loads; 0 = heuristic) */
 int uvx_debug_gemm_cluster(int cm, int cn);
 /* tuning hook: 1 = 1-SM kernel without its MMAs (load pipeline alone), 2 = without its TMA loads; outputs are garbage */

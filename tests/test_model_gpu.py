@@ -523,8 +523,8 @@ def test_local_inference_single_batch_stream_conversation():
     # checks of the padded path are teacher-forced (test_left_padded_batch_forward_and_generate); here the first tokens
     # (pure prefill) must agree and the continuations mostly
     assert np.mean(first) >= 0.75 and np.mean(rest) >= 0.4, (first, np.mean(rest))
-    with pytest.raises(NotImplementedError):
-        inf.infer(s3, max_tokens=2, temperature=0.7)
+    sampled = inf.infer(s3, max_tokens=3, temperature=0.7)          # ref infer.py:319-328: temperature > 0 samples
+    assert sampled.output_tokens >= 1 and sampled.input_tokens == inf.infer(s3, max_tokens=1).input_tokens
     # conversation mode: turn 2 only prefills its own suffix on top of the cache from turn 1
     conv = LocalInference(model, proc, tok, conversation_mode=True)
     c1 = conv.infer(s1, max_tokens=4)
@@ -568,3 +568,34 @@ def test_pipeline_end_to_end_and_repetition_penalty():
     assert len(set(strong)) == len(strong)                  # a huge penalty never repeats a token it has already produced
     with pytest.raises(NotImplementedError):
         pipe({"audio": a, "sampling_rate": 16000}, temperature=0.7)
+
+
+def test_llama_hidden_fused_paths_match_unfused():
+    """Round-2 prefill path (pre-tiled weight images, RoPE in the q|k|v epilogue, SwiGLU in the gate|up epilogue) against the
+    round-1 sequence of separate kernels on the row-major weights: bit-identical hidden states, with and without a KV cache."""
+    import ultravox_b200.model as mm
+    from ultravox_b200.config import PRESETS, preset
+    from ultravox_b200.model import UltravoxModel
+    base = PRESETS["v0_5_8b"]
+    cfg = preset("v0_5_8b", audio_config=dict(base["audio_config"], encoder_layers=1),
+                 text_config=dict(base["text_config"], num_hidden_layers=2, vocab_size=2048))
+    model = UltravoxModel(cfg, device="cuda").init_random_(seed=1)
+    g = torch.Generator().manual_seed(0)
+    emb = (torch.randn(2, 201, 4096, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    assert model._tiled_weights() is not None and model._tiled_weights()[0]["gate_up"].swiglu
+    fused = model.llama_hidden(emb.clone()).clone()
+    cache = model.new_cache(2, 210)
+    fused_c = model.llama_hidden(emb.clone(), cache).clone()
+    saved = (mm.USE_TILED, mm.FUSE_ROPE, mm.FUSE_SWIGLU)
+    try:
+        mm.USE_TILED = mm.FUSE_ROPE = mm.FUSE_SWIGLU = False
+        model._tiled = None
+        assert model._tiled_weights() is None
+        plain = model.llama_hidden(emb.clone()).clone()
+        cache2 = model.new_cache(2, 210)
+        plain_c = model.llama_hidden(emb.clone(), cache2).clone()
+    finally:
+        mm.USE_TILED, mm.FUSE_ROPE, mm.FUSE_SWIGLU = saved
+        model._tiled = None
+    assert torch.equal(fused, plain) and torch.equal(fused_c, plain_c) and torch.equal(fused, fused_c)
+    assert torch.equal(cache.k[:, :, :201], cache2.k[:, :, :201]) and torch.equal(cache.v[:, :, :201], cache2.v[:, :, :201])

@@ -449,3 +449,91 @@ def test_kv_write_and_token_finish(ops):
     tok.copy_(torch.tensor([100, 1, 2]))
     ops.token_finish(tok, done, eos, 55, seq, cur, step, (pos, lens), alld)
     assert tok.tolist() == [100, 55, 55] and done.tolist() == [1, 1, 1] and int(alld) == 1 and int(cur) == 8
+
+
+# ------------------------------------------------------------------------------------------ round 2: weight-stream GEMM
+def _tile_ref(w, R, interleave):
+    N, K = w.shape
+    n_tiles = -(-N // R)
+    if interleave:
+        F = N // 2
+        rows = []
+        for t in range(n_tiles):
+            for r in range(R):
+                g, j = divmod(r, 16)
+                f = t * (R // 2) + g * 8 + (j & 7)
+                rows.append((f if j < 8 else F + f) if f < F else -1)
+    else:
+        rows = [t * R + r if t * R + r < N else -1 for t in range(n_tiles) for r in range(R)]
+    idx = torch.tensor(rows, device=w.device)
+    src = torch.cat([w, torch.zeros(1, K, dtype=w.dtype, device=w.device)])[idx.clamp_min(-1)]        # -1 -> the zero row
+    return src.view(n_tiles, R, K // 64, 64).permute(0, 2, 1, 3).contiguous().view(-1)
+
+
+@pytest.mark.parametrize("N,K,R,inter", [(512, 256, 128, 0), (1000, 128, 208, 0), (1024, 192, 208, 8), (28672, 256, 208, 8), (6144, 128, 128, 0)])
+def test_tile_weight_layout(ops, N, K, R, inter):
+    w = rnd(N, K, seed=3)
+    t = ops.TiledWeight(w, R, swiglu=bool(inter))
+    assert torch.equal(t.image, _tile_ref(w, R, inter))
+
+
+@pytest.mark.parametrize("M", [201, 77, 402])
+def test_gemm_tiled_weights_match_row_major(ops, M):
+    """Same tile width, same k order -> the tiled image must reproduce the row-major result bit for bit (plain, residual +
+    fused RMSNorm through split-K, ragged 208-wide tiles), for every L2 prefetch distance."""
+    from ultravox_b200 import _lib
+    x = rnd(M, 1024, seed=1)
+    for N, R, splits in ((1024, 128, 0), (4096, 128, 0), (2000 // 16 * 16 + 64, 208, 0), (512, 64, 0), (768, 256, 0)):
+        w = rnd(N, 1024, scale=0.05, seed=N)
+        tw = ops.TiledWeight(w, R)
+        ref32 = x.float() @ w.float().T
+        outs = []
+        for pf in (0, 3, 12):
+            _lib.lib().uvx_debug_gemm_pf(pf)
+            outs.append(ops.linear_tiled(x, tw))
+        _lib.lib().uvx_debug_gemm_pf(-1)
+        assert rel(outs[0], ref32) < 1e-3, (N, R)
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    # residual + fused norm (o_proj / down_proj form) against the row-major path with the same configuration
+    N, K = 1024, 4096
+    xa, w, r, nw = rnd(M, K, seed=5), rnd(N, K, scale=0.03, seed=6), rnd(M, N, seed=7), rnd(N, seed=8)
+    tw = ops.TiledWeight(w, 128)
+    h1, n1 = r.clone(), torch.empty(M, N, dtype=BF, device="cuda")
+    ops.linear_tiled(xa, tw, residual=h1, out=h1, norm=(nw, 1e-5, n1))
+    assert rel(h1, xa.float() @ w.float().T + r.float()) < 1e-3
+    assert torch.equal(n1, ops.rmsnorm(h1, nw, 1e-5))
+
+
+@pytest.mark.parametrize("M,F,K", [(201, 14336, 4096), (201, 1000 // 8 * 8, 512), (64, 512, 256), (300, 2048, 1024)])
+def test_gemm_fused_swiglu_bit_exact(ops, M, F, K):
+    """act(gate) * up finished in the gate|up GEMM epilogue == GEMM -> bf16 [M, 2F] -> uvx_swiglu, bit for bit."""
+    x, w = rnd(M, K, seed=1), rnd(2 * F, K, scale=0.03, seed=2)
+    want = ops.swiglu(ops.linear(x, w), gate_first=True)
+    got = ops.linear_tiled(x, ops.TiledWeight(w, 208, swiglu=True), act=ops.ACT_SWIGLU)
+    assert got.shape == (M, F)
+    assert torch.equal(got, want)
+    xf, wf = x.float(), w.float()
+    ref = F_silu_mul(xf @ wf[:F].T, xf @ wf[F:].T)
+    assert rel(got, ref) < 4e-3          # two bf16 roundings inside, like the reference's op order
+
+
+def F_silu_mul(g, u):
+    return F.silu(g.to(BF).float()).to(BF).float() * u.to(BF).float()
+
+
+@pytest.mark.parametrize("tiled", [False, True])
+@pytest.mark.parametrize("M,S,past,with_pos", [(201, 201, 0, False), (402, 201, 3, False), (77, 77, 0, True)])
+def test_gemm_fused_rope_bit_exact(ops, tiled, M, S, past, with_pos):
+    """RoPE in the q|k|v GEMM epilogue (head_dim 128) == GEMM then uvx_rope, bit for bit; v heads untouched."""
+    Hq, Hkv, D, K = 8, 2, 128, 1024
+    N = (Hq + 2 * Hkv) * D
+    x, w = rnd(M, K, seed=1), rnd(N, K, scale=0.03, seed=2)
+    inv = ops.llama3_inv_freq(D, 500000.0, dict(rope_type="llama3", factor=8.0, low_freq_factor=1.0, high_freq_factor=4.0,
+                                                 original_max_position_embeddings=8192))
+    cos, sin = ops.rope_tables(inv, 512, "cuda")
+    positions = torch.randint(0, 500, (M,), dtype=torch.int32, device="cuda") if with_pos else None
+    want = ops.linear(x, w)
+    ops.rope_(want, Hq, Hkv, D, cos, sin, rows_per_seq=S, pos_offset=past, positions=positions)
+    rope = (cos, sin, positions, S, past, (Hq + Hkv) * D)
+    got = ops.linear_tiled(x, ops.TiledWeight(w, 128), rope=rope) if tiled else ops.linear(x, w, rope=rope)
+    assert torch.equal(got, want)

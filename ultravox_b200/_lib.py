@@ -22,7 +22,9 @@ class GemmArgs(C.Structure):
                 ("c_row_stride", c_i64), ("c_batch_rows", c_i64), ("c_row_offset", c_i64), ("c_row_map", c_vp),
                 ("bias", c_vp), ("R", c_vp), ("r_row_stride", c_i64), ("r_batch_stride", c_i64), ("alpha", c_f32),
                 ("act", c_i32), ("out_dtype", c_i32), ("workspace", c_vp), ("workspace_bytes", c_i64),
-                ("norm_w", c_vp), ("norm_out", c_vp), ("norm_eps", c_f32)]
+                ("norm_w", c_vp), ("norm_out", c_vp), ("norm_eps", c_f32), ("w_tiled", c_i32), ("rope_cols", c_i32),
+                ("rope_cos", c_vp), ("rope_sin", c_vp), ("rope_positions", c_vp), ("rope_rows_per_seq", c_i64),
+                ("rope_pos_offset", c_i64)]
 
 
 class AttnArgs(C.Structure):
@@ -46,6 +48,8 @@ SIGNATURES = {
     "uvx_debug_gemm_override": (C.c_int, [C.c_int, C.c_int]),
     "uvx_debug_gemm_cluster": (C.c_int, [C.c_int, C.c_int]),
     "uvx_debug_gemm_mode": (C.c_int, [C.c_int]),
+    "uvx_debug_gemm_pf": (C.c_int, [C.c_int]),
+    "uvx_tile_weight": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "uvx_layernorm": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_vp]),
     "uvx_rmsnorm": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_vp]),
     "uvx_attention": (C.c_int, [C.POINTER(AttnArgs), c_vp]),

@@ -172,7 +172,48 @@ __global__ void add_i32_kernel(int32_t* __restrict__ a, int32_t* __restrict__ b2
   }
 }
 
+// W [N, K] row-major -> pre-tiled image [ceil(N/R)][K/64][R][64] (see include/uvx.h: uvx_tile_weight); 16 bytes per thread.
+__global__ void tile_weight_kernel(const bf16* __restrict__ W, int64_t N, int64_t K, int64_t w_row_stride, int R, int interleave,
+                                   bf16* __restrict__ out, int64_t total_vec) {
+  const int64_t num_kb = K / 64;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total_vec; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % 8);
+    const int64_t rowi = idx / 8;                 // (t * num_kb + kb) * R + r
+    const int r = (int)(rowi % R);
+    const int64_t tk = rowi / R;
+    const int64_t kb = tk % num_kb, t = tk / num_kb;
+    int64_t src_row;
+    if (interleave == 8) {
+      const int64_t F = N / 2;
+      const int g = r / 16, j = r % 16;
+      const int64_t f = t * (R / 2) + (int64_t)g * 8 + (j & 7);
+      src_row = f < F ? (j < 8 ? f : F + f) : -1;
+    } else {
+      src_row = t * R + r;
+      if (src_row >= N) src_row = -1;
+    }
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (src_row >= 0) v = *reinterpret_cast<const uint4*>(W + src_row * w_row_stride + kb * 64 + c8 * 8);
+    reinterpret_cast<uint4*>(out)[idx] = v;
+  }
+}
+
 }  // namespace uvx
+
+extern "C" int uvx_tile_weight(const void* W, int64_t N, int64_t K, int64_t w_row_stride, int32_t R, int32_t interleave, void* out,
+                               uvx_stream_t stream) {
+  using namespace uvx;
+  UVX_REQUIRE(W && out && N >= 1 && K >= 64 && K % 64 == 0 && w_row_stride % 8 == 0, "uvx_tile_weight: K %% 64 == 0 required");
+  UVX_REQUIRE(R == 64 || R == 128 || R == 208 || R == 256, "uvx_tile_weight: R must be 64 / 128 / 208 / 256");
+  UVX_REQUIRE(interleave == 0 || (interleave == 8 && R % 16 == 0 && N % 16 == 0), "uvx_tile_weight: interleave must be 0 or 8");
+  const int64_t n_tiles = (N + R - 1) / R;
+  const int64_t total_vec = n_tiles * (K / 64) * R * 8;
+  int64_t blocks = (total_vec + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  launch_k(tile_weight_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const bf16*)W, N, K, w_row_stride, (int)R,
+           (int)interleave, (bf16*)out, total_vec);
+  return check_launch("tile_weight_kernel");
+}
 
 static int rope_launch(void* qkv, int64_t rows, int64_t row_stride, int Hq, int Hkv, int D, const float* cos_tab,
                        const float* sin_tab, const int32_t* positions, int64_t rows_per_seq, int64_t pos_offset, float sgn,

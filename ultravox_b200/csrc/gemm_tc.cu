@@ -52,6 +52,16 @@ struct GemmParams {
   int a_slice_rows, w_slice_rows;
   int m_groups, n_groups;  // ceil(tiles / cm), ceil(n_tiles / cn)
   int dbg_mode;            // tuning only: 1 = skip the MMAs (load pipeline alone), 2 = skip the TMA loads (MMA pipeline alone)
+  // ---- round 2: weight-stream pipeline + fused epilogues (production kernel only)
+  int w_tiled;             // W is the pre-tiled image [n_tiles][K/64][BN][64]: every TMA box is ONE contiguous BN*128-byte run
+  int pf;                  // L2 prefetch distance in k-blocks: UTMAPF of the W box `pf` k-blocks ahead of the smem ring, so the
+                           // HBM stream runs ahead of (and is decoupled from) the ring slots - 0 = off
+  int swiglu;              // epilogue pairs tile columns (8 gate | 8 up interleaved): out[:, 16 per 32-column chunk]
+  const float* rope_cos;   // fused RoPE (hf:modeling_llama.py:124-168) on tile columns < rope_cols, head_dim 128 == BN
+  const float* rope_sin;
+  const int32_t* rope_pos;
+  int64_t rope_rows_per_seq, rope_pos_offset;
+  int rope_cols;
 };
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -202,6 +212,17 @@ __device__ __forceinline__ void tma_load_3d_e(void* dst, const CUtensorMap* tm, 
       "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// L2 prefetch of a tensor-map box (UTMAPF.L2): same addressing as the load, no shared-memory destination, no barrier
+__device__ __forceinline__ void tma_prefetch_2d_e(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n"
+      "}\n" ::"l"(tm),
+      "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -312,6 +333,43 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   __syncwarp();  // the pad is reused by the next chunk
 }
 
+// Fused SwiGLU epilogue (Llama MLP act(gate) * up, hf:modeling_llama.py:183): the pre-tiled gate|up image interleaves 8 gate
+// rows with the 8 up rows of the same features, so one 32-column accumulator chunk holds 2 x (8 gate | 8 up) and yields 16
+// finished activations per row - the [M, 2*ffn] intermediate is never written or re-read.  Rounding order is the unfused
+// path's: gate and up rounded to bf16 (what the GEMM would have stored), silu rounded to bf16, product rounded to bf16.
+__device__ __forceinline__ void epilogue_chunk_swiglu(const GemmParams& p, const uint32_t* raw, float* stage, int lane, int b,
+                                                      int64_t m_warp0, int64_t n_out, int64_t n_out_lim) {
+  float o[16];
+#pragma unroll
+  for (int g2 = 0; g2 < 2; ++g2) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float gate = __bfloat162float(__float2bfloat16_rn(__uint_as_float(raw[g2 * 16 + i]) * p.alpha));
+      const float up = __bfloat162float(__float2bfloat16_rn(__uint_as_float(raw[g2 * 16 + 8 + i]) * p.alpha));
+      o[g2 * 8 + i] = __bfloat162float(__float2bfloat16_rn(silu(gate))) * up;
+    }
+  }
+  // 32 rows x 16 floats, 16-byte chunks XOR-swizzled by (row >> 1) & 3 (conflict-free both ways)
+  float4* srow = reinterpret_cast<float4*>(stage + lane * 16);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) srow[g ^ ((lane >> 1) & 3)] = make_float4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int r = (lane >> 1) + 16 * j, half = lane & 1;
+    const int64_t m = m_warp0 + r;
+    if (m >= p.a_rows || n_out + half * 8 >= n_out_lim) continue;
+    const int64_t orow = p.c_row_map ? (int64_t)p.c_row_map[(int64_t)b * p.a_rows + m] : (int64_t)b * p.c_batch_rows + m + p.c_row_offset;
+    if (orow < 0) continue;
+    const float4* row4 = reinterpret_cast<const float4*>(stage + r * 16);
+    const float4 t0 = row4[(2 * half) ^ ((r >> 1) & 3)];
+    const float4 t1 = row4[(2 * half + 1) ^ ((r >> 1) & 3)];
+    const float v8[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+    *reinterpret_cast<bf16x8*>(reinterpret_cast<bf16*>(p.C) + orow * p.c_row_stride + n_out + half * 8) = pack8(v8);
+  }
+  __syncwarp();
+}
+
 // Shared-memory plan of the 1-SM kernel (dynamic, 1024-byte aligned base, always the full 227 KB - one CTA per SM):
 //   [0, stages * stage_bytes)   ring of {A box, W box} stages; the geometry is a launch parameter because the A box
 //                               only holds round8(M) rows when one row tile covers the whole problem (M = 201 prefill:
@@ -379,7 +437,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();  // set-up above overlapped the previous kernel's tail; its outputs are visible from here on
+  // set-up above overlapped the previous kernel's tail; its outputs are visible after griddepcontrol.wait.  The producer warp
+  // delays its own wait until the first weight prefetches are issued (weights do not depend on the previous kernel).
+  if (warp != 0) pdl_wait();
 
   if (warp == 0) {
     // ---- TMA producer: all 32 lanes run the loop (convergent), elect.sync issues
@@ -391,6 +451,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       int s = 0;           // ring slot and its phase: the ring runs ahead across tile boundaries
       uint32_t ph = 0;
+      bool waited = false;
+      const int tiled = p.w_tiled;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         const int tile = unit / p.splits, split = unit % p.splits;
         const int tm_idx = tile % tiles_m_total;  // consecutive tiles share the W tile
@@ -404,16 +466,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // tile, and in lockstep they would all hit the same L2 lines at the same time
         const int nk = kb_end - kb_begin;
         const int rot = (int)(((unsigned)tile * 7u + (unsigned)split * 3u) % (unsigned)nk);
+        // W box of k-block kb: canonical [N, K] weights -> (kb * 64, n0); pre-tiled image [tile][kb][BN][64] viewed as
+        // [rows, 64] -> (0, (tn_idx * num_kb + kb) * BN): one contiguous BN * 128-byte run of DRAM
+        const int wt_base = tn_idx * num_kb * BN;
+        // the HBM -> L2 stream of the weights runs `pf` k-blocks ahead of the shared-memory ring: the ring (4-5 stages, half of
+        // each stage is the re-read activation tile) holds too few weight bytes in flight to cover DRAM latency at full rate
+        const int pf = p.pf < nk ? p.pf : nk;
+        for (int i = 0; i < pf; ++i) {
+          const int kb = kb_begin + (i + rot < nk ? i + rot : i + rot - nk);
+          tma_prefetch_2d_e(&tmW, tiled ? 0 : kb * kBK, tiled ? wt_base + kb * BN : n0);
+        }
+        if (!waited) {
+          pdl_wait();
+          waited = true;
+        }
         for (int i = 0; i < nk; ++i) {
           const int kb = kb_begin + (i + rot < nk ? i + rot : i + rot - nk);
+          if (i + pf < nk) {
+            const int j = i + pf;
+            const int kbp = kb_begin + (j + rot < nk ? j + rot : j + rot - nk);
+            tma_prefetch_2d_e(&tmW, tiled ? 0 : kbp * kBK, tiled ? wt_base + kbp * BN : n0);
+          }
           mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* sa = smem + s * p.stage_bytes;
           mbar_expect_tx_e(&full_bar[s], (uint32_t)p.stage_bytes);
           tma_load_3d_e(sa, &tmA, kb * kBK, m0, b, &full_bar[s]);
-          tma_load_2d_e(sa + p.a_box_bytes, &tmW, kb * kBK, n0, &full_bar[s]);
+          tma_load_2d_e(sa + p.a_box_bytes, &tmW, tiled ? 0 : kb * kBK, tiled ? wt_base + kb * BN : n0, &full_bar[s]);
           if (++s == stages) { s = 0; ph ^= 1u; }
         }
       }
+      if (!waited) pdl_wait();
     }
   } else if (warp == 1) {
     // ---- MMA issuer: convergent warp, elect.sync issues
@@ -498,17 +580,76 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       float* pad = reinterpret_cast<float*>(smem + L::kPadOff) + (warp - 2) * (kStageBytesPerWarp / 4);
       const int64_t n_lim = (int64_t)n0 + BN < p.N ? (int64_t)n0 + BN : p.N;  // ragged last column tile (N % BN != 0)
+      bool handled = false;
+      if constexpr (BN == 208) {
+        if (p.swiglu) {  // warp-uniform: tile columns are (8 gate | 8 up) groups, BN / 2 finished activations per row
+          handled = true;
+          const int64_t n_out0 = (int64_t)tn_idx * (BN / 2);
+          const int64_t n_out_lim = n_out0 + BN / 2 < p.N / 2 ? n_out0 + BN / 2 : p.N / 2;
 #pragma unroll 1
-      for (int mt = 0; mt < MT; ++mt) {
-        const int64_t m_warp0 = (int64_t)m0 + mt * kBM + q * 32;
-        if (m_warp0 >= p.a_rows) continue;  // sub-tile entirely out of range (warp-uniform)
+          for (int mt = 0; mt < MT; ++mt) {
+            const int64_t m_warp0 = (int64_t)m0 + mt * kBM + q * 32;
+            if (m_warp0 >= p.a_rows) continue;
 #pragma unroll 1
-        for (int c = cpar; c < L::kChunks; c += cstep) {
-          if ((int64_t)n0 + c * 32 >= n_lim) break;
-          uint32_t raw[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * L::kBNT) + (uint32_t)(mt * L::kBNT + c * 32), raw);
-          tmem_ld_wait();
-          epilogue_chunk(p, raw, pad, lane, b, m_warp0, (int64_t)n0 + c * 32, n_lim);
+            for (int c = cpar; c < L::kChunks; c += cstep) {
+              if (n_out0 + c * 16 >= n_out_lim) break;
+              uint32_t raw[32];
+              tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * L::kBNT) + (uint32_t)(mt * L::kBNT + c * 32), raw);
+              tmem_ld_wait();
+              epilogue_chunk_swiglu(p, raw, pad, lane, b, m_warp0, n_out0 + c * 16, n_out_lim);
+            }
+          }
+        }
+      }
+      if constexpr (MT == 1 && BN == 128) {
+        if (p.rope_cos != nullptr && n0 < p.rope_cols) {
+          // fused RoPE: the tile is one 128-wide head, columns j and j + 64 rotate together; this warp owns chunks cpar and
+          // cpar + 2, i.e. columns [32 cpar, +32) and their partners.  Same rounding as GEMM-then-uvx_rope: the projection is
+          // rounded to bf16 first, the rotation runs in fp32 on those values and is rounded once more by the store.
+          handled = true;
+          const int64_t m_warp0 = (int64_t)m0 + q * 32;
+          if (m_warp0 < p.a_rows) {
+            uint32_t r0[32], r1[32];
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * L::kBNT);
+            tmem_ld32(tbase + (uint32_t)(cpar * 32), r0);
+            tmem_ld32(tbase + (uint32_t)(64 + cpar * 32), r1);
+            tmem_ld_wait();
+            const int64_t m = m_warp0 + lane;
+            if (m < p.a_rows) {
+              const int64_t pos = p.rope_pos ? (int64_t)p.rope_pos[m] : p.rope_pos_offset + (m % p.rope_rows_per_seq);
+              const float4* cp = reinterpret_cast<const float4*>(p.rope_cos + pos * 64 + cpar * 32);
+              const float4* sp = reinterpret_cast<const float4*>(p.rope_sin + pos * 64 + cpar * 32);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 c4 = cp[g], s4 = sp[g];
+                const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float x1 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r0[4 * g + e]) * p.alpha));
+                  const float x2 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r1[4 * g + e]) * p.alpha));
+                  r0[4 * g + e] = __float_as_uint(x1 * cc[e] - x2 * ss[e]);
+                  r1[4 * g + e] = __float_as_uint(x2 * cc[e] + x1 * ss[e]);
+                }
+              }
+            }
+            epilogue_chunk(p, r0, pad, lane, b, m_warp0, (int64_t)n0 + cpar * 32, n_lim);
+            epilogue_chunk(p, r1, pad, lane, b, m_warp0, (int64_t)n0 + 64 + cpar * 32, n_lim);
+          }
+        }
+      }
+      if (!handled) {
+#pragma unroll 1
+        for (int mt = 0; mt < MT; ++mt) {
+          const int64_t m_warp0 = (int64_t)m0 + mt * kBM + q * 32;
+          if (m_warp0 >= p.a_rows) continue;  // sub-tile entirely out of range (warp-uniform)
+#pragma unroll 1
+          for (int c = cpar; c < L::kChunks; c += cstep) {
+            if ((int64_t)n0 + c * 32 >= n_lim) break;
+            uint32_t raw[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * L::kBNT) + (uint32_t)(mt * L::kBNT + c * 32), raw);
+            tmem_ld_wait();
+            epilogue_chunk(p, raw, pad, lane, b, m_warp0, (int64_t)n0 + c * 32, n_lim);
+          }
         }
       }
       // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator stage back
@@ -1194,6 +1335,16 @@ static int num_sms() {
   return n;
 }
 
+static int g_gemm_pf = -1;  // L2 prefetch distance in k-blocks (UVX_GEMM_PF / uvx_debug_gemm_pf; default 12)
+static int gemm_pf() {
+  if (g_gemm_pf < 0) {
+    const char* e = getenv("UVX_GEMM_PF");
+    g_gemm_pf = e ? atoi(e) : 12;
+    if (g_gemm_pf < 0) g_gemm_pf = 0;
+  }
+  return g_gemm_pf;
+}
+
 template <int MT, int BN>
 static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaStream_t stream) {
   using L = SmemLayout<MT, BN>;
@@ -1211,7 +1362,19 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
     int rc = encode_map(&tmA, a->A, 3, dims, st, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (rc) return rc;
   }
-  {
+  const bool tiled = a->w_tiled != 0;
+  if (tiled) {
+    // pre-tiled image [n_tiles][K/64][BN][64] (built once by the host, ops.tile_weight): a 2-D map over [rows, 64] whose
+    // BN-row boxes are contiguous BN*128-byte runs - the DRAM access pattern of a plain copy (measured 6.33 TB/s vs 5.66 TB/s
+    // for 128-byte pieces of 208 rows 8 KB apart, profiles/r2_probe_ws.txt)
+    UVX_REQUIRE(a->w_tiled == BN && cm == 1 && cn == 1 && a->K % kBK == 0, "uvx_gemm_bf16: tiled weights need BN == tile rows and K %% 64 == 0");
+    const uint64_t n_tiles_w = (uint64_t)((a->N + BN - 1) / BN);
+    uint64_t dims[2] = {(uint64_t)kBK, n_tiles_w * (uint64_t)(a->K / kBK) * (uint64_t)BN};
+    uint64_t st[1] = {(uint64_t)kBK * 2};
+    uint32_t box[2] = {kBK, (uint32_t)BN};
+    int rc = encode_map(&tmW, a->W, 2, dims, st, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (rc) return rc;
+  } else {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     uint64_t st[1] = {(uint64_t)a->w_row_stride * 2};
     uint32_t box[2] = {kBK, (uint32_t)w_slice_rows};
@@ -1219,6 +1382,16 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
     if (rc) return rc;
   }
   GemmParams p;
+  p.w_tiled = tiled ? 1 : 0;
+  p.pf = gemm_pf();
+  p.swiglu = a->act == UVX_ACT_SWIGLU ? 1 : 0;
+  p.rope_cos = a->rope_cos;
+  p.rope_sin = a->rope_sin;
+  p.rope_pos = a->rope_positions;
+  p.rope_rows_per_seq = a->rope_rows_per_seq > 0 ? a->rope_rows_per_seq : 1;
+  p.rope_pos_offset = a->rope_pos_offset;
+  p.rope_cols = a->rope_cos ? a->rope_cols : 0;
+  if (p.swiglu || p.rope_cos) splits = 1;  // fused epilogues are tile-local: no split-K
   p.a_rows = a->a_rows;
   p.a_batch = a->a_batch;
   p.K = a->K;
@@ -1402,6 +1575,12 @@ extern "C" int uvx_debug_gemm_mode(int mode) {
   return UVX_OK;
 }
 
+// tuning hook: L2 prefetch distance of the weight stream in k-blocks (0 = off, < 0 = default / UVX_GEMM_PF)
+extern "C" int uvx_debug_gemm_pf(int pf) {
+  uvx::g_gemm_pf = pf;
+  return UVX_OK;
+}
+
 // tuning hook: force the thread-block cluster shape (cm row tiles x cn column tiles, 0 = heuristic)
 extern "C" int uvx_debug_gemm_cluster(int cm, int cn) {
   forced_cm = cm;
@@ -1477,6 +1656,33 @@ extern "C" int uvx_gemm_bf16(const uvx_gemm_args* a, uvx_stream_t stream_) {
   if (forced_cm > 0 && forced_cn > 0) {
     cm = forced_cm;
     cn = forced_cn;
+  }
+  UVX_REQUIRE(a->act != UVX_ACT_SWIGLU || (a->w_tiled == 208 && !a->bias && !a->R && !a->norm_w && a->out_dtype == UVX_DT_BF16 && a->N % 16 == 0),
+              "uvx_gemm_bf16: UVX_ACT_SWIGLU needs the 208-row interleaved gate|up image, bf16 output, no bias / residual / norm");
+  UVX_REQUIRE(!a->rope_cos || (a->rope_sin && a->a_batch == 1 && a->alpha == 1.0f && !a->bias && !a->R && a->act == UVX_ACT_NONE &&
+                               a->rope_cols % 128 == 0 && (a->w_tiled == 0 || a->w_tiled == 128) && a->N % 128 == 0),
+              "uvx_gemm_bf16: fused RoPE needs head_dim 128 tiles, a_batch 1, no bias / residual / activation");
+  if (a->w_tiled) {
+    // the image was cut for one tile width: that width is the configuration (row sub-tiles still follow the row count)
+    UVX_REQUIRE(a->w_tiled == 64 || a->w_tiled == 128 || a->w_tiled == 208 || a->w_tiled == 256, "uvx_gemm_bf16: w_tiled must be 64 / 128 / 208 / 256");
+    int mt = cfg / 1000;
+    if (mt != 1 && mt != 2) mt = (a->a_rows > 128 && a->a_rows <= 256 && a->a_batch == 1) ? 2 : 1;
+    if (a->rope_cos) mt = 1;
+    cfg = mt * 1000 + (int)a->w_tiled;
+    cm = cn = 1;
+    const int64_t tiles = ((a->a_rows + mt * 128 - 1) / (mt * 128)) * a->a_batch * ((a->N + a->w_tiled - 1) / a->w_tiled);
+    const int num_kb = (int)((a->K + 63) / 64);
+    int sp = 1;
+    if (tiles * 2 <= 148 && num_kb >= 16) {
+      sp = (int)(148 / tiles);
+      if (sp > num_kb / 8) sp = num_kb / 8;
+      if (sp > 16) sp = 16;
+      if (sp < 1) sp = 1;
+    }
+    if (forced_splits > 0) sp = forced_splits;
+    splits = sp;
+  } else if (a->rope_cos) {
+    cfg = 1128;   // one 128-wide head per tile, both rotation halves in the same accumulator row
   }
   switch (cfg) {
     case 1064: return launch_gemm<1, 64>(a, splits, cm, cn, stream);

@@ -29,6 +29,9 @@ from . import ops
 from .config import LossConfig, LossFunction, UltravoxConfig
 
 FUSE_NORM = os.environ.get("UVX_FUSE_NORM", "1") != "0"   # tuning switch: RMSNorm fused into the o_proj / down_proj split-K pass
+USE_TILED = os.environ.get("UVX_TILED", "1") != "0"       # LLM prefill GEMMs stream pre-tiled weight images (contiguous DRAM runs)
+FUSE_ROPE = os.environ.get("UVX_FUSE_ROPE", "1") != "0"   # RoPE in the q|k|v GEMM epilogue (head_dim 128)
+FUSE_SWIGLU = os.environ.get("UVX_FUSE_SWIGLU", "1") != "0"   # act(gate)*up in the gate|up GEMM epilogue (needs the tiled image)
 BF16 = torch.bfloat16
 
 
@@ -443,7 +446,35 @@ class UltravoxModel(nn.Module):
         inv = ops.llama3_inv_freq(self.language_model.head_dim, float(theta), scaling)
         self._inv_freq = inv
         self._rope = None
+        self._tiled = None          # pre-tiled LLM weight images are rebuilt lazily from the (possibly new) weights
+        self._wT = None
         return self
+
+    @torch.no_grad()
+    def _tiled_weights(self):
+        """Per-layer pre-tiled images of the frozen LLM projections for the prefill GEMMs (``ops.TiledWeight``): q|k|v, o and
+        down as 128-row tiles, gate|up as 208-row tiles with 8 gate / 8 up rows interleaved (fused SwiGLU).  A derived copy like
+        the conv weights (the named parameters keep the reference layout for state-dict I/O, decode GEMVs and training); built
+        once, on first use, if the GPU has room for the second copy (8B: +15 GB; a 70B replica has not - it streams the
+        row-major weights)."""
+        if getattr(self, "_tiled", None) is None:
+            self._tiled = False
+            layers = self.language_model.model.layers
+            if USE_TILED and len(layers) > 0 and layers[0].self_attn.qkv_w.is_cuda:
+                tc = self.config.text_config
+                hs, ffn = tc.hidden_size, tc.intermediate_size
+                per_layer = 2 * (layers[0].self_attn.qkv_w.numel() + hs * layers[0].self_attn.o_proj.weight.shape[1] + 3 * hs * ffn)
+                free, _ = torch.cuda.mem_get_info(self.device)
+                if hs % 64 == 0 and ffn % 64 == 0 and ffn % 8 == 0 and free > 1.15 * per_layer * len(layers) + (8 << 30):
+                    out = []
+                    for layer in layers:
+                        sa, mlp = layer.self_attn, layer.mlp
+                        out.append(dict(qkv=ops.TiledWeight(sa.qkv_w, 128), o=ops.TiledWeight(sa.o_proj.weight, 128),
+                                        gate_up=ops.TiledWeight(mlp.gate_up_w, 208, swiglu=True) if FUSE_SWIGLU
+                                        else ops.TiledWeight(mlp.gate_up_w, 208),
+                                        down=ops.TiledWeight(mlp.down_proj.weight, 128)))
+                    self._tiled = out
+        return self._tiled or None
 
     def _rope_tables(self, need: int):
         """cos/sin [n, D/2] fp32; grown geometrically (long conversations with KV reuse decode one position at a time - growing
@@ -585,15 +616,24 @@ class UltravoxModel(nn.Module):
         qkv = torch.empty(B * S, (nq + 2 * nkv) * hd, dtype=BF16, device=dev)
         att = torch.empty(B * S, nq * hd, dtype=BF16, device=dev)
         ffn = tc.intermediate_size
-        gu = torch.empty(B * S, 2 * ffn, dtype=BF16, device=dev)
+        gu = None if (self._tiled_weights() is not None and self._tiled_weights()[0]["gate_up"].swiglu) else torch.empty(B * S, 2 * ffn, dtype=BF16, device=dev)
         act = torch.empty(B * S, ffn, dtype=BF16, device=dev)
         rs = qkv.stride(0)
         layers = lm.model.layers
+        tiled = self._tiled_weights()
+        fuse_act = tiled is not None and tiled[0]["gate_up"].swiglu
+        # RoPE rides in the q|k|v GEMM epilogue when a head is one 128-wide tile; same positions rule as uvx_rope
+        rope = (cos, sin, positions, S, past, (nq + nkv) * hd) if (FUSE_ROPE and hd == 128) else None
         ops.rmsnorm(h, layers[0].input_layernorm.weight, eps, out=x)
         for li, layer in enumerate(layers):
             sa, mlp = layer.self_attn, layer.mlp
-            ops.linear(x, sa.qkv_w, out=qkv)
-            ops.rope_(qkv, nq, nkv, hd, cos, sin, rows_per_seq=S, pos_offset=past, positions=positions)
+            tw = tiled[li] if tiled is not None else None
+            if tw is not None:
+                ops.linear_tiled(x, tw["qkv"], out=qkv, rope=rope)
+            else:
+                ops.linear(x, sa.qkv_w, out=qkv, rope=rope)
+            if rope is None:
+                ops.rope_(qkv, nq, nkv, hd, cos, sin, rows_per_seq=S, pos_offset=past, positions=positions)
             if cache is None:
                 ops.attention_fused_qkv(qkv, B, S, nq, nkv, hd, hd ** -0.5, True, kv_len, 0, out=att, kv_start=kv_start)
             else:
@@ -604,13 +644,27 @@ class UltravoxModel(nn.Module):
                               (rs, S * rs, nkv * hd, smax * nkv * hd, nkv * hd, smax * nkv * hd, nq * hd, S * nq * hd),
                               hd ** -0.5, True, kv_len, 0, kv_start)
             # o_proj / down_proj write the residual stream AND the RMSNorm the next block reads (fused into split-K's pass 2)
-            ops.linear(att, sa.o_proj.weight, residual=h, out=h, norm=(layer.post_attention_layernorm.weight, eps, x) if FUSE_NORM else None)
+            n1 = (layer.post_attention_layernorm.weight, eps, x) if FUSE_NORM else None
+            if tw is not None:
+                ops.linear_tiled(att, tw["o"], residual=h, out=h, norm=n1)
+            else:
+                ops.linear(att, sa.o_proj.weight, residual=h, out=h, norm=n1)
             if not FUSE_NORM:
                 ops.rmsnorm(h, layer.post_attention_layernorm.weight, eps, out=x)
-            ops.linear(x, mlp.gate_up_w, out=gu)
-            ops.swiglu(gu, gate_first=True, out=act)
+            if fuse_act:
+                ops.linear_tiled(x, tw["gate_up"], out=act, act=ops.ACT_SWIGLU)      # silu(gate) * up straight from the accumulators
+            else:
+                if tw is not None:
+                    ops.linear_tiled(x, tw["gate_up"], out=gu)
+                else:
+                    ops.linear(x, mlp.gate_up_w, out=gu)
+                ops.swiglu(gu, gate_first=True, out=act)
             nxt = layers[li + 1].input_layernorm.weight if li + 1 < len(layers) else lm.model.norm.weight
-            ops.linear(act, mlp.down_proj.weight, residual=h, out=h, norm=(nxt, eps, x) if FUSE_NORM else None)
+            n2 = (nxt, eps, x) if FUSE_NORM else None
+            if tw is not None:
+                ops.linear_tiled(act, tw["down"], residual=h, out=h, norm=n2)
+            else:
+                ops.linear(act, mlp.down_proj.weight, residual=h, out=h, norm=n2)
             if not FUSE_NORM:
                 ops.rmsnorm(h, nxt, eps, out=x)
         if cache is not None:
@@ -643,6 +697,7 @@ class UltravoxModel(nn.Module):
                                f"unexpected keys {list(res.unexpected_keys)}")
         res.missing_keys[:] = missing
         self._wT = None
+        self._tiled = None
         return res
 
     def new_cache(self, batch: int, max_len: int) -> KVCache:

@@ -87,7 +87,7 @@ def gemm_raw(A_ptr: int, a_batch: int, a_rows: int, K: int, a_row_stride: int, a
              W: torch.Tensor, C_t: torch.Tensor, c_row_stride: int, c_batch_rows: int, c_row_offset: int = 0,
              c_row_map: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
              R: Optional[torch.Tensor] = None, r_row_stride: int = 0, r_batch_stride: int = 0,
-             alpha: float = 1.0, act: int = ACT_NONE, norm: Optional[tuple] = None) -> None:
+             alpha: float = 1.0, act: int = ACT_NONE, norm: Optional[tuple] = None, rope: Optional[tuple] = None) -> None:
     a = GemmArgs()
     a.A, a.a_batch, a.a_rows, a.K = A_ptr, a_batch, a_rows, K
     a.a_row_stride, a.a_batch_stride = a_row_stride, a_batch_stride
@@ -102,13 +102,78 @@ def gemm_raw(A_ptr: int, a_batch: int, a_rows: int, K: int, a_row_stride: int, a
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     if norm is not None:                       # (weight, eps, out): fused RMSNorm of the finished rows
         a.norm_w, a.norm_eps, a.norm_out = norm[0].data_ptr(), float(norm[1]), norm[2].data_ptr()
+    if rope is not None:                       # (cos, sin, positions|None, rows_per_seq, pos_offset, rope_cols): fused RoPE, head_dim 128
+        cos, sin, positions, rows_per_seq, pos_offset, rope_cols = rope
+        a.rope_cos, a.rope_sin, a.rope_positions = cos.data_ptr(), sin.data_ptr(), _p(positions)
+        a.rope_rows_per_seq, a.rope_pos_offset, a.rope_cols = int(rows_per_seq), int(pos_offset), int(rope_cols)
     check(lib().uvx_gemm_bf16(C.byref(a), _stream()), "uvx_gemm_bf16")
+
+
+class TiledWeight:
+    """Pre-tiled image of an ``nn.Linear`` weight [N, K] for the weight-streaming GEMM (include/uvx.h: ``uvx_tile_weight`` /
+    ``uvx_gemm_args.w_tiled``): [ceil(N/R)][K/64][R][64] bf16, every (tile, k-block) box one contiguous R*128-byte run.
+    ``swiglu``: the rows alternate 8 gate rows / 8 up rows of the same features (fused gate|up projection, N = 2*ffn), which
+    is what ``linear_tiled(..., act=ACT_SWIGLU)`` needs to finish act(gate)*up inside the GEMM epilogue."""
+
+    def __init__(self, w: torch.Tensor, R: int, swiglu: bool = False):
+        _cuda(w, BF16, "w")
+        self.N, self.K, self.R, self.swiglu = int(w.shape[0]), int(w.shape[1]), int(R), bool(swiglu)
+        n_tiles = -(-self.N // R)
+        self.image = torch.empty(n_tiles * (self.K // 64) * R * 64, dtype=BF16, device=w.device)
+        check(lib().uvx_tile_weight(w.data_ptr(), self.N, self.K, w.stride(0), R, 8 if swiglu else 0, self.image.data_ptr(),
+                                    _stream()), "uvx_tile_weight")
+
+    @property
+    def n_out(self) -> int:
+        return self.N // 2 if self.swiglu else self.N
+
+
+ACT_SWIGLU = 2
+
+
+def linear_tiled(x: torch.Tensor, wt: TiledWeight, out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+                 act: int = ACT_NONE, norm: Optional[tuple] = None, rope: Optional[tuple] = None) -> torch.Tensor:
+    """y = x @ W.T (+ residual) over the pre-tiled weight image; ``act=ACT_SWIGLU`` -> y = silu(gate) * up [M, N/2] (needs a
+    ``swiglu`` image); ``rope=(cos, sin, positions|None, rows_per_seq, pos_offset, rope_cols)`` rotates the q / k heads in the
+    epilogue (head_dim 128); ``norm`` as in ``linear``."""
+    _cuda(x, BF16, "x")
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    n_out = wt.n_out if act == ACT_SWIGLU else wt.N
+    if (act == ACT_SWIGLU) != wt.swiglu:
+        raise ValueError("ACT_SWIGLU needs (and only works with) the gate|up-interleaved weight image")
+    if out is None:
+        out = torch.empty(*x.shape[:-1], n_out, dtype=BF16, device=x.device)
+    o2 = out.view(-1, n_out)
+    a = GemmArgs()
+    a.A, a.a_batch, a.a_rows, a.K = x2.data_ptr(), 1, M, K
+    a.a_row_stride, a.a_batch_stride = x2.stride(0), 0
+    a.W, a.N, a.w_row_stride = wt.image.data_ptr(), wt.N, K
+    a.C, a.c_row_stride, a.c_batch_rows, a.c_row_offset = o2.data_ptr(), o2.stride(0), M, 0
+    if residual is not None:
+        r2 = residual.reshape(-1, n_out)
+        a.R, a.r_row_stride = r2.data_ptr(), r2.stride(0)
+    a.alpha, a.act, a.out_dtype = 1.0, act, 0
+    ws = gemm_workspace(out.device)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    if norm is not None:
+        a.norm_w, a.norm_eps, a.norm_out = norm[0].data_ptr(), float(norm[1]), norm[2].data_ptr()
+    a.w_tiled = wt.R
+    if rope is not None:
+        cos, sin, positions, rows_per_seq, pos_offset, rope_cols = rope
+        a.rope_cos, a.rope_sin, a.rope_positions = cos.data_ptr(), sin.data_ptr(), _p(positions)
+        a.rope_rows_per_seq, a.rope_pos_offset, a.rope_cols = int(rows_per_seq), int(pos_offset), int(rope_cols)
+    check(lib().uvx_gemm_bf16(C.byref(a), _stream()), "uvx_gemm_bf16(tiled)")
+    return out
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
            residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
            out_dtype=BF16, row_map: Optional[torch.Tensor] = None, alpha: float = 1.0,
-           norm: Optional[tuple] = None) -> torch.Tensor:
+           norm: Optional[tuple] = None, rope: Optional[tuple] = None) -> torch.Tensor:
     """y = act(alpha * x @ w.T + bias) + residual for x [..., K] (last dim contiguous, uniform row stride).
     ``norm=(weight, eps, out)`` additionally writes out = RMSNorm(y) (fused into the split-K reduction when possible)."""
     _cuda(x, BF16, "x"), _cuda(w, BF16, "w")
@@ -124,7 +189,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     if residual is not None:
         r2 = residual.reshape(-1, N)
     gemm_raw(x2.data_ptr(), 1, M, K, x2.stride(0), 0, w, o2, o2.stride(-2) if o2.dim() >= 2 else N, M, 0,
-             row_map, bias, r2, r2.stride(0) if r2 is not None else 0, 0, alpha, act, norm)
+             row_map, bias, r2, r2.stride(0) if r2 is not None else 0, 0, alpha, act, norm, rope)
     return out
 
 
