@@ -507,9 +507,15 @@ def test_gemm_tiled_weights_match_row_major(ops, M):
 @pytest.mark.parametrize("M,F,K", [(201, 14336, 4096), (201, 1000 // 8 * 8, 512), (64, 512, 256), (300, 2048, 1024)])
 def test_gemm_fused_swiglu_bit_exact(ops, M, F, K):
     """act(gate) * up finished in the gate|up GEMM epilogue == GEMM -> bf16 [M, 2F] -> uvx_swiglu, bit for bit."""
+    from ultravox_b200 import _lib
     x, w = rnd(M, K, seed=1), rnd(2 * F, K, scale=0.03, seed=2)
-    want = ops.swiglu(ops.linear(x, w), gate_first=True)
-    got = ops.linear_tiled(x, ops.TiledWeight(w, 208, swiglu=True), act=ops.ACT_SWIGLU)
+    # same tile shape on both sides (the per-tile rotated K start makes the fp32 summation order a function of the tiling)
+    _lib.lib().uvx_debug_gemm_override((2 if 128 < M <= 256 else 1) * 1000 + 208, 1)
+    try:
+        want = ops.swiglu(ops.linear(x, w), gate_first=True)
+        got = ops.linear_tiled(x, ops.TiledWeight(w, 208, swiglu=True), act=ops.ACT_SWIGLU)
+    finally:
+        _lib.lib().uvx_debug_gemm_override(0, 0)
     assert got.shape == (M, F)
     assert torch.equal(got, want)
     xf, wf = x.float(), w.float()
@@ -531,8 +537,13 @@ def test_gemm_fused_rope_bit_exact(ops, tiled, M, S, past, with_pos):
     inv = ops.llama3_inv_freq(D, 500000.0, dict(rope_type="llama3", factor=8.0, low_freq_factor=1.0, high_freq_factor=4.0,
                                                  original_max_position_embeddings=8192))
     cos, sin = ops.rope_tables(inv, 512, "cuda")
+    from ultravox_b200 import _lib
     positions = torch.randint(0, 500, (M,), dtype=torch.int32, device="cuda") if with_pos else None
-    want = ops.linear(x, w)
+    _lib.lib().uvx_debug_gemm_override(1128, 1)          # the fused form runs one 128-wide head per tile: same tiling for the reference
+    try:
+        want = ops.linear(x, w)
+    finally:
+        _lib.lib().uvx_debug_gemm_override(0, 0)
     ops.rope_(want, Hq, Hkv, D, cos, sin, rows_per_seq=S, pos_offset=past, positions=positions)
     rope = (cos, sin, positions, S, past, (Hq + Hkv) * D)
     got = ops.linear_tiled(x, ops.TiledWeight(w, 128), rope=rope) if tiled else ops.linear(x, w, rope=rope)
