@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true", help="skip the stock-transformers bf16 GPU arm (N=1 only)")
+    ap.add_argument("--no-train-record", action="store_true", help="skip the secondary cfg3 (adapter training) record")
+    ap.add_argument("--train-batch", type=int, default=4, help="clips per GPU of the secondary cfg3 record")
     ap.add_argument("--ttft-iters", type=int, default=200, help="end-to-end iterations behind TTFT p50 / p90 (>= --steps)")
     ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU arm (0 = sweep and keep the fastest)")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall-clock budget of the CPU arm's timed steps")
@@ -366,6 +368,72 @@ def roofline_pass(model, eng, peaks, reps=20):
     return out
 
 
+# ----------------------------------------------------------------------------------------------- cfg3 record
+def train_record(model, cfg, args, rank, world, dev):
+    """Secondary record: BASELINE config 3 - adapter-only training, encoder + LLM frozen, bf16, data-parallel,
+    ONE gradient all-reduce per optimizer step - on the same weights, `--train-batch` 30 s clips per GPU, 1 warm-up + 3 timed
+    steps (CUDA events, max over ranks).  The all-reduce is timed separately (events on the launching stream around the NCCL
+    call).  This is the only path of the repo with a collective, so it is what the 1 -> 8 GPU scaling run sees of it."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ultravox_b200 import ops
+    from ultravox_b200.training import AdapterTrainer
+    B, secs = args.train_batch, args.secs
+    n = int(16000 * secs)
+    frames = -(-n // 160)
+    n_tok = -(-frames // 16)
+    g = torch.Generator().manual_seed(7 + rank)
+    S = 8 + n_tok + 5
+    ids = torch.randint(0, min(cfg.vocab_size, 128000), (B, S), generator=g)
+    labels = ids.clone()
+    labels[:, :-5] = -100
+    waves = np.stack([np.random.default_rng(5000 + rank * 1000 + i).standard_normal(n).astype(np.float32) for i in range(B)])
+    waves = torch.from_numpy(np.pad(waves, ((0, 0), (0, (-n) % 160)))).to(dev)
+    tr = AdapterTrainer(model, lr=2e-3)
+    ar_ms = []
+
+    def step():
+        tm = ops.logmel(waves, cfg.audio_config.num_mel_bins, want_f32=False, want_tm=True)
+        loss = tr.forward_backward(input_ids=ids, audio_values=None, audio_token_start_idx=torch.full((B,), 8),
+                                   audio_lens=torch.full((B,), frames), audio_token_len=torch.full((B,), n_tok, dtype=torch.int32),
+                                   audio_batch_size=torch.ones(B, dtype=torch.int64), labels=labels, audio_tm=tm)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        scale = tr.all_reduce()
+        a1.record()
+        tr.optimizer_step(scale)
+        ar_ms.append((a0, a1))
+        return loss
+
+    flat0 = model.multi_modal_projector.flat.clone()
+    loss0 = float(step())
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ar_ms.clear()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        loss = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / 3, max(a.elapsed_time(b) for a, b in ar_ms)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    loss1 = float(loss)
+    model.multi_modal_projector.flat.copy_(flat0)          # leave the weights as the other passes expect them
+    ms, ar = float(t[0]), float(t[1])
+    return {"config": "cfg3: adapter-only training (encoder + LLM frozen), bf16, data-parallel, one gradient all-reduce per step",
+            "per_gpu_batch": B, "global_batch": B * world, "clip_seconds": secs, "steps": 3, "warmup": 1, "ms_per_step": ms,
+            "clips_per_s": B * world / (ms * 1e-3), "audio_sec_per_s": B * world * secs / (ms * 1e-3),
+            "allreduce_ms": ar if world > 1 else 0.0, "allreduce_bytes": tr.grad.numel() * 4 if world > 1 else 0,
+            "allreduce": "NCCL sum all-reduce of the flat fp32 projector gradient; 1/world folded into the AdamW kernel" if world > 1 else "none (1 GPU)",
+            "loss_first": loss0, "loss_last": loss1, "timer": "CUDA events, max over ranks"}
+
+
 # ----------------------------------------------------------------------------------------------- main
 def main():
     args = parse()
@@ -477,6 +545,13 @@ def main():
     gpu_logits, gpu_token = eng.logits.clone(), int(eng.token[0])
     tokens_ok = 0 <= gpu_token < cfg.vocab_size and bool(torch.isfinite(gpu_logits).all())
 
+    train = None
+    if not args.no_train_record:
+        try:
+            train = train_record(model, cfg, args, rank, world, dev)
+        except Exception as e:
+            train = {"error": repr(e)[:300]}
+
     if rank == 0:
         peaks = {}
         try:
@@ -492,7 +567,7 @@ def main():
                 "ttft_ms_p50": statistics.median(per) * 1e3, "ttft_ms_p90": per_sorted[int(0.9 * (len(per) - 1))] * 1e3,
                 "ttft_ms_p50_cuda_events": per_ev[len(per_ev) // 2], "ttft_iters": n_tt,
                 "gpu_launches": eng.launches_per_step * K, "launches_per_step": eng.launches_per_step,
-                "clocks": clocks, "token_check": tokens_ok}
+                "clocks": clocks, "token_check": tokens_ok, "train": train}
         state = mel_used = None
         if not args.no_cpu_baseline:
             try:      # material for the CPU leg, fetched before anything else touches the allocator

@@ -119,6 +119,8 @@ typedef struct uvx_gemm_args {
 int uvx_gemm_bf16(const uvx_gemm_args* args, uvx_stream_t stream);
 /* tuning hook: force tile config MT*1000+BN (0 = heuristic) and split-K count (0 = heuristic) for later calls */
 int uvx_debug_gemm_override(int cfg, int splits);
+/* tuning hook: cap the shared-memory ring depth of uvx_gemm_bf16 (0 = as deep as fits) */
+int uvx_debug_gemm_stages(int n);
 /* tuning hook: L2 prefetch distance of the weight stream in k-blocks (0 = off; < 0 = default) */
 int uvx_debug_gemm_pf(int pf);
 /* W [N, K] bf16 row-major (row stride w_row_stride) -> the pre-tiled image uvx_gemm_args.w_tiled = R reads:

@@ -380,9 +380,9 @@ static constexpr int kSmemTotal = 227 * 1024;
 static constexpr int kBarOff = kSmemTotal - 256;
 static constexpr int kMaxStages = 8;
 
-template <int MT, int BN>
+template <int MT, int BN, int EW = 0>
 struct SmemLayout {
-  static constexpr int kEpiWarps = MT == 1 ? 8 : 4;   // tensor-bound shapes (MT = 1) get two epilogue warps per TMEM lane quarter
+  static constexpr int kEpiWarps = EW ? EW : (MT == 1 ? 8 : 4);   // tensor-bound shapes (MT = 1) get two epilogue warps per TMEM lane quarter
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
   static constexpr int kWBytes = BN * kBK * 2;
   static constexpr int kBNT = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);   // TMEM column stride of one 128-row accumulator
@@ -394,11 +394,14 @@ struct SmemLayout {
   static_assert(2 * (MT * kBM * kBK * 2 + kWBytes) <= kPadOff, "ring too shallow");
 };
 
-template <int MT, int BN>
-__global__ void __launch_bounds__(SmemLayout<MT, BN>::kThreads, 1)
+// EW: epilogue warps (0 = default for MT).  DIAG: tuning twin with the pipeline-isolation modes compiled in (uvx_debug_gemm_mode:
+// 1 = loads only, 2 = MMAs only, 3 = no epilogue stores) - same convergent producer / MMA loops as production, unlike
+// gemm_tc_kernel_x; never on the product path.
+template <int MT, int BN, int EW = 0, bool DIAG = false>
+__global__ void __launch_bounds__(SmemLayout<MT, BN, EW>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
   pdl_trigger();
-  using L = SmemLayout<MT, BN>;
+  using L = SmemLayout<MT, BN, EW>;
   constexpr int kAcc = L::kAcc;
   constexpr int kEpiWarps = L::kEpiWarps;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -488,6 +491,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_prefetch_2d_e(&tmW, tiled ? 0 : kbp * kBK, tiled ? wt_base + kbp * BN : n0);
           }
           mbar_wait(&empty_bar[s], ph ^ 1u);
+          if constexpr (DIAG) {
+            if (p.dbg_mode == 2) {  // MMAs only: hand the (never loaded) slot over
+              if (lane == 0) mbar_arrive(&full_bar[s]);
+              __syncwarp();
+              if (++s == stages) { s = 0; ph ^= 1u; }
+              continue;
+            }
+          }
           uint8_t* sa = smem + s * p.stage_bytes;
           mbar_expect_tx_e(&full_bar[s], (uint32_t)p.stage_bytes);
           tma_load_3d_e(sa, &tmA, kb * kBK, m0, b, &full_bar[s]);
@@ -515,6 +526,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if constexpr (DIAG) {
+            if (p.dbg_mode == 1) {  // loads only: free the slot at once
+              if (lane == 0) mbar_arrive(&empty_bar[s]);
+              __syncwarp();
+              if (++s == stages) { s = 0; ph ^= 1u; }
+              continue;
+            }
+          }
           const uint32_t sa = smem_u32(smem + s * p.stage_bytes);
           const uint64_t dw = make_smem_desc(sa + p.a_box_bytes);
 #pragma unroll
@@ -530,6 +549,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           umma_commit_e(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
           if (++s == stages) { s = 0; ph ^= 1u; }
+        }
+        if constexpr (DIAG) {
+          if (p.dbg_mode == 1) {
+            if (lane == 0) mbar_arrive(&tmem_full[acc]);
+            __syncwarp();
+            continue;
+          }
         }
         umma_commit_e(&tmem_full[acc]);  // accumulators of this tile complete
       }
@@ -551,6 +577,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t aph = (tcount / kAcc) & 1u;
       mbar_wait(&tmem_full[acc], aph);
       tc_fence_after();
+      if constexpr (DIAG) {
+        if (p.dbg_mode == 1 || p.dbg_mode == 3) {  // no epilogue work: hand the accumulator stage straight back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          continue;
+        }
+      }
       const bool direct = p.splits == 1;
       if (!direct) {
         // split-K: park the raw fp32 partial tile in the workspace; splitk_reduce_kernel sums the splits in a fixed
@@ -1335,19 +1369,21 @@ static int num_sms() {
   return n;
 }
 
-static int g_gemm_pf = -1;  // L2 prefetch distance in k-blocks (UVX_GEMM_PF / uvx_debug_gemm_pf; default 12)
+static int g_gemm_pf = -1;  // L2 prefetch distance in k-blocks (UVX_GEMM_PF / uvx_debug_gemm_pf; default 0)
 static int gemm_pf() {
   if (g_gemm_pf < 0) {
     const char* e = getenv("UVX_GEMM_PF");
-    g_gemm_pf = e ? atoi(e) : 12;
+    g_gemm_pf = e ? atoi(e) : 0;  // measured: prefetching ahead of the ring only slows the stream down (profiles/r2_ws_sweep_v1.txt)
     if (g_gemm_pf < 0) g_gemm_pf = 0;
   }
   return g_gemm_pf;
 }
 
-template <int MT, int BN>
+static int g_gemm_stage_cap = 0;  // tuning only (uvx_debug_gemm_stages): upper bound on the ring depth
+
+template <int MT, int BN, int EW = 0, bool DIAG = false>
 static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaStream_t stream) {
-  using L = SmemLayout<MT, BN>;
+  using L = SmemLayout<MT, BN, EW>;
   CUtensorMap tmA, tmW;
   // one row tile covers the whole problem: stage only round8(M) rows of A per k-block (more ring stages fit)
   if (cm < 1 || cn < 1 || cm * cn > 8 || (BN / cm) % 8 != 0 || BN % cm != 0) cm = cn = 1;
@@ -1428,6 +1464,7 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
   p.stage_bytes = p.a_box_bytes + L::kWBytes;
   p.stages = L::kPadOff / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
+  if (g_gemm_stage_cap >= 2 && p.stages > g_gemm_stage_cap) p.stages = g_gemm_stage_cap;
   p.cm = cm;
   p.dbg_mode = g_gemm_dbg;
   p.cn = cn;
@@ -1437,7 +1474,7 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
   p.n_groups = (p.n_tiles + cn - 1) / cn;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MT, BN, EW, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel_x<MT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm_tc_kernel<%d,%d>, smem %d): %s", MT, BN, kSmemTotal, cudaGetErrorString(e));
@@ -1448,16 +1485,17 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
   const int units = p.m_groups * p.n_groups * p.splits;  // cluster-level work units
   const int csize = cm * cn;
   UVX_REQUIRE(!(p.dbg_mode && csize > 1), "uvx_gemm_bf16: pipeline-isolation modes are for unclustered launches");
+  UVX_REQUIRE(EW == 0 || csize == 1, "uvx_gemm_bf16: cluster launches use the default epilogue width");
   if (csize == 1) {
     const int grid = units < num_sms() ? units : num_sms();
-    if (p.dbg_mode) launch_k(gemm_tc_kernel_x<MT, BN>, dim3((unsigned)grid), dim3(L::kThreads), kSmemTotal, stream, tmA, tmW, p);
-    else launch_k(gemm_tc_kernel<MT, BN>, dim3((unsigned)grid), dim3(L::kThreads), kSmemTotal, stream, tmA, tmW, p);
+    if (p.dbg_mode && !DIAG && EW == 0) launch_k(gemm_tc_kernel_x<MT, BN>, dim3((unsigned)grid), dim3(SmemLayout<MT, BN>::kThreads), kSmemTotal, stream, tmA, tmW, p);
+    else launch_k(gemm_tc_kernel<MT, BN, EW, DIAG>, dim3((unsigned)grid), dim3(L::kThreads), kSmemTotal, stream, tmA, tmW, p);
   } else {
     static int max_clusters[9] = {0};
     if (max_clusters[csize] == 0) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)(num_sms() / csize * csize));
-      cfg.blockDim = dim3(L::kThreads);
+      cfg.blockDim = dim3(SmemLayout<MT, BN>::kThreads);
       cfg.dynamicSmemBytes = kSmemTotal;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
@@ -1474,8 +1512,8 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
       max_clusters[csize] = n;
     }
     const int clusters = units < max_clusters[csize] ? units : max_clusters[csize];
-    launch_k_cluster(gemm_tc_kernel_x<MT, BN>, dim3((unsigned)(clusters * csize)), dim3(L::kThreads), kSmemTotal, stream, (unsigned)csize, tmA,
-                     tmW, p);
+    launch_k_cluster(gemm_tc_kernel_x<MT, BN>, dim3((unsigned)(clusters * csize)), dim3(SmemLayout<MT, BN>::kThreads), kSmemTotal, stream,
+                     (unsigned)csize, tmA, tmW, p);
   }
   int rc = check_launch("gemm_tc_kernel");
   if (rc) return rc;
@@ -1575,6 +1613,12 @@ extern "C" int uvx_debug_gemm_mode(int mode) {
   return UVX_OK;
 }
 
+// tuning hook: cap the shared-memory ring depth (0 = as deep as fits)
+extern "C" int uvx_debug_gemm_stages(int n) {
+  uvx::g_gemm_stage_cap = n;
+  return UVX_OK;
+}
+
 // tuning hook: L2 prefetch distance of the weight stream in k-blocks (0 = off, < 0 = default / UVX_GEMM_PF)
 extern "C" int uvx_debug_gemm_pf(int pf) {
   uvx::g_gemm_pf = pf;
@@ -1616,9 +1660,14 @@ static void pick_cfg(int64_t rows, int64_t batch, int64_t N, int64_t K, int* cfg
     if (N % 256 == 0 && m_tiles * (N / 256) >= (sms * 4) / 3) bn = 256;
     else bn = (N % 128 == 0 && m_tiles * (N / 128) >= sms / 2) ? 128 : 64;
   }
+  int variant = 0;  // tuning variants: 6xxx = (2, xxx) with 8 epilogue warps, 7xxx = (2, xxx) diagnostic twin, 8xxx = both
   if (forced > 0 && (N % (forced % 1000) == 0 || forced % 1000 == 208 || forced / 1000 == 5)) {
     mt = forced / 1000;
     bn = forced % 1000;
+    if (mt >= 6) {
+      variant = mt;
+      mt = 2;
+    }
   }
   const int64_t tiles = ((rows + mt * 128 - 1) / (mt * 128)) * batch * ((N + bn - 1) / bn);
   int sp = 1;
@@ -1629,7 +1678,7 @@ static void pick_cfg(int64_t rows, int64_t batch, int64_t N, int64_t K, int* cfg
     if (sp < 1) sp = 1;
   }
   if (forced_splits > 0) sp = forced_splits;
-  *cfg = mt * 1000 + bn;
+  *cfg = (variant ? variant : mt) * 1000 + bn;
   *splits = sp;
 }
 
@@ -1666,9 +1715,10 @@ extern "C" int uvx_gemm_bf16(const uvx_gemm_args* a, uvx_stream_t stream_) {
     // the image was cut for one tile width: that width is the configuration (row sub-tiles still follow the row count)
     UVX_REQUIRE(a->w_tiled == 64 || a->w_tiled == 128 || a->w_tiled == 208 || a->w_tiled == 256, "uvx_gemm_bf16: w_tiled must be 64 / 128 / 208 / 256");
     int mt = cfg / 1000;
+    const int variant = mt >= 6 ? mt : 0;
     if (mt != 1 && mt != 2) mt = (a->a_rows > 128 && a->a_rows <= 256 && a->a_batch == 1) ? 2 : 1;
     if (a->rope_cos) mt = 1;
-    cfg = mt * 1000 + (int)a->w_tiled;
+    cfg = (variant && mt == 2 ? variant : mt) * 1000 + (int)a->w_tiled;
     cm = cn = 1;
     const int64_t tiles = ((a->a_rows + mt * 128 - 1) / (mt * 128)) * a->a_batch * ((a->N + a->w_tiled - 1) / a->w_tiled);
     const int num_kb = (int)((a->K + 63) / 64);
@@ -1697,6 +1747,11 @@ extern "C" int uvx_gemm_bf16(const uvx_gemm_args* a, uvx_stream_t stream_) {
     case 4256: return launch_gemm_2sm<256, 1, 4>(a, stream);
     case 5416: return launch_gemm_2sm<208, 2, 4>(a, stream);   // 256 x 416 pair tiles (weight-streaming regime)
     case 5512: return launch_gemm_2sm<256, 2, 8>(a, stream);   // 256 x 512 pair tiles (tensor-bound regime)
+    case 6208: return launch_gemm<2, 208, 8, false>(a, splits, 1, 1, stream);   // tuning variants (uvx_debug_gemm_override)
+    case 6128: return launch_gemm<2, 128, 8, false>(a, splits, 1, 1, stream);
+    case 7208: return launch_gemm<2, 208, 0, true>(a, splits, 1, 1, stream);
+    case 7128: return launch_gemm<2, 128, 0, true>(a, splits, 1, 1, stream);
+    case 8208: return launch_gemm<2, 208, 8, true>(a, splits, 1, 1, stream);
     default: return launch_gemm<1, 64>(a, splits, cm, cn, stream);
   }
 }
