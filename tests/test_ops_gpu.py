@@ -548,3 +548,26 @@ def test_gemm_fused_rope_bit_exact(ops, tiled, M, S, past, with_pos):
     rope = (cos, sin, positions, S, past, (Hq + Hkv) * D)
     got = ops.linear_tiled(x, ops.TiledWeight(w, 128), rope=rope) if tiled else ops.linear(x, w, rope=rope)
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("M,N,K", [(201, 6144, 1024), (201, 28672, 512), (1500, 5120, 640), (77, 192, 200), (300, 1984, 256), (128, 64, 64)])
+def test_gemm_tma_store_epilogue_bit_identical(ops, M, N, K):
+    """bf16 outputs in plain row order leave through TMA stores (32 x 32 boxes, rows / columns past the matrix clipped by the
+    tensor map); same arithmetic as the transposing epilogue -> identical bits, with bias + GELU, ragged 208-wide tiles and
+    M / N tails, and nothing written outside the output."""
+    from ultravox_b200 import _lib
+    x, w, b = rnd(M, K, seed=1), rnd(N, K, scale=0.05, seed=2), rnd(N, seed=3)
+    res = {}
+    for on in (1, 0):
+        _lib.lib().uvx_debug_gemm_tma_store(on)
+        try:
+            guard = torch.full((M + 2, N + 64), 7.0, dtype=BF, device="cuda")     # output is a window of a larger buffer
+            out = guard[1:M + 1, :N]
+            ops.linear(x, w, out=out)
+            res[on] = (out.clone(), ops.linear(x, w, bias=b, act=ops.ACT_GELU), guard)
+        finally:
+            _lib.lib().uvx_debug_gemm_tma_store(1)
+    assert torch.equal(res[1][0], res[0][0]) and torch.equal(res[1][1], res[0][1])
+    assert rel(res[1][0], x.float() @ w.float().T) < 1e-3
+    g = res[1][2]
+    assert bool((g[0] == 7).all()) and bool((g[M + 1] == 7).all()) and bool((g[:, N:] == 7).all())

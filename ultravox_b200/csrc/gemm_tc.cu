@@ -62,6 +62,9 @@ struct GemmParams {
   const int32_t* rope_pos;
   int64_t rope_rows_per_seq, rope_pos_offset;
   int rope_cols;
+  int tma_store;           // direct epilogue writes bf16 through TMA stores (32 x 32 boxes staged in the per-warp pads)
+  long long* dbg_times;    // DIAG twin only: per CTA {t0 kernel entry, setup done, first stage landed, last MMA issued, accumulators
+                           // complete, epilogue done, globaltimer at entry, smid} (clock64 ticks)
 };
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -212,6 +215,51 @@ __device__ __forceinline__ void tma_load_3d_e(void* dst, const CUtensorMap* tm, 
       "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// TMA store of a shared-memory box (UTMASTG) + bulk-group bookkeeping
+__device__ __forceinline__ void tma_store_2d(const void* src, const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(c0), "r"(c1),
+               "r"(smem_u32(src))
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+// Fast epilogue of one 32-row x 32-column accumulator chunk (bf16 output, plain row order, no residual): alpha, bias, activation in
+// registers, 64 bytes per row into a 2 KB half of the warp's pad, ONE TMA store of the 32 x 32 box (rows past M and columns past N
+// are clipped by the tensor map).  The transposing epilogue_chunk costs ~1400 cycles per chunk on the exposed tail of a one-tile
+// CTA (profiles/r2_ws_times_v2.txt: 24 % of the gate|up kernel); this is a tcgen05.ld, 16 packs, 4 stores and one UTMASTG.
+__device__ __forceinline__ void epilogue_chunk_tma(const GemmParams& p, const CUtensorMap* tmC, const uint32_t* raw, uint8_t* half, int lane,
+                                                   int64_t m_warp0, int64_t n) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
+  if (p.bias) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float t[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(p.bias + n + g * 8), t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[g * 8 + i] += t[i];
+    }
+  }
+  if (p.act == UVX_ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(half + lane * 64);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const bf16x8 pk = pack8(v + 8 * g);
+    dst[g] = *reinterpret_cast<const uint4*>(&pk);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) tma_store_2d(half, tmC, (int)n, (int)m_warp0);
+}
+
 // L2 prefetch of a tensor-map box (UTMAPF.L2): same addressing as the load, no shared-memory destination, no barrier
 __device__ __forceinline__ void tma_prefetch_2d_e(const CUtensorMap* tm, int c0, int c1) {
   asm volatile(
@@ -399,8 +447,11 @@ struct SmemLayout {
 // gemm_tc_kernel_x; never on the product path.
 template <int MT, int BN, int EW = 0, bool DIAG = false>
 __global__ void __launch_bounds__(SmemLayout<MT, BN, EW>::kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmC,
+               const GemmParams p) {
   pdl_trigger();
+  long long t_entry = 0;
+  if constexpr (DIAG) t_entry = clock64();
   using L = SmemLayout<MT, BN, EW>;
   constexpr int kAcc = L::kAcc;
   constexpr int kEpiWarps = L::kEpiWarps;
@@ -443,6 +494,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // set-up above overlapped the previous kernel's tail; its outputs are visible after griddepcontrol.wait.  The producer warp
   // delays its own wait until the first weight prefetches are issued (weights do not depend on the previous kernel).
   if (warp != 0) pdl_wait();
+  if constexpr (DIAG) {
+    if (p.dbg_times && threadIdx.x == 64) {
+      long long* t = p.dbg_times + (size_t)blockIdx.x * 8;
+      unsigned long long gt;
+      unsigned smid;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      t[0] = t_entry;
+      t[1] = clock64();
+      t[6] = (long long)gt;
+      t[7] = (long long)smid;
+    }
+  }
 
   if (warp == 0) {
     // ---- TMA producer: all 32 lanes run the loop (convergent), elect.sync issues
@@ -527,6 +591,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           if constexpr (DIAG) {
+            if (p.dbg_times && lane == 0 && kb == kb_begin && tcount == 0) p.dbg_times[(size_t)blockIdx.x * 8 + 2] = clock64();
             if (p.dbg_mode == 1) {  // loads only: free the slot at once
               if (lane == 0) mbar_arrive(&empty_bar[s]);
               __syncwarp();
@@ -551,6 +616,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++s == stages) { s = 0; ph ^= 1u; }
         }
         if constexpr (DIAG) {
+          if (p.dbg_times && lane == 0) p.dbg_times[(size_t)blockIdx.x * 8 + 3] = clock64();
           if (p.dbg_mode == 1) {
             if (lane == 0) mbar_arrive(&tmem_full[acc]);
             __syncwarp();
@@ -578,6 +644,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tmem_full[acc], aph);
       tc_fence_after();
       if constexpr (DIAG) {
+        if (p.dbg_times && threadIdx.x == 64) p.dbg_times[(size_t)blockIdx.x * 8 + 4] = clock64();
         if (p.dbg_mode == 1 || p.dbg_mode == 3) {  // no epilogue work: hand the accumulator stage straight back
           tc_fence_before();
           __syncwarp();
@@ -615,6 +682,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       float* pad = reinterpret_cast<float*>(smem + L::kPadOff) + (warp - 2) * (kStageBytesPerWarp / 4);
       const int64_t n_lim = (int64_t)n0 + BN < p.N ? (int64_t)n0 + BN : p.N;  // ragged last column tile (N % BN != 0)
       bool handled = false;
+      uint8_t* pad8 = reinterpret_cast<uint8_t*>(pad);
+      uint32_t nstore = 0;   // TMA stores issued by this warp for this tile (pad halves alternate)
       if constexpr (BN == 208) {
         if (p.swiglu) {  // warp-uniform: tile columns are (8 gate | 8 up) groups, BN / 2 finished activations per row
           handled = true;
@@ -666,8 +735,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
               }
             }
-            epilogue_chunk(p, r0, pad, lane, b, m_warp0, (int64_t)n0 + cpar * 32, n_lim);
-            epilogue_chunk(p, r1, pad, lane, b, m_warp0, (int64_t)n0 + 64 + cpar * 32, n_lim);
+            if (p.tma_store) {
+              epilogue_chunk_tma(p, &tmC, r0, pad8, lane, m_warp0, (int64_t)n0 + cpar * 32);
+              epilogue_chunk_tma(p, &tmC, r1, pad8 + 2048, lane, m_warp0, (int64_t)n0 + 64 + cpar * 32);
+              nstore = 2;
+            } else {
+              epilogue_chunk(p, r0, pad, lane, b, m_warp0, (int64_t)n0 + cpar * 32, n_lim);
+              epilogue_chunk(p, r1, pad, lane, b, m_warp0, (int64_t)n0 + 64 + cpar * 32, n_lim);
+            }
           }
         }
       }
@@ -682,7 +757,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t raw[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * L::kBNT) + (uint32_t)(mt * L::kBNT + c * 32), raw);
             tmem_ld_wait();
-            epilogue_chunk(p, raw, pad, lane, b, m_warp0, (int64_t)n0 + c * 32, n_lim);
+            if (p.tma_store && (int64_t)n0 + c * 32 + 32 <= n_lim) {
+              // the half written now was last read by the store issued two chunks ago
+              if (nstore >= 2) {
+                if (lane == 0) tma_store_wait_read<1>();
+                __syncwarp();
+              }
+              epilogue_chunk_tma(p, &tmC, raw, pad8 + (nstore & 1u) * 2048, lane, m_warp0, (int64_t)n0 + c * 32);
+              ++nstore;
+            } else {
+              if (nstore > 0) {   // the transposing path uses the whole pad: drain the stores that still read it
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+                nstore = 0;
+              }
+              epilogue_chunk(p, raw, pad, lane, b, m_warp0, (int64_t)n0 + c * 32, n_lim);
+            }
           }
         }
       }
@@ -690,10 +780,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (nstore > 0) {   // shared memory of the pads must outlive the bulk reads (next tile / CTA exit)
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (DIAG) {
+    if (p.dbg_times && threadIdx.x == 64) {
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      p.dbg_times[(size_t)blockIdx.x * 8 + 5] = clock64();
+      p.dbg_times[(size_t)blockIdx.x * 8 + 7] = (long long)gt;   // with [6]: wall-clock length of the CTA -> SM clock during the kernel
+    }
+  }
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L::kTmemCols)
                  : "memory");
@@ -1358,6 +1460,28 @@ static int encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_
   return UVX_OK;
 }
 
+// 2-D bf16 tensor map without swizzle (output boxes of the TMA-store epilogue)
+static int encode_map_plain(CUtensorMap* tm, const void* base, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return UVX_ERR_CUDA;
+  }
+  cuuint64_t gd[2] = {dims[0], dims[1]};
+  cuuint64_t gs[1] = {strides_bytes[0]};
+  cuuint32_t bx[2] = {box[0], box[1]}, es[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (output map) failed with CUresult %d (dims %llu %llu stride %llu)", (int)r, (unsigned long long)dims[0],
+              (unsigned long long)dims[1], (unsigned long long)strides_bytes[0]);
+    return UVX_ERR_CUDA;
+  }
+  return UVX_OK;
+}
+
+static int g_gemm_tma_store = 1;  // tuning switch (uvx_debug_gemm_tma_store): 0 = always the transposing epilogue
+
 static int num_sms() {
   static int n = 0;
   if (!n) {
@@ -1380,6 +1504,7 @@ static int gemm_pf() {
 }
 
 static int g_gemm_stage_cap = 0;  // tuning only (uvx_debug_gemm_stages): upper bound on the ring depth
+static long long* g_gemm_times = nullptr;  // tuning only (uvx_debug_gemm_times): device buffer [grid][8] of the DIAG twin
 
 template <int MT, int BN, int EW = 0, bool DIAG = false>
 static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaStream_t stream) {
@@ -1418,7 +1543,21 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
     if (rc) return rc;
   }
   GemmParams p;
+  // bf16 output in plain row order without residual: the epilogue stores 32 x 32 boxes by TMA (tensor map of C, no swizzle: the
+  // 64-byte box rows are written by 32 lanes with at most a 4-way bank conflict on four stores per chunk)
+  CUtensorMap tmC = tmA;
+  p.tma_store = 0;
+  if (a->out_dtype == UVX_DT_BF16 && !a->R && !a->c_row_map && a->a_batch == 1 && a->c_row_offset == 0 && a->act != UVX_ACT_SWIGLU &&
+      cm == 1 && cn == 1 && g_gemm_tma_store) {
+    uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->a_rows};
+    uint64_t st[1] = {(uint64_t)a->c_row_stride * 2};
+    uint32_t box[2] = {32, 32};
+    int rc = encode_map_plain(&tmC, a->C, dims, st, box);
+    if (rc) return rc;
+    p.tma_store = 1;
+  }
   p.w_tiled = tiled ? 1 : 0;
+  p.dbg_times = DIAG ? g_gemm_times : nullptr;
   p.pf = gemm_pf();
   p.swiglu = a->act == UVX_ACT_SWIGLU ? 1 : 0;
   p.rope_cos = a->rope_cos;
@@ -1489,7 +1628,7 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
   if (csize == 1) {
     const int grid = units < num_sms() ? units : num_sms();
     if (p.dbg_mode && !DIAG && EW == 0) launch_k(gemm_tc_kernel_x<MT, BN>, dim3((unsigned)grid), dim3(SmemLayout<MT, BN>::kThreads), kSmemTotal, stream, tmA, tmW, p);
-    else launch_k(gemm_tc_kernel<MT, BN, EW, DIAG>, dim3((unsigned)grid), dim3(L::kThreads), kSmemTotal, stream, tmA, tmW, p);
+    else launch_k(gemm_tc_kernel<MT, BN, EW, DIAG>, dim3((unsigned)grid), dim3(L::kThreads), kSmemTotal, stream, tmA, tmW, tmC, p);
   } else {
     static int max_clusters[9] = {0};
     if (max_clusters[csize] == 0) {
@@ -1610,6 +1749,18 @@ extern "C" int uvx_debug_gemm_override(int cfg, int splits) {
 // tuning hook: 1 = run the 1-SM kernel without its MMAs, 2 = without its TMA loads (results are garbage; timing only)
 extern "C" int uvx_debug_gemm_mode(int mode) {
   uvx::g_gemm_dbg = mode;
+  return UVX_OK;
+}
+
+// tuning hook: 1 = TMA-store epilogue where eligible (default), 0 = transposing epilogue everywhere
+extern "C" int uvx_debug_gemm_tma_store(int on) {
+  uvx::g_gemm_tma_store = on;
+  return UVX_OK;
+}
+
+// tuning hook: device buffer [grid][8] int64 the DIAG twin (cfg 7xxx / 8xxx) fills with per-CTA phase timestamps (NULL = off)
+extern "C" int uvx_debug_gemm_times(void* dev_buf) {
+  uvx::g_gemm_times = (long long*)dev_buf;
   return UVX_OK;
 }
 
