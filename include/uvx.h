@@ -9,9 +9,11 @@
  * Conventions
  *   - plain pointers + sizes only; all pointers are DEVICE pointers unless named host_*;
  *   - bf16 tensors are passed as `const void*` / `void*` (2-byte elements, row-major);
- *   - every call is asynchronous on `stream` (a cudaStream_t), allocates nothing, performs no host
- *     synchronisation and keeps no mutable global state (immutable per-device tables - twiddles, mel
- *     filters - are built once on first use);
+ *   - every call is asynchronous on `stream` (a cudaStream_t), allocates nothing and performs no host
+ *     synchronisation.  Process-wide state: immutable per-device tables (twiddles, mel filters) built once on
+ *     first use, and the uvx_debug_* tuning hooks (tile / split / pipeline-isolation overrides - process
+ *     globals, for benchmarking only: leave them at their defaults in production).  The split-K workspace is
+ *     the CALLER's buffer (uvx_gemm_args.workspace): one workspace per stream if GEMMs run concurrently;
  *   - returns 0 on success, a negative UVX_ERR_* otherwise; `uvx_last_error()` gives the message
  *     (thread-local).  Argument validation that the reference does in Python stays in Python.
  */

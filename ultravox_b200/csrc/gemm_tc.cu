@@ -227,12 +227,20 @@ __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
-// Fast epilogue of one 32-row x 32-column accumulator chunk (bf16 output, plain row order, no residual): alpha, bias, activation in
-// registers, 64 bytes per row into a 2 KB half of the warp's pad, ONE TMA store of the 32 x 32 box (rows past M and columns past N
+// Fast epilogue of one 32-row x 32-column accumulator chunk (bf16 output, plain row order): alpha, bias, activation, residual in
+// registers (+ the residual row of the lane), 64 bytes per row into a 2 KB half of the warp's pad, ONE TMA store of the 32 x 32 box (rows past M and columns past N
 // are clipped by the tensor map).  The transposing epilogue_chunk costs ~1400 cycles per chunk on the exposed tail of a one-tile
 // CTA (profiles/r2_ws_times_v2.txt: 24 % of the gate|up kernel); this is a tcgen05.ld, 16 packs, 4 stores and one UTMASTG.
 __device__ __forceinline__ void epilogue_chunk_tma(const GemmParams& p, const CUtensorMap* tmC, const uint32_t* raw, uint8_t* half, int lane,
                                                    int64_t m_warp0, int64_t n) {
+  // residual row of this lane (64 contiguous bytes), issued first so its latency hides behind the math
+  uint4 rres[4];
+  const bool has_r = p.R != nullptr && m_warp0 + lane < p.a_rows;
+  if (has_r) {
+    const uint4* rr = reinterpret_cast<const uint4*>(p.R + (m_warp0 + lane) * p.r_row_stride + n);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) rres[g] = rr[g];
+  }
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
@@ -249,6 +257,15 @@ __device__ __forceinline__ void epilogue_chunk_tma(const GemmParams& p, const CU
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
   }
+  if (has_r) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float t[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(&rres[g]), t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[g * 8 + i] += t[i];
+    }
+  }
   uint4* dst = reinterpret_cast<uint4*>(half + lane * 64);
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -258,6 +275,31 @@ __device__ __forceinline__ void epilogue_chunk_tma(const GemmParams& p, const CU
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncwarp();
   if (lane == 0) tma_store_2d(half, tmC, (int)n, (int)m_warp0);
+}
+
+// Fused SwiGLU, fast form: 16 finished activations per row and chunk -> 32 bytes per row into a 1 KB slice of the pad -> one
+// TMA store of the 32-row x 16-column box of the [M, N/2] output.
+__device__ __forceinline__ void epilogue_chunk_swiglu_tma(const GemmParams& p, const CUtensorMap* tmC, const uint32_t* raw, uint8_t* slice,
+                                                          int lane, int64_t m_warp0, int64_t n_out) {
+  float o[16];
+#pragma unroll
+  for (int g2 = 0; g2 < 2; ++g2) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float gate = __bfloat162float(__float2bfloat16_rn(__uint_as_float(raw[g2 * 16 + i]) * p.alpha));
+      const float up = __bfloat162float(__float2bfloat16_rn(__uint_as_float(raw[g2 * 16 + 8 + i]) * p.alpha));
+      o[g2 * 8 + i] = __bfloat162float(__float2bfloat16_rn(silu(gate))) * up;
+    }
+  }
+  uint4* dst = reinterpret_cast<uint4*>(slice + lane * 32);
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const bf16x8 pk = pack8(o + 8 * g);
+    dst[g] = *reinterpret_cast<const uint4*>(&pk);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) tma_store_2d(slice, tmC, (int)n_out, (int)m_warp0);
 }
 
 // L2 prefetch of a tensor-map box (UTMAPF.L2): same addressing as the load, no shared-memory destination, no barrier
@@ -699,7 +741,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               uint32_t raw[32];
               tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * L::kBNT) + (uint32_t)(mt * L::kBNT + c * 32), raw);
               tmem_ld_wait();
-              epilogue_chunk_swiglu(p, raw, pad, lane, b, m_warp0, n_out0 + c * 16, n_out_lim);
+              if (p.tma_store && c * 32 + 32 <= BN && n_out0 + c * 16 + 16 <= n_out_lim) {
+                if (nstore >= 4) {   // four 1 KB slices rotate: the one written now was read by the store issued four chunks ago
+                  if (lane == 0) tma_store_wait_read<3>();
+                  __syncwarp();
+                }
+                epilogue_chunk_swiglu_tma(p, &tmC, raw, pad8 + (nstore & 3u) * 1024, lane, m_warp0, n_out0 + c * 16);
+                ++nstore;
+              } else {
+                if (nstore > 0) {
+                  if (lane == 0) tma_store_wait_read<0>();
+                  __syncwarp();
+                  nstore = 0;
+                }
+                epilogue_chunk_swiglu(p, raw, pad, lane, b, m_warp0, n_out0 + c * 16, n_out_lim);
+              }
             }
           }
         }
@@ -1375,11 +1431,24 @@ __global__ void __launch_bounds__(256) splitk_reduce_rmsnorm_kernel(const GemmPa
       const float* src = p.ws_partial + (size_t)r * p.N + n;
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
-      for (int sidx = 0; sidx < p.splits; ++sidx) {
-        const float4 t0 = __ldcg(reinterpret_cast<const float4*>(src + sidx * split_stride));
-        const float4 t1 = __ldcg(reinterpret_cast<const float4*>(src + sidx * split_stride) + 1);
-        v[i][0] += t0.x; v[i][1] += t0.y; v[i][2] += t0.z; v[i][3] += t0.w;
-        v[i][4] += t1.x; v[i][5] += t1.y; v[i][6] += t1.z; v[i][7] += t1.w;
+      // loads of four splits are issued together (the kernel is a latency chain: partials -> row sum -> write), sums stay in
+      // split order so the result does not depend on the batching
+      for (int s0 = 0; s0 < p.splits; s0 += 4) {
+        float4 t0[4], t1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (s0 + u < p.splits) {
+            t0[u] = __ldcg(reinterpret_cast<const float4*>(src + (s0 + u) * split_stride));
+            t1[u] = __ldcg(reinterpret_cast<const float4*>(src + (s0 + u) * split_stride) + 1);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (s0 + u < p.splits) {
+            v[i][0] += t0[u].x; v[i][1] += t0[u].y; v[i][2] += t0[u].z; v[i][3] += t0[u].w;
+            v[i][4] += t1[u].x; v[i][5] += t1[u].y; v[i][6] += t1[u].z; v[i][7] += t1[u].w;
+          }
+        }
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[i][e] *= p.alpha;
@@ -1547,11 +1616,11 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
   // 64-byte box rows are written by 32 lanes with at most a 4-way bank conflict on four stores per chunk)
   CUtensorMap tmC = tmA;
   p.tma_store = 0;
-  if (a->out_dtype == UVX_DT_BF16 && !a->R && !a->c_row_map && a->a_batch == 1 && a->c_row_offset == 0 && a->act != UVX_ACT_SWIGLU &&
-      cm == 1 && cn == 1 && g_gemm_tma_store) {
-    uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->a_rows};
+  if (a->out_dtype == UVX_DT_BF16 && !a->c_row_map && a->a_batch == 1 && a->c_row_offset == 0 && cm == 1 && cn == 1 && g_gemm_tma_store) {
+    const bool sw = a->act == UVX_ACT_SWIGLU;   // [M, N/2] output, 16 columns per accumulator chunk
+    uint64_t dims[2] = {(uint64_t)(sw ? a->N / 2 : a->N), (uint64_t)a->a_rows};
     uint64_t st[1] = {(uint64_t)a->c_row_stride * 2};
-    uint32_t box[2] = {32, 32};
+    uint32_t box[2] = {sw ? 16u : 32u, 32};
     int rc = encode_map_plain(&tmC, a->C, dims, st, box);
     if (rc) return rc;
     p.tma_store = 1;

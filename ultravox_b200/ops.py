@@ -74,12 +74,21 @@ GEMM_WS_BYTES = 160 << 20
 
 
 def gemm_workspace(device) -> torch.Tensor:
-    """Per-device split-K workspace (counters must start at zero; the kernel keeps them zero)."""
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    """Split-K workspace of the CURRENT stream on ``device`` (fp32 partial sums; contents on entry do not matter).  One buffer per
+    (device, stream): GEMMs issued on different streams - e.g. ``infer_stream``'s generation thread next to the main thread,
+    ref infer.py:227-241 - never share partial sums.  Kernels recorded into CUDA graphs use one more buffer per device (graph
+    replays are serialised by the engines); it is created together with the first eager workspace so that it never comes out of
+    a graph's private memory pool."""
+    idx = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    capturing = torch.cuda.is_current_stream_capturing()
+    key = (idx, "graph") if capturing else (idx, torch.cuda.current_stream(idx).cuda_stream)
     ws = _GEMM_WS.get(key)
     if ws is None:
-        ws = torch.zeros(GEMM_WS_BYTES, dtype=torch.uint8, device=torch.device("cuda", key))
-        _GEMM_WS[key] = ws
+        with torch.cuda.device(idx):
+            ws = torch.zeros(GEMM_WS_BYTES, dtype=torch.uint8, device=torch.device("cuda", idx))
+            _GEMM_WS[key] = ws
+            if not capturing and (idx, "graph") not in _GEMM_WS:
+                _GEMM_WS[(idx, "graph")] = torch.zeros(GEMM_WS_BYTES, dtype=torch.uint8, device=torch.device("cuda", idx))
     return ws
 
 
