@@ -175,6 +175,9 @@ typedef struct uvx_attn_args {
                                     /* (ref collator ultravox_processing.py:53-63; hf masking_utils padding mask)       */
 } uvx_attn_args;
 int uvx_attention(const uvx_attn_args* args, uvx_stream_t stream);
+/* head_dim 128 with a tile of queries per head (Llama prefill / training) runs on tcgen05 tensor cores with TMEM accumulators
+ * (attention_llm_tc.cu); single-token decode steps and head_dim 64 on mma.sync.  Tuning hook: 0 forces mma.sync everywhere. */
+int uvx_debug_attn_tc(int on);
 /* Whisper-encoder specialisation on tcgen05 tensor cores (head_dim 64, Sq == Skv, non-causal + key-length / block-causal
  * masks): qkv is the fused projection [B*S, row_stride] with head h's q / k / v at columns q_col + 64h, k_col + 64h,
  * v_col + 64h; output o[b*S + i, 64h .. 64h+63] (row stride o_rs).  Same math as uvx_attention.                      */

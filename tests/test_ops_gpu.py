@@ -272,6 +272,47 @@ def test_attention_left_padding(ops, B, Hq, Hkv, S, D):
         assert torch.count_nonzero(out[b, :p0]) == 0
 
 
+@pytest.mark.parametrize("B,Hq,Hkv,S,causal,ragged", [(1, 32, 8, 201, True, False), (2, 8, 2, 128, True, False), (1, 4, 4, 129, True, False),
+                                                       (2, 8, 2, 640, True, True), (1, 4, 1, 300, False, True), (3, 4, 2, 77, True, True)])
+def test_attention_llm_tcgen05(ops, B, Hq, Hkv, S, causal, ragged):
+    """tcgen05 / TMEM causal GQA attention (head_dim 128) against fp32 math, against the mma.sync kernel, with the log-sum-exp the
+    training backward reads, and in the KV-cache form (separate K / V buffers longer than the query block)."""
+    from ultravox_b200 import _lib
+    D = 128
+    W = (Hq + 2 * Hkv) * D
+    qkv = rnd(B * S, W, seed=3)
+    kv_len = torch.tensor([S, max(1, S // 3), S - 1][:B], dtype=torch.int32).cuda() if ragged else None
+    t = qkv.view(B, S, Hq + 2 * Hkv, D).permute(0, 2, 1, 3)
+    ref = _attn_ref(t[:, :Hq], t[:, Hq:Hq + Hkv], t[:, Hq + Hkv:], D ** -0.5, causal, kv_len).permute(0, 2, 1, 3).reshape(B * S, Hq * D)
+    out = torch.empty(B * S, Hq * D, dtype=BF, device="cuda")
+    lse = torch.empty(B * Hq * S, dtype=torch.float32, device="cuda")
+    ops.attention_fused_qkv_train(qkv, B, S, Hq, Hkv, D, D ** -0.5, causal, out, lse, kv_len)
+    _lib.lib().uvx_debug_attn_tc(0)
+    try:
+        out_mma = torch.empty_like(out)
+        lse_mma = torch.empty_like(lse)
+        ops.attention_fused_qkv_train(qkv, B, S, Hq, Hkv, D, D ** -0.5, causal, out_mma, lse_mma, kv_len)
+    finally:
+        _lib.lib().uvx_debug_attn_tc(-1)
+    valid = torch.ones(B, S, dtype=torch.bool, device="cuda")
+    assert rel(out, ref) < 3e-3, rel(out, ref)
+    assert rel(out, out_mma.float()) < 3e-3
+    assert float((lse - lse_mma).abs().max()) < 2e-3
+    # KV-cache form: query block of 70 rows at the end of a longer key sequence (shift = Skv - Sq > 0), strided cache buffers
+    if causal and S > 80 and not ragged:
+        Sq = 70
+        kc = torch.zeros(B, S + 9, Hkv, D, dtype=BF, device="cuda")
+        vc = torch.zeros_like(kc)
+        t4 = qkv.view(B, S, Hq + 2 * Hkv, D)
+        kc[:, :S], vc[:, :S] = t4[:, :, Hq:Hq + Hkv], t4[:, :, Hq + Hkv:]
+        qb = t4[:, S - Sq:, :Hq].contiguous()                           # [B, Sq, Hq, D]
+        o2 = torch.empty(B * Sq, Hq * D, dtype=BF, device="cuda")
+        smax = S + 9
+        ops.attention(qb.data_ptr(), kc.data_ptr(), vc.data_ptr(), o2, B, Hq, Hkv, Sq, S, D,
+                      (Hq * D, Sq * Hq * D, Hkv * D, smax * Hkv * D, Hkv * D, smax * Hkv * D, Hq * D, Sq * Hq * D), D ** -0.5, True)
+        assert rel(o2.view(B, Sq, -1), ref.view(B, S, -1)[:, S - Sq:]) < 3e-3
+
+
 @pytest.mark.parametrize("B,H,S,block,ragged", [(1, 2, 128, 0, False), (1, 3, 256, 0, False), (2, 6, 50, 0, True),
                                                  (1, 20, 1500, 0, False), (2, 4, 300, 100, True), (3, 2, 700, 0, True)])
 def test_attention_encoder_tcgen05(ops, B, H, S, block, ragged):

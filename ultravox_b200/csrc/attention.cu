@@ -5,6 +5,8 @@
 // indices (key length per clip, causal offset, block-causal streaming) - no dense mask tensor is read, and
 // key tiles that are fully masked are skipped.  (A tcgen05/TMEM version of this kernel is the next step for
 // the encoder's T=1500 attention; at S=201 the LLM attention is latency-bound either way.)
+#include <stdlib.h>
+
 #include "uvx_common.cuh"
 
 namespace uvx {
@@ -274,7 +276,16 @@ static int launch_attn(const uvx_attn_args* a, cudaStream_t st) {
   return check_launch("attn_fwd_kernel");
 }
 
+int launch_attn_llm_tc(const uvx_attn_args* a, cudaStream_t st);  // attention_llm_tc.cu (tcgen05, head_dim 128, prefill shapes)
+static int g_attn_tc = -1;                                          // UVX_ATTN_TC=0 keeps every shape on the mma.sync kernel (A/B runs)
+
 }  // namespace uvx
+
+// tuning hook: 1 = tcgen05 kernel for head_dim 128 prefill shapes (default), 0 = mma.sync kernel everywhere, -1 = UVX_ATTN_TC / default
+extern "C" int uvx_debug_attn_tc(int on) {
+  uvx::g_attn_tc = on;
+  return UVX_OK;
+}
 
 extern "C" int uvx_attention(const uvx_attn_args* a, uvx_stream_t stream) {
   using namespace uvx;
@@ -288,5 +299,13 @@ extern "C" int uvx_attention(const uvx_attn_args* a, uvx_stream_t stream) {
               "uvx_attention: strides must keep 16-byte alignment");
   UVX_REQUIRE(((uintptr_t)a->q | (uintptr_t)a->k | (uintptr_t)a->v) % 16 == 0 && (uintptr_t)a->o % 4 == 0,
               "uvx_attention: base pointers must be 16-byte aligned");
+  if (g_attn_tc < 0) {
+    const char* e = getenv("UVX_ATTN_TC");
+    g_attn_tc = e ? atoi(e) : 1;
+  }
+  // Llama prefill / training shapes (head_dim 128, a tile of queries per head): tcgen05 + TMEM kernel; single-token decode steps and
+  // head_dim 64 (Llama-3.2-1B) stay on the mma.sync kernel below
+  if (g_attn_tc && a->D == 128 && a->Sq >= 16 && a->block == 0 && a->o_rs % 8 == 0 && (uintptr_t)a->o % 16 == 0)
+    return launch_attn_llm_tc(a, (cudaStream_t)stream);
   return a->D == 64 ? launch_attn<64>(a, (cudaStream_t)stream) : launch_attn<128>(a, (cudaStream_t)stream);
 }

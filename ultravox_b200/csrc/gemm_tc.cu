@@ -222,6 +222,12 @@ __device__ __forceinline__ void tma_store_2d(const void* src, const CUtensorMap*
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const void* src, const CUtensorMap* tm, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2),
+               "r"(smem_u32(src))
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
@@ -699,6 +705,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // split-K: park the raw fp32 partial tile in the workspace; splitk_reduce_kernel sums the splits in a fixed
         // order and applies the epilogue (deterministic, and the reduction is spread over every SM)
         float* part = p.ws_partial + (size_t)split * (size_t)(p.a_batch * p.a_rows) * (size_t)p.N;
+        uint32_t pstore = 0;
 #pragma unroll 1
         for (int mt = 0; mt < MT; ++mt) {
           if ((int64_t)m0 + mt * kBM + q * 32 >= p.a_rows) continue;
@@ -709,7 +716,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t raw[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * L::kBNT) + (uint32_t)(mt * L::kBNT + c * 32), raw);
             tmem_ld_wait();
-            if (row_ok) {
+            if (p.tma_store) {
+              // fp32 partial tile through the pad as two 32-row x 16-column boxes (64-byte rows), TMA-stored into
+              // [split][row][col]; rows past M are clipped by the map
+              uint8_t* pd = smem + L::kPadOff + (warp - 2) * kStageBytesPerWarp;
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                if (pstore >= 2) {
+                  if (lane == 0) tma_store_wait_read<1>();
+                  __syncwarp();
+                }
+                uint4* dsts = reinterpret_cast<uint4*>(pd + (pstore & 1u) * 2048 + lane * 64);
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                  dsts[g] = make_uint4(raw[hh * 16 + 4 * g], raw[hh * 16 + 4 * g + 1], raw[hh * 16 + 4 * g + 2], raw[hh * 16 + 4 * g + 3]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) tma_store_3d(pd + (pstore & 1u) * 2048, &tmC, n0 + c * 32 + hh * 16, m0 + mt * kBM + q * 32, split);
+                ++pstore;
+              }
+            } else if (row_ok) {
               uint4* dst = reinterpret_cast<uint4*>(part + ((size_t)b * p.a_rows + m) * p.N + n0 + c * 32);
 #pragma unroll
               for (int g = 0; g < 8; ++g) dst[g] = make_uint4(raw[4 * g], raw[4 * g + 1], raw[4 * g + 2], raw[4 * g + 3]);
@@ -719,6 +745,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);  // accumulator stage is free again
+        if (pstore > 0) {
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+          pstore = 0;
+        }
         continue;
       }
       float* pad = reinterpret_cast<float*>(smem + L::kPadOff) + (warp - 2) * (kStageBytesPerWarp / 4);
@@ -1529,17 +1560,19 @@ static int encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_
   return UVX_OK;
 }
 
-// 2-D bf16 tensor map without swizzle (output boxes of the TMA-store epilogue)
-static int encode_map_plain(CUtensorMap* tm, const void* base, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+// tensor map without swizzle (output boxes of the TMA-store epilogue): rank 2 bf16 (C) or rank 3 fp32 (split-K partials)
+static int encode_map_plain(CUtensorMap* tm, const void* base, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                            int rank = 2, bool f32 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
     return UVX_ERR_CUDA;
   }
-  cuuint64_t gd[2] = {dims[0], dims[1]};
-  cuuint64_t gs[1] = {strides_bytes[0]};
-  cuuint32_t bx[2] = {box[0], box[1]}, es[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  cuuint64_t gd[3] = {dims[0], dims[1], rank > 2 ? dims[2] : 1};
+  cuuint64_t gs[2] = {strides_bytes[0], rank > 2 ? strides_bytes[1] : 0};
+  cuuint32_t bx[3] = {box[0], box[1], 1}, es[3] = {1, 1, 1};
+  CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd,
+                   gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (output map) failed with CUresult %d (dims %llu %llu stride %llu)", (int)r, (unsigned long long)dims[0],
@@ -1612,19 +1645,8 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
     if (rc) return rc;
   }
   GemmParams p;
-  // bf16 output in plain row order without residual: the epilogue stores 32 x 32 boxes by TMA (tensor map of C, no swizzle: the
-  // 64-byte box rows are written by 32 lanes with at most a 4-way bank conflict on four stores per chunk)
   CUtensorMap tmC = tmA;
   p.tma_store = 0;
-  if (a->out_dtype == UVX_DT_BF16 && !a->c_row_map && a->a_batch == 1 && a->c_row_offset == 0 && cm == 1 && cn == 1 && g_gemm_tma_store) {
-    const bool sw = a->act == UVX_ACT_SWIGLU;   // [M, N/2] output, 16 columns per accumulator chunk
-    uint64_t dims[2] = {(uint64_t)(sw ? a->N / 2 : a->N), (uint64_t)a->a_rows};
-    uint64_t st[1] = {(uint64_t)a->c_row_stride * 2};
-    uint32_t box[2] = {sw ? 16u : 32u, 32};
-    int rc = encode_map_plain(&tmC, a->C, dims, st, box);
-    if (rc) return rc;
-    p.tma_store = 1;
-  }
   p.w_tiled = tiled ? 1 : 0;
   p.dbg_times = DIAG ? g_gemm_times : nullptr;
   p.pf = gemm_pf();
@@ -1668,6 +1690,27 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
   p.kb_per_split = (num_kb + splits - 1) / splits;
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
   p.ws_partial = (float*)a->workspace;
+  if (cm == 1 && cn == 1 && g_gemm_tma_store && a->a_batch == 1) {
+    if (p.splits > 1) {
+      // split-K: fp32 partial tiles leave through TMA stores into [split][row][col] (rows past M clipped by the map)
+      uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->a_rows, (uint64_t)p.splits};
+      uint64_t st[2] = {(uint64_t)a->N * 4, (uint64_t)a->a_rows * (uint64_t)a->N * 4};
+      uint32_t box[2] = {16, 32};
+      int rc = encode_map_plain(&tmC, a->workspace, dims, st, box, 3, true);
+      if (rc) return rc;
+      p.tma_store = 1;
+    } else if (a->out_dtype == UVX_DT_BF16 && !a->c_row_map && a->c_row_offset == 0) {
+      // bf16 output in plain row order: the epilogue stores 32 x 32 boxes by TMA (tensor map of C, no swizzle: the 64-byte box
+      // rows are written by 32 lanes with at most a 4-way bank conflict on four stores per chunk); fused SwiGLU: 32 x 16 boxes
+      const bool sw = a->act == UVX_ACT_SWIGLU;   // [M, N/2] output, 16 columns per accumulator chunk
+      uint64_t dims[2] = {(uint64_t)(sw ? a->N / 2 : a->N), (uint64_t)a->a_rows};
+      uint64_t st[1] = {(uint64_t)a->c_row_stride * 2};
+      uint32_t box[2] = {sw ? 16u : 32u, 32};
+      int rc = encode_map_plain(&tmC, a->C, dims, st, box);
+      if (rc) return rc;
+      p.tma_store = 1;
+    }
+  }
   p.a_box_bytes = a_box_rows * kBK * 2;
   p.stage_bytes = p.a_box_bytes + L::kWBytes;
   p.stages = L::kPadOff / p.stage_bytes;
