@@ -568,6 +568,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t ph = 0;
       bool waited = false;
       const int tiled = p.w_tiled;
+      // Programmatic dependent launch: this CTA may be resident while the previous kernel is still running.  Weights do not
+      // depend on it, so the W boxes of the first ring round are requested BEFORE griddepcontrol.wait (their latency - and the
+      // launch / set-up above - hide under the previous kernel's tail); the activation boxes follow after the wait.
+      int pre = 0;
+      if ((int)blockIdx.x < num_units) {
+        const int unit = blockIdx.x;
+        const int tile = unit / p.splits, split = unit % p.splits;
+        const int tn_idx = tile / tiles_m_total;
+        const int kb_begin = split * p.kb_per_split;
+        const int nk = min(num_kb, kb_begin + p.kb_per_split) - kb_begin;
+        const int rot = (int)(((unsigned)tile * 7u + (unsigned)split * 3u) % (unsigned)nk);
+        pre = stages < nk ? stages : nk;
+        for (int i = 0; i < pre; ++i) {
+          const int kb = kb_begin + (i + rot < nk ? i + rot : i + rot - nk);
+          mbar_expect_tx_e(&full_bar[i], (uint32_t)p.stage_bytes);
+          tma_load_2d_e(smem + i * p.stage_bytes + p.a_box_bytes, &tmW, tiled ? 0 : kb * kBK, tiled ? (tn_idx * num_kb + kb) * BN : tn_idx * BN,
+                        &full_bar[i]);
+        }
+      }
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         const int tile = unit / p.splits, split = unit % p.splits;
         const int tm_idx = tile % tiles_m_total;  // consecutive tiles share the W tile
@@ -602,6 +621,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int kbp = kb_begin + (j + rot < nk ? j + rot : j + rot - nk);
             tma_prefetch_2d_e(&tmW, tiled ? 0 : kbp * kBK, tiled ? wt_base + kbp * BN : n0);
           }
+          uint8_t* sa = smem + s * p.stage_bytes;
+          if (pre > 0) {   // first ring round of the first unit: the W box is already in flight, only the activation box is missing
+            --pre;
+            if constexpr (DIAG) {
+              if (p.dbg_mode == 2) {   // (isolation mode: the early W loads still land; nothing else to do)
+                tma_load_3d_e(sa, &tmA, kb * kBK, m0, b, &full_bar[s]);
+                if (++s == stages) { s = 0; ph ^= 1u; }
+                continue;
+              }
+            }
+            tma_load_3d_e(sa, &tmA, kb * kBK, m0, b, &full_bar[s]);
+            if (++s == stages) { s = 0; ph ^= 1u; }
+            continue;
+          }
           mbar_wait(&empty_bar[s], ph ^ 1u);
           if constexpr (DIAG) {
             if (p.dbg_mode == 2) {  // MMAs only: hand the (never loaded) slot over
@@ -611,7 +644,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               continue;
             }
           }
-          uint8_t* sa = smem + s * p.stage_bytes;
           mbar_expect_tx_e(&full_bar[s], (uint32_t)p.stage_bytes);
           tma_load_3d_e(sa, &tmA, kb * kBK, m0, b, &full_bar[s]);
           tma_load_2d_e(sa + p.a_box_bytes, &tmW, tiled ? 0 : kb * kBK, tiled ? wt_base + kb * BN : n0, &full_bar[s]);
