@@ -63,6 +63,9 @@ struct GemmParams {
   int64_t rope_rows_per_seq, rope_pos_offset;
   int rope_cols;
   int tma_store;           // direct epilogue writes bf16 through TMA stores (32 x 32 boxes staged in the per-warp pads)
+  int epi_ring;            // every CTA has at most one unit: once its accumulators are complete the operand ring is idle, and each
+                           // epilogue warp stages its boxes in 16 KB of it (8 stores in flight instead of 2)
+  int pdl;                 // launched with programmatic stream serialization: request the first W boxes before griddepcontrol.wait
   long long* dbg_times;    // DIAG twin only: per CTA {t0 kernel entry, setup done, first stage landed, last MMA issued, accumulators
                            // complete, epilogue done, globaltimer at entry, smid} (clock64 ticks)
 };
@@ -572,7 +575,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // depend on it, so the W boxes of the first ring round are requested BEFORE griddepcontrol.wait (their latency - and the
       // launch / set-up above - hide under the previous kernel's tail); the activation boxes follow after the wait.
       int pre = 0;
-      if ((int)blockIdx.x < num_units) {
+      if (p.pdl && (int)blockIdx.x < num_units) {
         const int unit = blockIdx.x;
         const int tile = unit / p.splits, split = unit % p.splits;
         const int tn_idx = tile / tiles_m_total;
@@ -732,6 +735,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           continue;
         }
       }
+      // staging buffers of the TMA-store epilogue: 2 KB each; two in the warp's pad, or eight in the idle operand ring
+      uint8_t* const epi_pad = smem + L::kPadOff + (warp - 2) * kStageBytesPerWarp;
+      uint8_t* const epi_ring = smem + (warp - 2) * 16384;
+      const bool ring = p.epi_ring != 0;
+      auto epi_acquire = [&](uint32_t n) -> uint8_t* {
+        if (ring) {
+          if (n >= 8) {   // the buffer written now was last read by the store issued eight boxes ago
+            if (lane == 0) tma_store_wait_read<7>();
+            __syncwarp();
+          }
+          return epi_ring + (n & 7u) * 2048;
+        }
+        if (n >= 2) {
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+        }
+        return epi_pad + (n & 1u) * 2048;
+      };
       const bool direct = p.splits == 1;
       if (!direct) {
         // split-K: park the raw fp32 partial tile in the workspace; splitk_reduce_kernel sums the splits in a fixed
@@ -751,20 +772,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.tma_store) {
               // fp32 partial tile through the pad as two 32-row x 16-column boxes (64-byte rows), TMA-stored into
               // [split][row][col]; rows past M are clipped by the map
-              uint8_t* pd = smem + L::kPadOff + (warp - 2) * kStageBytesPerWarp;
 #pragma unroll
               for (int hh = 0; hh < 2; ++hh) {
-                if (pstore >= 2) {
-                  if (lane == 0) tma_store_wait_read<1>();
-                  __syncwarp();
-                }
-                uint4* dsts = reinterpret_cast<uint4*>(pd + (pstore & 1u) * 2048 + lane * 64);
+                uint8_t* buf = epi_acquire(pstore);
+                uint4* dsts = reinterpret_cast<uint4*>(buf + lane * 64);
 #pragma unroll
                 for (int g = 0; g < 4; ++g)
                   dsts[g] = make_uint4(raw[hh * 16 + 4 * g], raw[hh * 16 + 4 * g + 1], raw[hh * 16 + 4 * g + 2], raw[hh * 16 + 4 * g + 3]);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) tma_store_3d(pd + (pstore & 1u) * 2048, &tmC, n0 + c * 32 + hh * 16, m0 + mt * kBM + q * 32, split);
+                if (lane == 0) tma_store_3d(buf, &tmC, n0 + c * 32 + hh * 16, m0 + mt * kBM + q * 32, split);
                 ++pstore;
               }
             } else if (row_ok) {
@@ -787,7 +804,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       float* pad = reinterpret_cast<float*>(smem + L::kPadOff) + (warp - 2) * (kStageBytesPerWarp / 4);
       const int64_t n_lim = (int64_t)n0 + BN < p.N ? (int64_t)n0 + BN : p.N;  // ragged last column tile (N % BN != 0)
       bool handled = false;
-      uint8_t* pad8 = reinterpret_cast<uint8_t*>(pad);
       uint32_t nstore = 0;   // TMA stores issued by this warp for this tile (pad halves alternate)
       if constexpr (BN == 208) {
         if (p.swiglu) {  // warp-uniform: tile columns are (8 gate | 8 up) groups, BN / 2 finished activations per row
@@ -805,14 +821,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * L::kBNT) + (uint32_t)(mt * L::kBNT + c * 32), raw);
               tmem_ld_wait();
               if (p.tma_store && c * 32 + 32 <= BN && n_out0 + c * 16 + 16 <= n_out_lim) {
-                if (nstore >= 4) {   // four 1 KB slices rotate: the one written now was read by the store issued four chunks ago
-                  if (lane == 0) tma_store_wait_read<3>();
-                  __syncwarp();
-                }
-                epilogue_chunk_swiglu_tma(p, &tmC, raw, pad8 + (nstore & 3u) * 1024, lane, m_warp0, n_out0 + c * 16);
+                uint8_t* buf = epi_acquire(nstore);
+                epilogue_chunk_swiglu_tma(p, &tmC, raw, buf, lane, m_warp0, n_out0 + c * 16);
                 ++nstore;
               } else {
-                if (nstore > 0) {
+                if (!ring && nstore > 0) {   // the transposing path uses the whole pad: drain the stores that still read it
                   if (lane == 0) tma_store_wait_read<0>();
                   __syncwarp();
                   nstore = 0;
@@ -855,8 +868,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
             if (p.tma_store) {
-              epilogue_chunk_tma(p, &tmC, r0, pad8, lane, m_warp0, (int64_t)n0 + cpar * 32);
-              epilogue_chunk_tma(p, &tmC, r1, pad8 + 2048, lane, m_warp0, (int64_t)n0 + 64 + cpar * 32);
+              epilogue_chunk_tma(p, &tmC, r0, epi_acquire(0), lane, m_warp0, (int64_t)n0 + cpar * 32);
+              epilogue_chunk_tma(p, &tmC, r1, epi_acquire(1), lane, m_warp0, (int64_t)n0 + 64 + cpar * 32);
               nstore = 2;
             } else {
               epilogue_chunk(p, r0, pad, lane, b, m_warp0, (int64_t)n0 + cpar * 32, n_lim);
@@ -877,15 +890,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * L::kBNT) + (uint32_t)(mt * L::kBNT + c * 32), raw);
             tmem_ld_wait();
             if (p.tma_store && (int64_t)n0 + c * 32 + 32 <= n_lim) {
-              // the half written now was last read by the store issued two chunks ago
-              if (nstore >= 2) {
-                if (lane == 0) tma_store_wait_read<1>();
-                __syncwarp();
-              }
-              epilogue_chunk_tma(p, &tmC, raw, pad8 + (nstore & 1u) * 2048, lane, m_warp0, (int64_t)n0 + c * 32);
+              uint8_t* buf = epi_acquire(nstore);
+              epilogue_chunk_tma(p, &tmC, raw, buf, lane, m_warp0, (int64_t)n0 + c * 32);
               ++nstore;
             } else {
-              if (nstore > 0) {   // the transposing path uses the whole pad: drain the stores that still read it
+              if (!ring && nstore > 0) {   // the transposing path uses the whole pad: drain the stores that still read it
                 if (lane == 0) tma_store_wait_read<0>();
                 __syncwarp();
                 nstore = 0;
@@ -1767,6 +1776,8 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
   }
   const int units = p.m_groups * p.n_groups * p.splits;  // cluster-level work units
   const int csize = cm * cn;
+  p.epi_ring = (p.tma_store && csize == 1 && units <= num_sms() && p.stages * p.stage_bytes >= L::kEpiWarps * 16384) ? 1 : 0;
+  p.pdl = pdl_enabled() ? 1 : 0;
   UVX_REQUIRE(!(p.dbg_mode && csize > 1), "uvx_gemm_bf16: pipeline-isolation modes are for unclustered launches");
   UVX_REQUIRE(EW == 0 || csize == 1, "uvx_gemm_bf16: cluster launches use the default epilogue width");
   if (csize == 1) {
