@@ -197,7 +197,7 @@ class CpuOracle:
                 f"{self.threads} threads" + (f" (sweep s/layer-pair: {({k: round(v, 3) for k, v in self.sweep.items()})})" if self.sweep else ""))
 
 
-def cpu_leg(cfg, wl, args, state=None, gpu_logits=None, gpu_token=None, max_steps=2, warm=0, mel_used=None):
+def cpu_leg(cfg, wl, args, state=None, gpu_logits=None, gpu_token=None, max_steps=2, warm=0, mel_used=None, lib_logits=None):
     """cpu_baseline for the main line (1 timed full-depth step on the GPU model's weights, doubling as the output check) or the
     body of the `--impl reference` arm (random weights, up to `max_steps` timed steps inside --cpu-budget-s)."""
     import numpy as np
@@ -221,12 +221,20 @@ def cpu_leg(cfg, wl, args, state=None, gpu_logits=None, gpu_token=None, max_step
         g = gpu_logits.float().cpu().view(-1)
         rel = float((g - logits).norm() / logits.norm())
         top5 = logits.topk(5).indices.tolist()
+        # end-to-end error against the fp32 oracle is judged against HF's own bf16 forward on the SAME weights and
+        # mel (stock transformers modules on this GPU), both numbers side by side; 3e-2 is the bound when that arm did not run
+        lib_rel = None
+        if lib_logits is not None:
+            lib_rel = float((lib_logits.float().view(-1) - logits).norm() / logits.norm())
+        bound = max(3e-2, 1.25 * lib_rel) if lib_rel is not None else 3e-2
         check = {"what": "GPU engine's last-row logits / token vs the full-depth fp32 CPU oracle on the same weights and clip",
-                 "logits_rel_err": rel, "gpu_token": int(gpu_token), "oracle_token": int(tok),
+                 "logits_rel_err": rel, "library_bf16_logits_rel_err_same_weights": lib_rel, "gpu_token": int(gpu_token),
+                 "oracle_token": int(tok), "library_token": int(lib_logits.argmax()) if lib_logits is not None else None,
                  "gpu_token_in_oracle_top5": int(gpu_token) in top5,
                  "oracle_logit_gap_of_gpu_token": float(logits.max() - logits[int(gpu_token)]),
                  "mel_max_abs_diff_gpu_vs_oracle": getattr(orc, "mel_max_abs_diff", None),
-                 "tolerance": "rel <= 3e-2 (SURVEY 7: HF's own bf16 forward is at 1.3e-2 after 32 layers)", "ok": bool(rel <= 3e-2 and int(gpu_token) in top5)}
+                 "tolerance": "rel <= max(3e-2, 1.25 x the error of HF's own bf16 forward on the same weights) and the token in the oracle's top-5",
+                 "ok": bool(rel <= bound and int(gpu_token) in top5)}
     return out, check
 
 
@@ -290,7 +298,7 @@ def roofline_pass(model, eng, peaks, reps=20):
         hooks[name] = orig
         setattr(ops, name, wrapped)
 
-    for name in ("gemm_raw", "gemm_ws"):
+    for name in ("gemm_raw", "linear_tiled"):
         if hasattr(ops, name):
             record(name)
     try:
@@ -307,8 +315,9 @@ def roofline_pass(model, eng, peaks, reps=20):
             M, K, W, C_t = a[1] * a[2], a[3], a[6], a[7]
             R = k.get("R", a[13] if len(a) > 13 else None)
             return M, W.shape[0], K, C_t.element_size(), R is not None
-        x, W = a[0], a[1]
-        return x.shape[0], int(k.get("n_out", W.shape[0])), x.shape[1], 2, k.get("residual") is not None
+        x, wt = a[0], a[1]                      # ops.linear_tiled(x, TiledWeight, ...): N weight rows, n_out output columns
+        rows = x.numel() // x.shape[-1]
+        return rows, wt.N, x.shape[-1], 2 * (wt.n_out if k.get("act", 0) == ops.ACT_SWIGLU else wt.N) / wt.N, k.get("residual") is not None
 
     def group(pred):
         sel = [c for c in calls if pred(*shape_of(c)[:3])]
@@ -568,7 +577,7 @@ def main():
                 "ttft_ms_p50_cuda_events": per_ev[len(per_ev) // 2], "ttft_iters": n_tt,
                 "gpu_launches": eng.launches_per_step * K, "launches_per_step": eng.launches_per_step,
                 "clocks": clocks, "token_check": tokens_ok, "train": train}
-        state = mel_used = None
+        state = mel_used = lib_logits = None
         if not args.no_cpu_baseline:
             try:      # material for the CPU leg, fetched before anything else touches the allocator
                 from ultravox_b200 import ops
@@ -586,14 +595,16 @@ def main():
             try:
                 sys.path.insert(0, os.path.join(ROOT, "scripts"))
                 import hf_gpu_baseline
-                line["gpu_library_baseline"] = hf_gpu_baseline.run(cfg, wl, dev, iters=20, warmup=3)
+                lib_out = hf_gpu_baseline.run(cfg, wl, dev, iters=20, warmup=3, state=model.state_dict(), check_mel=mel_used)
+                lib_logits = lib_out.pop("_check_logits", None)
+                line["gpu_library_baseline"] = lib_out
             except Exception as e:
                 line["gpu_library_baseline"] = {"error": repr(e)[:300]}
         if state is not None:
             # full-depth fp32 CPU oracle on THIS model's weights: the cpu_baseline sample and the check of the GPU output in one
             try:
                 cb, check = cpu_leg(cfg, wl, args, state=state, gpu_logits=gpu_logits, gpu_token=gpu_token, max_steps=1,
-                                    mel_used=mel_used)
+                                    mel_used=mel_used, lib_logits=lib_logits)
                 line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "stage_seconds", "host_cpus")}
                 line["check"] = check
                 line["token_check"] = bool(tokens_ok and check["ok"])

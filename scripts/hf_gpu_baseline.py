@@ -72,13 +72,28 @@ def device_step(enc, proj, llm, audio_values, input_ids, start, n_tok):
     return out.logits[:, -1].argmax(-1)
 
 
-def run(cfg, wl, device="cuda", iters=20, warmup=3, attn="sdpa", try_graph=True):
-    """Returns a dict for bench.py's ``gpu_library_baseline`` key."""
+def load_weights(enc, proj, llm, state):
+    """Copies an ``UltravoxModel``-named state dict (audio_tower.* / multi_modal_projector.* / language_model.*: the reference's
+    names are transformers' own) into the stock modules, so both paths run on IDENTICAL weights."""
+    def sub(prefix):
+        return {k[len(prefix):]: v for k, v in state.items() if k.startswith(prefix)}
+    enc.load_state_dict(sub("audio_tower."), strict=True)
+    proj.load_state_dict(sub("multi_modal_projector."), strict=True)
+    res = llm.load_state_dict(sub("language_model."), strict=False)
+    assert not res.unexpected_keys and all("rotary" in k or "inv_freq" in k for k in res.missing_keys), res
+
+
+def run(cfg, wl, device="cuda", iters=20, warmup=3, attn="sdpa", try_graph=True, state=None, check_mel=None):
+    """Returns a dict for bench.py's ``gpu_library_baseline`` key.  ``state`` (optional): weights to run on (the measured model's
+    own); ``check_mel`` [1, n_mels, T] (optional): the result also carries ``_check_logits`` = this path's last-row logits for
+    that mel, for the side-by-side error against the fp32 oracle (parity is judged against HF's own bf16 error)."""
     import numpy as np
     from transformers import WhisperFeatureExtractor
     dev = torch.device(device)
     on_gpu = dev.type == "cuda"
     enc, proj, llm = build(cfg, dev, attn)
+    if state is not None:
+        load_weights(enc, proj, llm, state)
     fe = WhisperFeatureExtractor(feature_size=cfg.audio_config.num_mel_bins)
     wave = np.random.default_rng(1000).standard_normal(wl["n"]).astype(np.float32)
     ids = wl["input_ids"].to(dev)
@@ -151,6 +166,17 @@ def run(cfg, wl, device="cuda", iters=20, warmup=3, attn="sdpa", try_graph=True)
             out["graph_token"] = int(gtok[0])
         except Exception as e:  # capture is best effort: the eager numbers stand on their own
             out["graph_error"] = repr(e)[:300]
+    if check_mel is not None:
+        with torch.no_grad():
+            m = check_mel.to(dev, torch.bfloat16)
+            if m.shape[-1] < want:
+                m = F.pad(m, (0, want - m.shape[-1]))
+            h = enc(m).last_hidden_state
+            aud = proj(h)
+            emb = llm.get_input_embeddings()(ids)
+            emb[0, start:start + n_tok] = aud[0, :n_tok]
+            out["_check_logits"] = llm(inputs_embeds=emb, logits_to_keep=1, use_cache=False).logits[:, -1].float().cpu().view(-1)
+        out["weights"] = "the measured model's own (identical to the B200 path)" if state is not None else "own random init"
     secs = wl["n"] / 16000.0
     best = out.get("graph_ms_device_part", eager_ms)
     out["audio_sec_per_s_best"] = secs / (best * 1e-3)

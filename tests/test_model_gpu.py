@@ -566,13 +566,15 @@ def test_pipeline_end_to_end_and_repetition_penalty():
     toks = pen.split()
     strong = pipe({"audio": a, "sampling_rate": 16000}, max_new_tokens=8, repetition_penalty=50.0).split()
     assert len(set(strong)) == len(strong)                  # a huge penalty never repeats a token it has already produced
-    with pytest.raises(NotImplementedError):
-        pipe({"audio": a, "sampling_rate": 16000}, temperature=0.7)
+    sampled = pipe({"audio": a, "sampling_rate": 16000}, temperature=0.7, max_new_tokens=4)      # temperature > 0 samples (ref infer.py:319-328)
+    assert isinstance(sampled, str)
 
 
 def test_llama_hidden_fused_paths_match_unfused():
     """Round-2 prefill path (pre-tiled weight images, RoPE in the q|k|v epilogue, SwiGLU in the gate|up epilogue) against the
-    round-1 sequence of separate kernels on the row-major weights: bit-identical hidden states, with and without a KV cache."""
+    round-1 sequence of separate kernels on the row-major weights.  Cache and cache-less runs of one path are bit-identical;
+    across the two paths the gate|up tiling (hence the fp32 summation order) and the sigmoid approximation differ, so hidden
+    states agree to bf16 rounding noise, not bit for bit."""
     import ultravox_b200.model as mm
     from ultravox_b200.config import PRESETS, preset
     from ultravox_b200.model import UltravoxModel
@@ -597,5 +599,7 @@ def test_llama_hidden_fused_paths_match_unfused():
     finally:
         mm.USE_TILED, mm.FUSE_ROPE, mm.FUSE_SWIGLU = saved
         model._tiled = None
-    assert torch.equal(fused, plain) and torch.equal(fused_c, plain_c) and torch.equal(fused, fused_c)
-    assert torch.equal(cache.k[:, :, :201], cache2.k[:, :, :201]) and torch.equal(cache.v[:, :, :201], cache2.v[:, :, :201])
+    assert torch.equal(fused, fused_c) and torch.equal(plain, plain_c)
+    assert rel(fused, plain) < 6e-3, rel(fused, plain)
+    assert torch.equal(cache.k[0, :, :201], cache2.k[0, :, :201]) and torch.equal(cache.v[0, :, :201], cache2.v[0, :, :201])  # layer 0: same inputs
+    assert rel(cache.k[1, :, :201], cache2.k[1, :, :201]) < 6e-3

@@ -546,19 +546,17 @@ def test_gemm_tiled_weights_match_row_major(ops, M):
 
 
 @pytest.mark.parametrize("M,F,K", [(201, 14336, 4096), (201, 1000 // 8 * 8, 512), (64, 512, 256), (300, 2048, 1024)])
-def test_gemm_fused_swiglu_bit_exact(ops, M, F, K):
-    """act(gate) * up finished in the gate|up GEMM epilogue == GEMM -> bf16 [M, 2F] -> uvx_swiglu, bit for bit."""
-    from ultravox_b200 import _lib
+def test_gemm_fused_swiglu(ops, M, F, K):
+    """act(gate) * up finished in the gate|up GEMM epilogue against GEMM -> bf16 [M, 2F] -> uvx_swiglu and against fp32 math.
+    Not bit-identical by construction: the interleaved image puts a feature's gate and up rows into another tile than the
+    row-major weight does, the per-tile rotated K start changes the fp32 summation order, and the fused epilogue uses the
+    ex2 / rcp approximations for the sigmoid - all far below the two bf16 roundings of the reference's own op order."""
     x, w = rnd(M, K, seed=1), rnd(2 * F, K, scale=0.03, seed=2)
-    # same tile shape on both sides (the per-tile rotated K start makes the fp32 summation order a function of the tiling)
-    _lib.lib().uvx_debug_gemm_override((2 if 128 < M <= 256 else 1) * 1000 + 208, 1)
-    try:
-        want = ops.swiglu(ops.linear(x, w), gate_first=True)
-        got = ops.linear_tiled(x, ops.TiledWeight(w, 208, swiglu=True), act=ops.ACT_SWIGLU)
-    finally:
-        _lib.lib().uvx_debug_gemm_override(0, 0)
+    want = ops.swiglu(ops.linear(x, w), gate_first=True)
+    got = ops.linear_tiled(x, ops.TiledWeight(w, 208, swiglu=True), act=ops.ACT_SWIGLU)
     assert got.shape == (M, F)
-    assert torch.equal(got, want)
+    assert rel(got, want.float()) < 3e-3
+    assert float((got.float() - want.float()).abs().max()) <= 2 ** -6 * float(want.float().abs().max())   # a few bf16 ulps at most
     xf, wf = x.float(), w.float()
     ref = F_silu_mul(xf @ wf[:F].T, xf @ wf[F:].T)
     assert rel(got, ref) < 4e-3          # two bf16 roundings inside, like the reference's op order

@@ -31,9 +31,8 @@ __global__ void rope_kernel(bf16* __restrict__ qkv, int64_t rows, int64_t row_st
     *reinterpret_cast<float4*>(s + 4) = sp[1];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float se = sgn * s[e];            // sgn = -1 applies the transposed rotation (backward)
-      o1[e] = x1[e] * c[e] - x2[e] * se;      // x*cos + rotate_half(x)*sin, first half: -x2
-      o2[e] = x2[e] * c[e] + x1[e] * se;      // second half: +x1
+      // x*cos + rotate_half(x)*sin (first half: -x2, second half: +x1); sgn = -1 applies the transposed rotation (backward)
+      rope_pair(x1[e], x2[e], c[e], sgn * s[e], o1[e], o2[e]);
     }
     *reinterpret_cast<bf16x8*>(base) = pack8(o1);
     *reinterpret_cast<bf16x8*>(base + half) = pack8(o2);

@@ -297,7 +297,7 @@ __device__ __forceinline__ void epilogue_chunk_swiglu_tma(const GemmParams& p, c
     for (int i = 0; i < 8; ++i) {
       const float gate = __bfloat162float(__float2bfloat16_rn(__uint_as_float(raw[g2 * 16 + i]) * p.alpha));
       const float up = __bfloat162float(__float2bfloat16_rn(__uint_as_float(raw[g2 * 16 + 8 + i]) * p.alpha));
-      o[g2 * 8 + i] = __bfloat162float(__float2bfloat16_rn(silu(gate))) * up;
+      o[g2 * 8 + i] = __bfloat162float(__float2bfloat16_rn(silu_fast(gate))) * up;
     }
   }
   uint4* dst = reinterpret_cast<uint4*>(slice + lane * 32);
@@ -862,8 +862,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int e = 0; e < 4; ++e) {
                   const float x1 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r0[4 * g + e]) * p.alpha));
                   const float x2 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r1[4 * g + e]) * p.alpha));
-                  r0[4 * g + e] = __float_as_uint(x1 * cc[e] - x2 * ss[e]);
-                  r1[4 * g + e] = __float_as_uint(x2 * cc[e] + x1 * ss[e]);
+                  float o1, o2;
+                  rope_pair(x1, x2, cc[e], ss[e], o1, o2);
+                  r0[4 * g + e] = __float_as_uint(o1);
+                  r1[4 * g + e] = __float_as_uint(o2);
                 }
               }
             }

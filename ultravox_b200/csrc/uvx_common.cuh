@@ -145,5 +145,19 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return x * (x >= 0.f ? 1.0f - half_erfc : half_erfc);
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+// x * sigmoid(x) with one ex2.approx and one rcp.approx (relative error ~2^-21, far below the bf16 rounding that follows): the
+// fused gate|up epilogue evaluates 21k of these per CTA on four warps, where expf + a true division cost ~10 us of exposed tail
+__device__ __forceinline__ float silu_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
+// RoPE pair rotation with the rounding spelled out (no FMA contraction), shared by uvx_rope and the fused q|k|v epilogue so that
+// both produce the same bits: o1 = x1 cos - x2 sin, o2 = x2 cos + x1 sin
+__device__ __forceinline__ void rope_pair(float x1, float x2, float c, float s, float& o1, float& o2) {
+  o1 = __fsub_rn(__fmul_rn(x1, c), __fmul_rn(x2, s));
+  o2 = __fadd_rn(__fmul_rn(x2, c), __fmul_rn(x1, s));
+}
 
 }  // namespace uvx
