@@ -121,7 +121,8 @@ typedef struct uvx_gemm_args {
 int uvx_gemm_bf16(const uvx_gemm_args* args, uvx_stream_t stream);
 /* tuning hook: force tile config MT*1000+BN (0 = heuristic) and split-K count (0 = heuristic) for later calls */
 int uvx_debug_gemm_override(int cfg, int splits);
-/* tuning hook: 1 = bf16 outputs in plain row order are written by TMA stores (default), 0 = transposing epilogue everywhere */
+/* tuning hook, bit mask: 1 = bf16 outputs in plain row order without residual are written by TMA stores (default), 2 = also with a
+ * residual, 4 = fp32 split-K partials too; 0 = transposing epilogue everywhere */
 int uvx_debug_gemm_tma_store(int on);
 /* tuning hook: device buffer [grid][8] int64 filled with per-CTA phase timestamps by the diagnostic twin kernels (NULL = off) */
 int uvx_debug_gemm_times(void* dev_buf);

@@ -50,7 +50,7 @@ print("-- encoder layer 10");
 names = [e.name for e in step]
 ln = [i for i, nme in enumerate(names) if "layernorm" in nme]
 dump(ln[20], ln[22] + 1)
-rn = [i for i, nme in enumerate(names) if "gemm_tc_kernel<2, 208>" in nme or "gemm_tc_kernel<2,208>" in nme.replace(" ", "")]
+an = [i for i, nme in enumerate(names) if "attn_llm_tc" in nme or "attn_fwd_kernel<128>" in nme]
 print("-- llama layer 10")
-if rn:
-    dump(rn[10] - 6, rn[10] + 6)
+if len(an) > 11:
+    dump(an[10] - 3, an[11] - 3)

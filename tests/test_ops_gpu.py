@@ -545,7 +545,7 @@ def test_gemm_tiled_weights_match_row_major(ops, M):
     assert torch.equal(n1, ops.rmsnorm(h1, nw, 1e-5))
 
 
-@pytest.mark.parametrize("M,F,K", [(201, 14336, 4096), (201, 1000 // 8 * 8, 512), (64, 512, 256), (300, 2048, 1024)])
+@pytest.mark.parametrize("M,F,K", [(201, 14336, 4096), (201, 992, 512), (64, 512, 256), (300, 2048, 1024)])
 def test_gemm_fused_swiglu(ops, M, F, K):
     """act(gate) * up finished in the gate|up GEMM epilogue against GEMM -> bf16 [M, 2F] -> uvx_swiglu and against fp32 math.
     Not bit-identical by construction: the interleaved image puts a feature's gate and up rows into another tile than the
@@ -597,16 +597,22 @@ def test_gemm_tma_store_epilogue_bit_identical(ops, M, N, K):
     from ultravox_b200 import _lib
     x, w, b = rnd(M, K, seed=1), rnd(N, K, scale=0.05, seed=2), rnd(N, seed=3)
     res = {}
-    for on in (1, 0):
+    for on in (7, 0):                                     # 7: every TMA-store variant (plain, residual, fp32 split-K partials)
         _lib.lib().uvx_debug_gemm_tma_store(on)
         try:
             guard = torch.full((M + 2, N + 64), 7.0, dtype=BF, device="cuda")     # output is a window of a larger buffer
             out = guard[1:M + 1, :N]
             ops.linear(x, w, out=out)
-            res[on] = (out.clone(), ops.linear(x, w, bias=b, act=ops.ACT_GELU), guard)
+            r = rnd(M, N, seed=4)
+            _lib.lib().uvx_debug_gemm_override(0, 3 if K >= 512 else 0)          # split-K partials as well where K allows
+            sk = ops.linear(x, w, residual=r)
+            _lib.lib().uvx_debug_gemm_override(0, 0)
+            res[on] = (out.clone(), ops.linear(x, w, bias=b, act=ops.ACT_GELU), guard, ops.linear(x, w, bias=b, residual=r), sk)
         finally:
             _lib.lib().uvx_debug_gemm_tma_store(1)
-    assert torch.equal(res[1][0], res[0][0]) and torch.equal(res[1][1], res[0][1])
-    assert rel(res[1][0], x.float() @ w.float().T) < 1e-3
-    g = res[1][2]
+            _lib.lib().uvx_debug_gemm_override(0, 0)
+    for i in (0, 1, 3, 4):
+        assert torch.equal(res[7][i], res[0][i]), i
+    assert rel(res[7][0], x.float() @ w.float().T) < 1e-3
+    g = res[7][2]
     assert bool((g[0] == 7).all()) and bool((g[M + 1] == 7).all()) and bool((g[:, N:] == 7).all())

@@ -619,7 +619,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < nk; ++i) {
           const int kb = kb_begin + (i + rot < nk ? i + rot : i + rot - nk);
-          if (i + pf < nk) {
+          if (pf > 0 && i + pf < nk) {
             const int j = i + pf;
             const int kbp = kb_begin + (j + rot < nk ? j + rot : j + rot - nk);
             tma_prefetch_2d_e(&tmW, tiled ? 0 : kbp * kBK, tiled ? wt_base + kbp * BN : n0);
@@ -1625,7 +1625,10 @@ static int encode_map_plain(CUtensorMap* tm, const void* base, const uint64_t* d
   return UVX_OK;
 }
 
-static int g_gemm_tma_store = 1;  // tuning switch (uvx_debug_gemm_tma_store): 0 = always the transposing epilogue
+// tuning switch (uvx_debug_gemm_tma_store), bit mask: 1 = bf16 outputs without residual through TMA stores (default), 2 = also with
+// a residual (measured slower in situ: each lane reads 64 B of its own row instead of the transposing path's coalesced reads),
+// 4 = fp32 split-K partials (measured slower than the direct 16-byte stores); 0 = the transposing epilogue everywhere
+static int g_gemm_tma_store = 1;
 
 static int num_sms() {
   static int n = 0;
@@ -1735,6 +1738,7 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
   p.ws_partial = (float*)a->workspace;
   if (cm == 1 && cn == 1 && g_gemm_tma_store && a->a_batch == 1) {
     if (p.splits > 1) {
+      if (g_gemm_tma_store & 4) {
       // split-K: fp32 partial tiles leave through TMA stores into [split][row][col] (rows past M clipped by the map)
       uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->a_rows, (uint64_t)p.splits};
       uint64_t st[2] = {(uint64_t)a->N * 4, (uint64_t)a->a_rows * (uint64_t)a->N * 4};
@@ -1742,7 +1746,8 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
       int rc = encode_map_plain(&tmC, a->workspace, dims, st, box, 3, true);
       if (rc) return rc;
       p.tma_store = 1;
-    } else if (a->out_dtype == UVX_DT_BF16 && !a->c_row_map && a->c_row_offset == 0) {
+      }
+    } else if (a->out_dtype == UVX_DT_BF16 && !a->c_row_map && a->c_row_offset == 0 && (!a->R || (g_gemm_tma_store & 2))) {
       // bf16 output in plain row order: the epilogue stores 32 x 32 boxes by TMA (tensor map of C, no swizzle: the 64-byte box
       // rows are written by 32 lanes with at most a 4-way bank conflict on four stores per chunk); fused SwiGLU: 32 x 16 boxes
       const bool sw = a->act == UVX_ACT_SWIGLU;   // [M, N/2] output, 16 columns per accumulator chunk
