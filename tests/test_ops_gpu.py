@@ -609,7 +609,7 @@ def test_gemm_tma_store_epilogue_bit_identical(ops, M, N, K):
             _lib.lib().uvx_debug_gemm_override(0, 0)
             res[on] = (out.clone(), ops.linear(x, w, bias=b, act=ops.ACT_GELU), guard, ops.linear(x, w, bias=b, residual=r), sk)
         finally:
-            _lib.lib().uvx_debug_gemm_tma_store(1)
+            _lib.lib().uvx_debug_gemm_tma_store(-1)
             _lib.lib().uvx_debug_gemm_override(0, 0)
     for i in (0, 1, 3, 4):
         assert torch.equal(res[7][i], res[0][i]), i

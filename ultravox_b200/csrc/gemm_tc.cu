@@ -496,7 +496,10 @@ struct SmemLayout {
 // EW: epilogue warps (0 = default for MT).  DIAG: tuning twin with the pipeline-isolation modes compiled in (uvx_debug_gemm_mode:
 // 1 = loads only, 2 = MMAs only, 3 = no epilogue stores) - same convergent producer / MMA loops as production, unlike
 // gemm_tc_kernel_x; never on the product path.
-template <int MT, int BN, int EW = 0, bool DIAG = false>
+// FEAT: bit 0 = weight-stream producer (pre-tiled images, PDL early W loads, L2 prefetch hook), bit 1 = round-2 epilogues (TMA stores,
+// fused RoPE / SwiGLU).  FEAT = 0 compiles the round-1 loops unchanged: the single-thread producer / MMA loops are latency-critical and
+// every extra select or branch in them showed up as 2-3 us per launch in situ (profiles/r2_insitu_timeline_v2.txt).
+template <int MT, int BN, int EW = 0, bool DIAG = false, int FEAT = 3>
 __global__ void __launch_bounds__(SmemLayout<MT, BN, EW>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmC,
                const GemmParams p) {
@@ -504,6 +507,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   long long t_entry = 0;
   if constexpr (DIAG) t_entry = clock64();
   using L = SmemLayout<MT, BN, EW>;
+  constexpr bool kWS = (FEAT & 1) != 0, kEpi = (FEAT & 2) != 0;
   constexpr int kAcc = L::kAcc;
   constexpr int kEpiWarps = L::kEpiWarps;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -570,12 +574,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int s = 0;           // ring slot and its phase: the ring runs ahead across tile boundaries
       uint32_t ph = 0;
       bool waited = false;
-      const int tiled = p.w_tiled;
+      const int tiled = kWS ? p.w_tiled : 0;
       // Programmatic dependent launch: this CTA may be resident while the previous kernel is still running.  Weights do not
       // depend on it, so the W boxes of the first ring round are requested BEFORE griddepcontrol.wait (their latency - and the
       // launch / set-up above - hide under the previous kernel's tail); the activation boxes follow after the wait.
       int pre = 0;
-      if (p.pdl && (int)blockIdx.x < num_units) {
+      if (kWS && p.pdl && (int)blockIdx.x < num_units) {
         const int unit = blockIdx.x;
         const int tile = unit / p.splits, split = unit % p.splits;
         const int tn_idx = tile / tiles_m_total;
@@ -608,7 +612,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int wt_base = tn_idx * num_kb * BN;
         // the HBM -> L2 stream of the weights runs `pf` k-blocks ahead of the shared-memory ring: the ring (4-5 stages, half of
         // each stage is the re-read activation tile) holds too few weight bytes in flight to cover DRAM latency at full rate
-        const int pf = p.pf < nk ? p.pf : nk;
+        const int pf = kWS ? (p.pf < nk ? p.pf : nk) : 0;
         for (int i = 0; i < pf; ++i) {
           const int kb = kb_begin + (i + rot < nk ? i + rot : i + rot - nk);
           tma_prefetch_2d_e(&tmW, tiled ? 0 : kb * kBK, tiled ? wt_base + kb * BN : n0);
@@ -619,13 +623,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < nk; ++i) {
           const int kb = kb_begin + (i + rot < nk ? i + rot : i + rot - nk);
-          if (pf > 0 && i + pf < nk) {
+          if (kWS && pf > 0 && i + pf < nk) {
             const int j = i + pf;
             const int kbp = kb_begin + (j + rot < nk ? j + rot : j + rot - nk);
             tma_prefetch_2d_e(&tmW, tiled ? 0 : kbp * kBK, tiled ? wt_base + kbp * BN : n0);
           }
           uint8_t* sa = smem + s * p.stage_bytes;
-          if (pre > 0) {   // first ring round of the first unit: the W box is already in flight, only the activation box is missing
+          if (kWS && pre > 0) {   // first ring round of the first unit: the W box is already in flight, only the activation box is missing
             --pre;
             if constexpr (DIAG) {
               if (p.dbg_mode == 2) {   // (isolation mode: the early W loads still land; nothing else to do)
@@ -738,7 +742,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // staging buffers of the TMA-store epilogue: 2 KB each; two in the warp's pad, or eight in the idle operand ring
       uint8_t* const epi_pad = smem + L::kPadOff + (warp - 2) * kStageBytesPerWarp;
       uint8_t* const epi_ring = smem + (warp - 2) * 16384;
-      const bool ring = p.epi_ring != 0;
+      const bool ring = kEpi && p.epi_ring != 0;
+      const bool tma = kEpi && p.tma_store != 0;
       auto epi_acquire = [&](uint32_t n) -> uint8_t* {
         if (ring) {
           if (n >= 8) {   // the buffer written now was last read by the store issued eight boxes ago
@@ -769,7 +774,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t raw[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * L::kBNT) + (uint32_t)(mt * L::kBNT + c * 32), raw);
             tmem_ld_wait();
-            if (p.tma_store) {
+            if (tma) {
               // fp32 partial tile through the pad as two 32-row x 16-column boxes (64-byte rows), TMA-stored into
               // [split][row][col]; rows past M are clipped by the map
 #pragma unroll
@@ -805,7 +810,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int64_t n_lim = (int64_t)n0 + BN < p.N ? (int64_t)n0 + BN : p.N;  // ragged last column tile (N % BN != 0)
       bool handled = false;
       uint32_t nstore = 0;   // TMA stores issued by this warp for this tile (pad halves alternate)
-      if constexpr (BN == 208) {
+      if constexpr (BN == 208 && kEpi) {
         if (p.swiglu) {  // warp-uniform: tile columns are (8 gate | 8 up) groups, BN / 2 finished activations per row
           handled = true;
           const int64_t n_out0 = (int64_t)tn_idx * (BN / 2);
@@ -820,7 +825,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               uint32_t raw[32];
               tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * L::kBNT) + (uint32_t)(mt * L::kBNT + c * 32), raw);
               tmem_ld_wait();
-              if (p.tma_store && c * 32 + 32 <= BN && n_out0 + c * 16 + 16 <= n_out_lim) {
+              if (tma && c * 32 + 32 <= BN && n_out0 + c * 16 + 16 <= n_out_lim) {
                 uint8_t* buf = epi_acquire(nstore);
                 epilogue_chunk_swiglu_tma(p, &tmC, raw, buf, lane, m_warp0, n_out0 + c * 16);
                 ++nstore;
@@ -836,7 +841,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
-      if constexpr (MT == 1 && BN == 128) {
+      if constexpr (MT == 1 && BN == 128 && kEpi) {
         if (p.rope_cos != nullptr && n0 < p.rope_cols) {
           // fused RoPE: the tile is one 128-wide head, columns j and j + 64 rotate together; this warp owns chunks cpar and
           // cpar + 2, i.e. columns [32 cpar, +32) and their partners.  Same rounding as GEMM-then-uvx_rope: the projection is
@@ -869,7 +874,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
               }
             }
-            if (p.tma_store) {
+            if (tma) {
               epilogue_chunk_tma(p, &tmC, r0, epi_acquire(0), lane, m_warp0, (int64_t)n0 + cpar * 32);
               epilogue_chunk_tma(p, &tmC, r1, epi_acquire(1), lane, m_warp0, (int64_t)n0 + 64 + cpar * 32);
               nstore = 2;
@@ -891,7 +896,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t raw[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (MT * L::kBNT) + (uint32_t)(mt * L::kBNT + c * 32), raw);
             tmem_ld_wait();
-            if (p.tma_store && (int64_t)n0 + c * 32 + 32 <= n_lim) {
+            if (tma && (int64_t)n0 + c * 32 + 32 <= n_lim) {
               uint8_t* buf = epi_acquire(nstore);
               epilogue_chunk_tma(p, &tmC, raw, buf, lane, m_warp0, (int64_t)n0 + c * 32);
               ++nstore;
@@ -1625,10 +1630,11 @@ static int encode_map_plain(CUtensorMap* tm, const void* base, const uint64_t* d
   return UVX_OK;
 }
 
-// tuning switch (uvx_debug_gemm_tma_store), bit mask: 1 = bf16 outputs without residual through TMA stores (default), 2 = also with
-// a residual (measured slower in situ: each lane reads 64 B of its own row instead of the transposing path's coalesced reads),
-// 4 = fp32 split-K partials (measured slower than the direct 16-byte stores); 0 = the transposing epilogue everywhere
-static int g_gemm_tma_store = 1;
+// tuning switch (uvx_debug_gemm_tma_store / UVX_TMA_STORE), bit mask: 1 = bf16 outputs without residual through TMA stores, 2 = also
+// with a residual (default 3: 9.71 vs 9.89 ms per prefill step in situ, profiles/r2_ab_bench_v3.txt), 4 = fp32 split-K partials
+// (measured slower than the direct 16-byte stores); 0 = the transposing epilogue everywhere
+static int g_gemm_tma_store = -1;  // -1: UVX_TMA_STORE env or 1
+static int g_gemm_epi_ring = -1;   // -1: UVX_EPI_RING env or 1 (tuning: 0 = stage TMA-store boxes in the per-warp pads only)
 
 static int num_sms() {
   static int n = 0;
@@ -1736,6 +1742,14 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
   p.kb_per_split = (num_kb + splits - 1) / splits;
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
   p.ws_partial = (float*)a->workspace;
+  if (g_gemm_tma_store < 0) {
+    const char* e = getenv("UVX_TMA_STORE");
+    g_gemm_tma_store = e ? atoi(e) : 1;
+  }
+  if (g_gemm_epi_ring < 0) {
+    const char* e = getenv("UVX_EPI_RING");
+    g_gemm_epi_ring = e ? atoi(e) : 1;
+  }
   if (cm == 1 && cn == 1 && g_gemm_tma_store && a->a_batch == 1) {
     if (p.splits > 1) {
       if (g_gemm_tma_store & 4) {
@@ -1773,7 +1787,8 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
   p.n_groups = (p.n_tiles + cn - 1) / cn;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MT, BN, EW, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MT, BN, EW, DIAG, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<MT, BN, EW, DIAG, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel_x<MT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm_tc_kernel<%d,%d>, smem %d): %s", MT, BN, kSmemTotal, cudaGetErrorString(e));
@@ -1783,14 +1798,17 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
   }
   const int units = p.m_groups * p.n_groups * p.splits;  // cluster-level work units
   const int csize = cm * cn;
-  p.epi_ring = (p.tma_store && csize == 1 && units <= num_sms() && p.stages * p.stage_bytes >= L::kEpiWarps * 16384) ? 1 : 0;
+  p.epi_ring = (g_gemm_epi_ring && p.tma_store && csize == 1 && units <= num_sms() && p.stages * p.stage_bytes >= L::kEpiWarps * 16384) ? 1 : 0;
   p.pdl = pdl_enabled() ? 1 : 0;
   UVX_REQUIRE(!(p.dbg_mode && csize > 1), "uvx_gemm_bf16: pipeline-isolation modes are for unclustered launches");
   UVX_REQUIRE(EW == 0 || csize == 1, "uvx_gemm_bf16: cluster launches use the default epilogue width");
   if (csize == 1) {
     const int grid = units < num_sms() ? units : num_sms();
     if (p.dbg_mode && !DIAG && EW == 0) launch_k(gemm_tc_kernel_x<MT, BN>, dim3((unsigned)grid), dim3(SmemLayout<MT, BN>::kThreads), kSmemTotal, stream, tmA, tmW, p);
-    else launch_k(gemm_tc_kernel<MT, BN, EW, DIAG>, dim3((unsigned)grid), dim3(L::kThreads), kSmemTotal, stream, tmA, tmW, tmC, p);
+    else if (tiled || p.pdl || p.pf || p.tma_store || p.swiglu || p.rope_cos || DIAG || EW)
+      launch_k(gemm_tc_kernel<MT, BN, EW, DIAG, 3>, dim3((unsigned)grid), dim3(L::kThreads), kSmemTotal, stream, tmA, tmW, tmC, p);
+    else   // none of the round-2 features applies (residual / split-K / fp32 / remapped outputs): the round-1 loops, unchanged
+      launch_k(gemm_tc_kernel<MT, BN, EW, DIAG, 0>, dim3((unsigned)grid), dim3(L::kThreads), kSmemTotal, stream, tmA, tmW, tmC, p);
   } else {
     static int max_clusters[9] = {0};
     if (max_clusters[csize] == 0) {

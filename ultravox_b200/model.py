@@ -31,6 +31,7 @@ from .config import LossConfig, LossFunction, UltravoxConfig
 FUSE_NORM = os.environ.get("UVX_FUSE_NORM", "1") != "0"   # tuning switch: RMSNorm fused into the o_proj / down_proj split-K pass
 USE_TILED = os.environ.get("UVX_TILED", "1") != "0"       # LLM prefill GEMMs stream pre-tiled weight images (contiguous DRAM runs)
 FUSE_ROPE = os.environ.get("UVX_FUSE_ROPE", "1") != "0"   # RoPE in the q|k|v GEMM epilogue (head_dim 128)
+TILED_SET = os.environ.get("UVX_TILED_SET", "gate_up")        # which LLM projections get a pre-tiled image: "all" | "gate_up" | "mlp" (in situ only gate|up gains: r2_ab_bench_v3)
 FUSE_SWIGLU = os.environ.get("UVX_FUSE_SWIGLU", "1") != "0"   # act(gate)*up in the gate|up GEMM epilogue (needs the tiled image)
 BF16 = torch.bfloat16
 
@@ -469,10 +470,13 @@ class UltravoxModel(nn.Module):
                     out = []
                     for layer in layers:
                         sa, mlp = layer.self_attn, layer.mlp
-                        out.append(dict(qkv=ops.TiledWeight(sa.qkv_w, 128), o=ops.TiledWeight(sa.o_proj.weight, 128),
+                        attn_t = TILED_SET == "all"
+                        down_t = TILED_SET in ("all", "mlp")
+                        out.append(dict(qkv=ops.TiledWeight(sa.qkv_w, 128) if attn_t else None,
+                                        o=ops.TiledWeight(sa.o_proj.weight, 128) if attn_t else None,
                                         gate_up=ops.TiledWeight(mlp.gate_up_w, 208, swiglu=True) if FUSE_SWIGLU
                                         else ops.TiledWeight(mlp.gate_up_w, 208),
-                                        down=ops.TiledWeight(mlp.down_proj.weight, 128)))
+                                        down=ops.TiledWeight(mlp.down_proj.weight, 128) if down_t else None))
                     self._tiled = out
         return self._tiled or None
 
@@ -628,7 +632,7 @@ class UltravoxModel(nn.Module):
         for li, layer in enumerate(layers):
             sa, mlp = layer.self_attn, layer.mlp
             tw = tiled[li] if tiled is not None else None
-            if tw is not None:
+            if tw is not None and tw["qkv"] is not None:
                 ops.linear_tiled(x, tw["qkv"], out=qkv, rope=rope)
             else:
                 ops.linear(x, sa.qkv_w, out=qkv, rope=rope)
@@ -645,7 +649,7 @@ class UltravoxModel(nn.Module):
                               hd ** -0.5, True, kv_len, 0, kv_start)
             # o_proj / down_proj write the residual stream AND the RMSNorm the next block reads (fused into split-K's pass 2)
             n1 = (layer.post_attention_layernorm.weight, eps, x) if FUSE_NORM else None
-            if tw is not None:
+            if tw is not None and tw["o"] is not None:
                 ops.linear_tiled(att, tw["o"], residual=h, out=h, norm=n1)
             else:
                 ops.linear(att, sa.o_proj.weight, residual=h, out=h, norm=n1)
@@ -661,7 +665,7 @@ class UltravoxModel(nn.Module):
                 ops.swiglu(gu, gate_first=True, out=act)
             nxt = layers[li + 1].input_layernorm.weight if li + 1 < len(layers) else lm.model.norm.weight
             n2 = (nxt, eps, x) if FUSE_NORM else None
-            if tw is not None:
+            if tw is not None and tw["down"] is not None:
                 ops.linear_tiled(act, tw["down"], residual=h, out=h, norm=n2)
             else:
                 ops.linear(act, mlp.down_proj.weight, residual=h, out=h, norm=n2)
