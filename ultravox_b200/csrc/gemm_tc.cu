@@ -1744,7 +1744,7 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
   p.ws_partial = (float*)a->workspace;
   if (g_gemm_tma_store < 0) {
     const char* e = getenv("UVX_TMA_STORE");
-    g_gemm_tma_store = e ? atoi(e) : 1;
+    g_gemm_tma_store = e ? atoi(e) : 3;
   }
   if (g_gemm_epi_ring < 0) {
     const char* e = getenv("UVX_EPI_RING");
