@@ -1805,7 +1805,7 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
   if (csize == 1) {
     const int grid = units < num_sms() ? units : num_sms();
     if (p.dbg_mode && !DIAG && EW == 0) launch_k(gemm_tc_kernel_x<MT, BN>, dim3((unsigned)grid), dim3(SmemLayout<MT, BN>::kThreads), kSmemTotal, stream, tmA, tmW, p);
-    else if (tiled || p.pdl || p.pf || p.tma_store || p.swiglu || p.rope_cos || DIAG || EW)
+    else if (tiled || p.pf || p.tma_store || p.swiglu || p.rope_cos || DIAG || EW)
       launch_k(gemm_tc_kernel<MT, BN, EW, DIAG, 3>, dim3((unsigned)grid), dim3(L::kThreads), kSmemTotal, stream, tmA, tmW, tmC, p);
     else   // none of the round-2 features applies (residual / split-K / fp32 / remapped outputs): the round-1 loops, unchanged
       launch_k(gemm_tc_kernel<MT, BN, EW, DIAG, 0>, dim3((unsigned)grid), dim3(L::kThreads), kSmemTotal, stream, tmA, tmW, tmC, p);
