@@ -22,7 +22,10 @@ bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("UVX_PDL");
-    v = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured slower than plain graph edges in round 1 (profiles/README)
+    // on by default since round 2 (UVX_PDL=0 turns it off): with the W boxes of a GEMM's first ring round requested before
+    // griddepcontrol.wait the programmatic edges are worth 0.06-0.15 ms per prefill step (profiles/r2_ab_bench_v3..v5.txt);
+    // round 1, without the early loads, measured them slower than plain graph edges
+    v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
 }

@@ -1631,7 +1631,8 @@ static int encode_map_plain(CUtensorMap* tm, const void* base, const uint64_t* d
 }
 
 // tuning switch (uvx_debug_gemm_tma_store / UVX_TMA_STORE), bit mask: 1 = bf16 outputs without residual through TMA stores, 2 = also
-// with a residual (default 3: 9.71 vs 9.89 ms per prefill step in situ, profiles/r2_ab_bench_v3.txt), 4 = fp32 split-K partials
+// with a residual (within noise of 1 once those GEMMs run the unchanged round-1 loops, profiles/r2_ab_bench_v5.txt; default 1),
+// 4 = fp32 split-K partials
 // (measured slower than the direct 16-byte stores); 0 = the transposing epilogue everywhere
 static int g_gemm_tma_store = -1;  // -1: UVX_TMA_STORE env or 1
 static int g_gemm_epi_ring = -1;   // -1: UVX_EPI_RING env or 1 (tuning: 0 = stage TMA-store boxes in the per-warp pads only)
@@ -1744,7 +1745,7 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
   p.ws_partial = (float*)a->workspace;
   if (g_gemm_tma_store < 0) {
     const char* e = getenv("UVX_TMA_STORE");
-    g_gemm_tma_store = e ? atoi(e) : 3;
+    g_gemm_tma_store = e ? atoi(e) : 1;
   }
   if (g_gemm_epi_ring < 0) {
     const char* e = getenv("UVX_EPI_RING");

@@ -34,8 +34,9 @@ typedef __nv_bfloat16 bf16;
 // pdl_trigger() (let the next kernel's CTAs be scheduled as soon as SM resources free up) followed - after its
 // input-independent set-up - by pdl_wait() (all memory of the preceding grids is complete and visible).  Inside a CUDA
 // graph this turns the kernel->kernel edges into programmatic edges: launch latency, barrier init, TMEM allocation and
-// descriptor prefetch of kernel N+1 overlap the tail of kernel N.  Opt-in with UVX_PDL=1 (round-1 measurement: 10.86 ms
-// per prefill step with PDL vs 10.47 ms without, so plain launches are the default; griddepcontrol.* are no-ops then).
+// descriptor prefetch of kernel N+1 overlap the tail of kernel N.  On by default since round 2 (UVX_PDL=0 disables it; the
+// griddepcontrol.* instructions are no-ops then): the GEMM additionally requests the weight boxes of its first ring round before
+// the wait.  Round 1 (no early loads) had measured 10.86 ms per prefill step with PDL vs 10.47 ms without.
 bool pdl_enabled();
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
