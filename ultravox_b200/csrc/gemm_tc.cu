@@ -2051,6 +2051,15 @@ extern "C" int uvx_gemm_bf16(const uvx_gemm_args* a, uvx_stream_t stream_) {
     if (mt != 1 && mt != 2) mt = (a->a_rows > 128 && a->a_rows <= 256 && a->a_batch == 1) ? 2 : 1;
     if (a->rope_cos) mt = 1;
     cfg = (variant && mt == 2 ? variant : mt) * 1000 + (int)a->w_tiled;
+    if (a->act == UVX_ACT_SWIGLU && mt == 2 && !variant) {
+      // the fused SwiGLU epilogue is arithmetic on the exposed tail of a one-tile CTA: UVX_SWIGLU_EW=8 spreads it over eight warps
+      static int sw_ew = -1;
+      if (sw_ew < 0) {
+        const char* e = getenv("UVX_SWIGLU_EW");
+        sw_ew = e ? atoi(e) : 4;
+      }
+      if (sw_ew == 8) cfg = 6000 + (int)a->w_tiled;
+    }
     cm = cn = 1;
     const int64_t tiles = ((a->a_rows + mt * 128 - 1) / (mt * 128)) * a->a_batch * ((a->N + a->w_tiled - 1) / a->w_tiled);
     const int num_kb = (int)((a->K + 63) / 64);
