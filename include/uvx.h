@@ -116,6 +116,8 @@ typedef struct uvx_gemm_args {
   const float* rope_sin;
   const int32_t* rope_positions;
   int64_t rope_rows_per_seq, rope_pos_offset;
+  int32_t flags;            /* bit 0: run the round-1 kernel variant (no TMA-store epilogue / weight-stream producer) for this call */
+  int32_t reserved;
 } uvx_gemm_args;
 
 int uvx_gemm_bf16(const uvx_gemm_args* args, uvx_stream_t stream);

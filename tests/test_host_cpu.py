@@ -180,7 +180,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/uvx.h but not exported by libuvx.so"
         assert name in _lib.SIGNATURES, f"{name} not bound in ultravox_b200/_lib.py"
     assert lib.uvx_abi_version() == 1
-    assert ctypes.sizeof(_lib.GemmArgs) == 8 * 18 + 4 * 3 + 4 + 16 + 24 + 8 + 5 * 8  # ... + w_tiled/rope_cols + 3 ptr + 2 int64 (round 2)
+    assert ctypes.sizeof(_lib.GemmArgs) == 8 * 18 + 4 * 3 + 4 + 16 + 24 + 8 + 5 * 8 + 8  # (+ flags / reserved) ... + w_tiled/rope_cols + 3 ptr + 2 int64 (round 2)
 
 
 def test_host_only_mel_filter_table_is_bit_exact_with_hf():

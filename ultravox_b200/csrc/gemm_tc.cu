@@ -1751,7 +1751,7 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
     const char* e = getenv("UVX_EPI_RING");
     g_gemm_epi_ring = e ? atoi(e) : 1;
   }
-  if (cm == 1 && cn == 1 && g_gemm_tma_store && a->a_batch == 1) {
+  if (cm == 1 && cn == 1 && g_gemm_tma_store && a->a_batch == 1 && !(a->flags & 1)) {
     if (p.splits > 1) {
       if (g_gemm_tma_store & 4) {
       // split-K: fp32 partial tiles leave through TMA stores into [split][row][col] (rows past M clipped by the map)

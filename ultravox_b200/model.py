@@ -31,6 +31,7 @@ from .config import LossConfig, LossFunction, UltravoxConfig
 FUSE_NORM = os.environ.get("UVX_FUSE_NORM", "1") != "0"   # tuning switch: RMSNorm fused into the o_proj / down_proj split-K pass
 USE_TILED = os.environ.get("UVX_TILED", "1") != "0"       # LLM prefill GEMMs stream pre-tiled weight images (contiguous DRAM runs)
 FUSE_ROPE = os.environ.get("UVX_FUSE_ROPE", "1") != "0"   # RoPE in the q|k|v GEMM epilogue (head_dim 128)
+QKV_MODE = os.environ.get("UVX_QKV_MODE", "fused")        # Llama q|k|v GEMM: "fused" RoPE epilogue | "r1" round-1 kernel + uvx_rope | "tma" + uvx_rope
 TILED_SET = os.environ.get("UVX_TILED_SET", "gate_up")        # which LLM projections get a pre-tiled image: "all" | "gate_up" | "mlp" (in situ only gate|up gains: r2_ab_bench_v3)
 FUSE_SWIGLU = os.environ.get("UVX_FUSE_SWIGLU", "1") != "0"   # act(gate)*up in the gate|up GEMM epilogue (needs the tiled image)
 BF16 = torch.bfloat16
@@ -627,7 +628,8 @@ class UltravoxModel(nn.Module):
         tiled = self._tiled_weights()
         fuse_act = tiled is not None and tiled[0]["gate_up"].swiglu
         # RoPE rides in the q|k|v GEMM epilogue when a head is one 128-wide tile; same positions rule as uvx_rope
-        rope = (cos, sin, positions, S, past, (nq + nkv) * hd) if (FUSE_ROPE and hd == 128) else None
+        rope = (cos, sin, positions, S, past, (nq + nkv) * hd) if (FUSE_ROPE and QKV_MODE == "fused" and hd == 128) else None
+        qkv_flags = 1 if QKV_MODE == "r1" else 0
         ops.rmsnorm(h, layers[0].input_layernorm.weight, eps, out=x)
         for li, layer in enumerate(layers):
             sa, mlp = layer.self_attn, layer.mlp
@@ -635,7 +637,7 @@ class UltravoxModel(nn.Module):
             if tw is not None and tw["qkv"] is not None:
                 ops.linear_tiled(x, tw["qkv"], out=qkv, rope=rope)
             else:
-                ops.linear(x, sa.qkv_w, out=qkv, rope=rope)
+                ops.linear(x, sa.qkv_w, out=qkv, rope=rope, flags=qkv_flags)
             if rope is None:
                 ops.rope_(qkv, nq, nkv, hd, cos, sin, rows_per_seq=S, pos_offset=past, positions=positions)
             if cache is None:

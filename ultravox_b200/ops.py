@@ -96,8 +96,10 @@ def gemm_raw(A_ptr: int, a_batch: int, a_rows: int, K: int, a_row_stride: int, a
              W: torch.Tensor, C_t: torch.Tensor, c_row_stride: int, c_batch_rows: int, c_row_offset: int = 0,
              c_row_map: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
              R: Optional[torch.Tensor] = None, r_row_stride: int = 0, r_batch_stride: int = 0,
-             alpha: float = 1.0, act: int = ACT_NONE, norm: Optional[tuple] = None, rope: Optional[tuple] = None) -> None:
+             alpha: float = 1.0, act: int = ACT_NONE, norm: Optional[tuple] = None, rope: Optional[tuple] = None,
+             flags: int = 0) -> None:
     a = GemmArgs()
+    a.flags = flags
     a.A, a.a_batch, a.a_rows, a.K = A_ptr, a_batch, a_rows, K
     a.a_row_stride, a.a_batch_stride = a_row_stride, a_batch_stride
     a.W, a.N, a.w_row_stride = W.data_ptr(), W.shape[0], W.stride(0)
@@ -182,7 +184,7 @@ def linear_tiled(x: torch.Tensor, wt: TiledWeight, out: Optional[torch.Tensor] =
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
            residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
            out_dtype=BF16, row_map: Optional[torch.Tensor] = None, alpha: float = 1.0,
-           norm: Optional[tuple] = None, rope: Optional[tuple] = None) -> torch.Tensor:
+           norm: Optional[tuple] = None, rope: Optional[tuple] = None, flags: int = 0) -> torch.Tensor:
     """y = act(alpha * x @ w.T + bias) + residual for x [..., K] (last dim contiguous, uniform row stride).
     ``norm=(weight, eps, out)`` additionally writes out = RMSNorm(y) (fused into the split-K reduction when possible)."""
     _cuda(x, BF16, "x"), _cuda(w, BF16, "w")
@@ -198,7 +200,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     if residual is not None:
         r2 = residual.reshape(-1, N)
     gemm_raw(x2.data_ptr(), 1, M, K, x2.stride(0), 0, w, o2, o2.stride(-2) if o2.dim() >= 2 else N, M, 0,
-             row_map, bias, r2, r2.stride(0) if r2 is not None else 0, 0, alpha, act, norm, rope)
+             row_map, bias, r2, r2.stride(0) if r2 is not None else 0, 0, alpha, act, norm, rope, flags)
     return out
 
 
