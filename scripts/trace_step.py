@@ -39,13 +39,27 @@ busy = sum(v[1] for v in agg.values())
 print(f"kernels {len(step)} span_us {span:.1f} busy_us {busy:.1f} gaps_us {span - busy:.1f}")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{k:60s} {v[0]:4d} {v[1]:9.1f} {v[1] / v[0]:8.2f} {100 * v[1] / span:5.1f}%")
+# Under programmatic dependent launch a kernel STARTS (launch, set-up, first weight boxes) while its predecessor still runs, so
+# start-to-end durations overlap and over-count.  What a kernel adds to the step is the time from its predecessor's END to its
+# own END: those deltas sum to the span exactly.
+adv = collections.OrderedDict()
+prev_end = t0
+for e in step:
+    k = e.name.split("(")[0][-60:]
+    end = max(e.time_range.end, prev_end)
+    a = adv.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += end - prev_end
+    prev_end = end
+print("-- end-to-end advance per kernel (sums to the span)")
+for k, v in sorted(adv.items(), key=lambda kv: -kv[1][1]):
+    print(f"{k:60s} {v[0]:4d} {v[1]:9.1f} {v[1] / v[0]:8.2f} {100 * v[1] / span:5.1f}%")
 def dump(lo, hi):
-    prev = None
+    prev = step[lo - 1].time_range.end if lo > 0 else None
     for e in step[lo:hi]:
         s, d = e.time_range.start - t0, e.time_range.end - e.time_range.start
         gap = (e.time_range.start - prev) if prev is not None else 0.0
-        print(f"  +{s:9.1f}us gap {gap:5.1f} dur {d:7.2f}  {e.name.split('(')[0][-50:]}")
-        prev = e.time_range.end
+        adv_ = (e.time_range.end - prev) if prev is not None else d
+        print(f"  +{s:9.1f}us gap {gap:5.1f} dur {d:7.2f} advance {adv_:7.2f}  {e.name.split('(')[0][-50:]}")
+        prev = max(e.time_range.end, prev) if prev is not None else e.time_range.end
 print("-- encoder layer 10"); 
 names = [e.name for e in step]
 ln = [i for i, nme in enumerate(names) if "layernorm" in nme]
@@ -53,4 +67,5 @@ dump(ln[20], ln[22] + 1)
 an = [i for i, nme in enumerate(names) if "attn_llm_tc" in nme or "attn_fwd_kernel<128>" in nme]
 print("-- llama layer 10")
 if len(an) > 11:
-    dump(an[10] - 3, an[11] - 3)
+    per = an[11] - an[10]
+    dump(an[10] - 3, an[10] - 3 + per)

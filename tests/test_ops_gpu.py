@@ -496,7 +496,14 @@ def test_kv_write_and_token_finish(ops):
 def _tile_ref(w, R, interleave):
     N, K = w.shape
     n_tiles = -(-N // R)
-    if interleave:
+    if interleave == 64:
+        F = N // 2
+        rows = []
+        for t in range(n_tiles):
+            for r in range(R):
+                f = t * (R // 2) + r % (R // 2)
+                rows.append((f if r < R // 2 else F + f) if f < F else -1)
+    elif interleave:
         F = N // 2
         rows = []
         for t in range(n_tiles):
@@ -511,7 +518,8 @@ def _tile_ref(w, R, interleave):
     return src.view(n_tiles, R, K // 64, 64).permute(0, 2, 1, 3).contiguous().view(-1)
 
 
-@pytest.mark.parametrize("N,K,R,inter", [(512, 256, 128, 0), (1000, 128, 208, 0), (1024, 192, 208, 8), (28672, 256, 208, 8), (6144, 128, 128, 0)])
+@pytest.mark.parametrize("N,K,R,inter", [(512, 256, 128, 0), (1000, 128, 208, 0), (1024, 192, 208, 8), (28672, 256, 208, 8), (6144, 128, 128, 0),
+                                         (1024, 192, 128, 64), (28672, 128, 128, 64)])
 def test_tile_weight_layout(ops, N, K, R, inter):
     w = rnd(N, K, seed=3)
     t = ops.TiledWeight(w, R, swiglu=bool(inter))
@@ -578,11 +586,14 @@ def test_gemm_fused_rope_bit_exact(ops, tiled, M, S, past, with_pos):
     cos, sin = ops.rope_tables(inv, 512, "cuda")
     from ultravox_b200 import _lib
     positions = torch.randint(0, 500, (M,), dtype=torch.int32, device="cuda") if with_pos else None
-    _lib.lib().uvx_debug_gemm_override(1128, 1)          # the fused form runs one 128-wide head per tile: same tiling for the reference
-    try:
-        want = ops.linear(x, w)
-    finally:
-        _lib.lib().uvx_debug_gemm_override(0, 0)
+    if M <= 256:
+        want = ops.linear(x, w)                              # weight-streaming form on both sides: same units, same summation order
+    else:
+        _lib.lib().uvx_debug_gemm_override(1128, 1)          # the fused form runs one 128-wide head per tile: same tiling for the reference
+        try:
+            want = ops.linear(x, w)
+        finally:
+            _lib.lib().uvx_debug_gemm_override(0, 0)
     ops.rope_(want, Hq, Hkv, D, cos, sin, rows_per_seq=S, pos_offset=past, positions=positions)
     rope = (cos, sin, positions, S, past, (Hq + Hkv) * D)
     got = ops.linear_tiled(x, ops.TiledWeight(w, 128), rope=rope) if tiled else ops.linear(x, w, rope=rope)
@@ -616,3 +627,68 @@ def test_gemm_tma_store_epilogue_bit_identical(ops, M, N, K):
     assert rel(res[7][0], x.float() @ w.float().T) < 1e-3
     g = res[7][2]
     assert bool((g[0] == 7).all()) and bool((g[M + 1] == 7).all()) and bool((g[:, N:] == 7).all())
+
+
+# ------------------------------------------------------------------------------------------ weight-streaming form (gemm_ws.cu)
+def _old_kernel(ops, *a, **k):
+    return ops.linear(*a, flags=2, **k)
+
+
+@pytest.mark.parametrize("M,N,K", [(201, 4096, 4096), (201, 6144, 4096), (201, 28672, 512), (201, 4096, 14336), (1, 4096, 4096), (16, 1024, 256),
+                                   (37, 192, 200), (256, 128, 64), (129, 320, 72), (77, 2048, 8192), (5, 16064, 512)])
+def test_gemm_ws_plain_and_epilogues(ops, M, N, K):
+    """Rows <= 256 run the weight-streaming form (tokens on the UMMA N dimension, stream-K with in-kernel fix-up): fp32 math on
+    the same bf16 inputs rounded once (1e-3), agreement with gemm_tc_kernel on the same call, run-to-run identical bits
+    (the owner adds the contributors' partial accumulators in CTA order), nothing written outside the output window;
+    bias / GELU / residual / in-place residual + RMSNorm epilogues; N and K tails."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    x, w, b, r = rnd(M, K, seed=1), rnd(N, K, scale=0.03, seed=2), rnd(N, seed=3), rnd(M, N, seed=4)
+    ref = x.float() @ w.float().T
+    guard = torch.full((M + 2, N + 64), 7.0, dtype=BF, device="cuda")
+    out = guard[1:M + 1, :N]
+    ops.linear(x, w, out=out)
+    assert rel(out, ref) < 1e-3
+    assert bool((guard[0] == 7).all()) and bool((guard[M + 1] == 7).all()) and bool((guard[:, N:] == 7).all())
+    assert torch.equal(out, ops.linear(x, w))                                        # deterministic
+    assert rel(out, _old_kernel(ops, x, w).float()) < 2e-3                           # both rounded: two bf16 roundings apart at most
+    y = ops.linear(x, w, bias=b, act=ops.ACT_GELU)
+    assert rel(y, F.gelu(ref + b.float())) < 1.5e-3
+    y = ops.linear(x, w, bias=b, residual=r)
+    assert rel(y, ref + b.float() + r.float()) < 1e-3
+    if N <= 16384:                                                                   # (uvx_rmsnorm's row limit)
+        nw, h, n = rnd(N, seed=5), r.clone(), torch.empty(M, N, dtype=BF, device="cuda")
+        ops.linear(x, w, residual=h, out=h, norm=(nw, 1e-5, n))                      # o_proj / down_proj form (in-place residual stream)
+        assert rel(h, ref + r.float()) < 1e-3
+        assert torch.equal(n, ops.rmsnorm(h, nw, 1e-5))
+    if K % 64 == 0:
+        assert torch.equal(ops.linear_tiled(x, ops.TiledWeight(w, 128)), out)        # same units, same order: the image only moves bytes
+
+
+@pytest.mark.parametrize("grid", [148, 97, 32, 5])
+def test_gemm_ws_stream_k_any_grid(ops, grid):
+    """The unit ranges are cut for whatever grid runs: tiles split over 1..many CTAs, contributors of a tile in the middle of
+    another CTA's range - every cut gives the fp32-math result."""
+    from ultravox_b200 import _lib
+    M, N, K = 201, 1536, 2048
+    x, w = rnd(M, K, seed=1), rnd(N, K, scale=0.03, seed=2)
+    _lib.lib().uvx_debug_gemm_ws(1, 0, grid)
+    try:
+        y = ops.linear(x, w)
+        y2 = ops.linear(x, w)
+    finally:
+        _lib.lib().uvx_debug_gemm_ws(-1, 0, 0)
+    assert rel(y, x.float() @ w.float().T) < 1e-3 and torch.equal(y, y2)
+
+
+@pytest.mark.parametrize("M,F,K", [(201, 14336, 4096), (201, 1024, 512), (64, 512, 256), (1, 256, 128), (256, 128, 4096)])
+def test_gemm_ws_fused_swiglu(ops, M, F, K):
+    """act(gate) * up in the weight-streaming epilogue (64 gate | 64 up rows per tile, partner values swapped through shared
+    memory) against GEMM -> bf16 [M, 2F] -> uvx_swiglu (a few bf16 ulps: ex2 / rcp sigmoid) and against fp32 math."""
+    x, w = rnd(M, K, seed=1), rnd(2 * F, K, scale=0.03, seed=2)
+    want = ops.swiglu(ops.linear(x, w), gate_first=True)
+    got = ops.linear_tiled(x, ops.TiledWeight(w, 128, swiglu=True), act=ops.ACT_SWIGLU)
+    assert got.shape == (M, F)
+    assert rel(got, want.float()) < 3e-3
+    assert float((got.float() - want.float()).abs().max()) <= 2 ** -6 * float(want.float().abs().max())
+    xf, wf = x.float(), w.float()
+    assert rel(got, F_silu_mul(xf @ wf[:F].T, xf @ wf[F:].T)) < 4e-3

@@ -187,6 +187,12 @@ __global__ void tile_weight_kernel(const bf16* __restrict__ W, int64_t N, int64_
       const int g = r / 16, j = r % 16;
       const int64_t f = t * (R / 2) + (int64_t)g * 8 + (j & 7);
       src_row = f < F ? (j < 8 ? f : F + f) : -1;
+    } else if (interleave == 64) {
+      // weight-streaming GEMM (gemm_ws.cu): rows [0, R/2) of a tile are gate rows, [R/2, R) the up rows of the same features
+      const int64_t F = N / 2;
+      const int h = R / 2;
+      const int64_t f = t * h + (r % h);
+      src_row = f < F ? (r < h ? f : F + f) : -1;
     } else {
       src_row = t * R + r;
       if (src_row >= N) src_row = -1;
@@ -204,7 +210,8 @@ extern "C" int uvx_tile_weight(const void* W, int64_t N, int64_t K, int64_t w_ro
   using namespace uvx;
   UVX_REQUIRE(W && out && N >= 1 && K >= 64 && K % 64 == 0 && w_row_stride % 8 == 0, "uvx_tile_weight: K %% 64 == 0 required");
   UVX_REQUIRE(R == 64 || R == 128 || R == 208 || R == 256, "uvx_tile_weight: R must be 64 / 128 / 208 / 256");
-  UVX_REQUIRE(interleave == 0 || (interleave == 8 && R % 16 == 0 && N % 16 == 0), "uvx_tile_weight: interleave must be 0 or 8");
+  UVX_REQUIRE(interleave == 0 || (interleave == 8 && R % 16 == 0 && N % 16 == 0) || (interleave == 64 && R == 128 && N % 2 == 0),
+              "uvx_tile_weight: interleave must be 0, 8 (8 gate | 8 up rows) or 64 (R = 128: 64 gate | 64 up rows)");
   const int64_t n_tiles = (N + R - 1) / R;
   const int64_t total_vec = n_tiles * (K / 64) * R * 8;
   int64_t blocks = (total_vec + 255) / 256;

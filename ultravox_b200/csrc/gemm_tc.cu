@@ -18,12 +18,14 @@
 #include <stdlib.h>
 
 #include "uvx_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace uvx {
 
+bool gemm_ws_eligible(const uvx_gemm_args* a);                   // gemm_ws.cu
+int launch_gemm_ws(const uvx_gemm_args* a, cudaStream_t stream);
+
 static int g_gemm_dbg = 0;  // uvx_debug_gemm_mode
-static constexpr int kBM = 128;
-static constexpr int kBK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
 
 struct GemmParams {
   int64_t a_rows, a_batch, K, N;
@@ -70,171 +72,6 @@ struct GemmParams {
                            // complete, epilogue done, globaltimer at entry, smid} (clock64 ticks)
 };
 
-// ---------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
-          "r"(smem_u32(dst)),
-      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::
-          "r"(smem_u32(dst)),
-      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;" ::
-          "r"(smem_u32(dst)),
-      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_barrier() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major operand tile, 128-byte swizzle: rows are 128 B apart, 8-row groups 1024 B apart (SBO), LBO unused.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
-  d |= (uint64_t)(1024u >> 4) << 32;         // stride byte offset, bits [32,46)
-  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
-  return d;
-}
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
-__host__ __device__ constexpr uint32_t make_idesc(int bn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(mask)
-               : "memory");
-}
-// Warp-convergent issue forms: the WHOLE warp executes the statement and elect.sync picks the one lane that issues.  Under an
-// `if (lane == 0)` branch the compiler wraps every uniform-datapath instruction (UTCHMMA / UTCBAR / UTMALDG / SYNCS) in an
-// elect-and-retry loop plus register->uniform moves, which triples the instruction count of the single-thread producer / MMA
-// loops - and those loops are the critical path of the kernel (about 575 cycles per k-block regardless of N <= 128).
-__device__ __forceinline__ void umma_f16_e(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p, q;\n"
-      "elect.sync _|q, 0xffffffff;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_e(uint64_t* bar) {
-  asm volatile(
-      "{\n"
-      ".reg .pred q;\n"
-      "elect.sync _|q, 0xffffffff;\n"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
-      "}\n" ::"r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx_e(uint64_t* bar, uint32_t bytes) {
-  asm volatile(
-      "{\n"
-      ".reg .pred q;\n"
-      "elect.sync _|q, 0xffffffff;\n"
-      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(bytes)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_e(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "{\n"
-      ".reg .pred q;\n"
-      "elect.sync _|q, 0xffffffff;\n"
-      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
-      "}\n" ::"r"(smem_u32(dst)),
-      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_e(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
-  asm volatile(
-      "{\n"
-      ".reg .pred q;\n"
-      "elect.sync _|q, 0xffffffff;\n"
-      "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
-      "}\n" ::"r"(smem_u32(dst)),
-      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-// TMA store of a shared-memory box (UTMASTG) + bulk-group bookkeeping
-__device__ __forceinline__ void tma_store_2d(const void* src, const CUtensorMap* tm, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(c0), "r"(c1),
-               "r"(smem_u32(src))
-               : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const void* src, const CUtensorMap* tm, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2),
-               "r"(smem_u32(src))
-               : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
 
 // Fast epilogue of one 32-row x 32-column accumulator chunk (bf16 output, plain row order): alpha, bias, activation, residual in
 // registers (+ the residual row of the lane), 64 bytes per row into a 2 KB half of the warp's pad, ONE TMA store of the 32 x 32 box (rows past M and columns past N
@@ -309,34 +146,6 @@ __device__ __forceinline__ void epilogue_chunk_swiglu_tma(const GemmParams& p, c
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncwarp();
   if (lane == 0) tma_store_2d(slice, tmC, (int)n_out, (int)m_warp0);
-}
-
-// L2 prefetch of a tensor-map box (UTMAPF.L2): same addressing as the load, no shared-memory destination, no barrier
-__device__ __forceinline__ void tma_prefetch_2d_e(const CUtensorMap* tm, int c0, int c1) {
-  asm volatile(
-      "{\n"
-      ".reg .pred q;\n"
-      "elect.sync _|q, 0xffffffff;\n"
-      "@q cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n"
-      "}\n" ::"l"(tm),
-      "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 
@@ -1737,7 +1546,8 @@ static int launch_gemm(const uvx_gemm_args* a, int splits, int cm, int cn, cudaS
   if (BN % 32 != 0 || a->N % BN != 0) splits = 1;  // ragged column tiles exist only in the direct epilogue
   // split-K needs the caller's workspace: [splits][rows][N] fp32 partial sums
   const size_t per_split = (size_t)a->a_batch * (size_t)a->a_rows * (size_t)a->N * 4;
-  while (splits > 1 && (!a->workspace || per_split * (size_t)splits > (size_t)a->workspace_bytes)) --splits;
+  // (the last 1 KB of the workspace belongs to gemm_ws.cu's slot flags)
+  while (splits > 1 && (!a->workspace || per_split * (size_t)splits + 1024 > (size_t)a->workspace_bytes)) --splits;
   if (splits > num_kb) splits = num_kb;
   if (splits < 1) splits = 1;
   p.kb_per_split = (num_kb + splits - 1) / splits;
@@ -1964,13 +1774,17 @@ extern "C" int uvx_debug_gemm_cluster(int cm, int cn) {
   return UVX_OK;
 }
 
-static void pick_cfg(int64_t rows, int64_t batch, int64_t N, int64_t K, int* cfg, int* splits) {
+static void read_forced() {
   if (forced < 0) {
     const char* e = getenv("UVX_GEMM_CFG");
     forced = e ? atoi(e) : 0;
     const char* s = getenv("UVX_GEMM_SPLITS");
     forced_splits = s ? atoi(s) : 0;
   }
+}
+
+static void pick_cfg(int64_t rows, int64_t batch, int64_t N, int64_t K, int* cfg, int* splits) {
+  read_forced();
   const int sms = 148;
   const int num_kb = (int)((K + 63) / 64);
   int mt, bn;
@@ -2032,6 +1846,10 @@ extern "C" int uvx_gemm_bf16(const uvx_gemm_args* a, uvx_stream_t stream_) {
   UVX_REQUIRE(!(a->norm_w && a->norm_out) || (a->out_dtype == UVX_DT_BF16 && !a->c_row_map && a->c_row_offset == 0 &&
                                               (a->a_batch == 1 || a->c_batch_rows == a->a_rows)),
               "uvx_gemm_bf16: fused RMSNorm needs a plain bf16 output");
+  // rows <= 256 in one batch: the weight-streaming form (tokens on the UMMA N dimension, stream-K; gemm_ws.cu)
+  // (a forced tile configuration / split count / cluster shape / isolation mode addresses gemm_tc_kernel: those calls stay there)
+  read_forced();
+  if (forced <= 0 && forced_splits <= 0 && forced_cm == 0 && g_gemm_dbg == 0 && gemm_ws_eligible(a)) return launch_gemm_ws(a, stream);
   int cfg, splits, cm = 1, cn = 1;
   pick_cfg(a->a_rows, a->a_batch, a->N, a->K, &cfg, &splits);
   if (forced_cm > 0 && forced_cn > 0) {

@@ -33,6 +33,7 @@ USE_TILED = os.environ.get("UVX_TILED", "1") != "0"       # LLM prefill GEMMs st
 FUSE_ROPE = os.environ.get("UVX_FUSE_ROPE", "1") != "0"   # RoPE in the q|k|v GEMM epilogue (head_dim 128)
 QKV_MODE = os.environ.get("UVX_QKV_MODE", "fused")        # Llama q|k|v GEMM: "fused" RoPE epilogue | "r1" round-1 kernel + uvx_rope | "tma" + uvx_rope
 TILED_SET = os.environ.get("UVX_TILED_SET", "gate_up")        # which LLM projections get a pre-tiled image: "all" | "gate_up" | "mlp" (in situ only gate|up gains: r2_ab_bench_v3)
+USE_WS = os.environ.get("UVX_GEMM_WS", "1") != "0"         # rows <= 256: weight-streaming GEMM (tokens on the UMMA N dimension, stream-K), 128-row images of all four projections
 FUSE_SWIGLU = os.environ.get("UVX_FUSE_SWIGLU", "1") != "0"   # act(gate)*up in the gate|up GEMM epilogue (needs the tiled image)
 BF16 = torch.bfloat16
 
@@ -471,12 +472,13 @@ class UltravoxModel(nn.Module):
                     out = []
                     for layer in layers:
                         sa, mlp = layer.self_attn, layer.mlp
-                        attn_t = TILED_SET == "all"
-                        down_t = TILED_SET in ("all", "mlp")
+                        attn_t = USE_WS or TILED_SET == "all"
+                        down_t = USE_WS or TILED_SET in ("all", "mlp")
+                        gu_rows = 128 if USE_WS else 208
                         out.append(dict(qkv=ops.TiledWeight(sa.qkv_w, 128) if attn_t else None,
                                         o=ops.TiledWeight(sa.o_proj.weight, 128) if attn_t else None,
-                                        gate_up=ops.TiledWeight(mlp.gate_up_w, 208, swiglu=True) if FUSE_SWIGLU
-                                        else ops.TiledWeight(mlp.gate_up_w, 208),
+                                        gate_up=ops.TiledWeight(mlp.gate_up_w, gu_rows, swiglu=True) if FUSE_SWIGLU
+                                        else ops.TiledWeight(mlp.gate_up_w, gu_rows),
                                         down=ops.TiledWeight(mlp.down_proj.weight, 128) if down_t else None))
                     self._tiled = out
         return self._tiled or None
@@ -621,12 +623,14 @@ class UltravoxModel(nn.Module):
         qkv = torch.empty(B * S, (nq + 2 * nkv) * hd, dtype=BF16, device=dev)
         att = torch.empty(B * S, nq * hd, dtype=BF16, device=dev)
         ffn = tc.intermediate_size
-        gu = None if (self._tiled_weights() is not None and self._tiled_weights()[0]["gate_up"].swiglu) else torch.empty(B * S, 2 * ffn, dtype=BF16, device=dev)
+        tiled = self._tiled_weights()
+        if USE_WS and B * S > 256:
+            tiled = None            # the 128-row images belong to the weight-streaming GEMM (rows <= 256); larger batches read the row-major weights
+        fuse_act = tiled is not None and tiled[0]["gate_up"].swiglu
+        gu = None if fuse_act else torch.empty(B * S, 2 * ffn, dtype=BF16, device=dev)
         act = torch.empty(B * S, ffn, dtype=BF16, device=dev)
         rs = qkv.stride(0)
         layers = lm.model.layers
-        tiled = self._tiled_weights()
-        fuse_act = tiled is not None and tiled[0]["gate_up"].swiglu
         # RoPE rides in the q|k|v GEMM epilogue when a head is one 128-wide tile; same positions rule as uvx_rope
         rope = (cos, sin, positions, S, past, (nq + nkv) * hd) if (FUSE_ROPE and QKV_MODE == "fused" and hd == 128) else None
         qkv_flags = 1 if QKV_MODE == "r1" else 0

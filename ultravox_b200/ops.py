@@ -123,15 +123,16 @@ def gemm_raw(A_ptr: int, a_batch: int, a_rows: int, K: int, a_row_stride: int, a
 class TiledWeight:
     """Pre-tiled image of an ``nn.Linear`` weight [N, K] for the weight-streaming GEMM (include/uvx.h: ``uvx_tile_weight`` /
     ``uvx_gemm_args.w_tiled``): [ceil(N/R)][K/64][R][64] bf16, every (tile, k-block) box one contiguous R*128-byte run.
-    ``swiglu``: the rows alternate 8 gate rows / 8 up rows of the same features (fused gate|up projection, N = 2*ffn), which
-    is what ``linear_tiled(..., act=ACT_SWIGLU)`` needs to finish act(gate)*up inside the GEMM epilogue."""
+    ``swiglu``: gate and up rows of the same features share a tile (fused gate|up projection, N = 2*ffn), which is what
+    ``linear_tiled(..., act=ACT_SWIGLU)`` needs to finish act(gate)*up inside the GEMM epilogue: R = 128 -> 64 gate rows | 64 up
+    rows per tile (the weight-streaming GEMM, rows <= 256), R = 208 -> 8 gate / 8 up rows alternating (gemm_tc.cu)."""
 
     def __init__(self, w: torch.Tensor, R: int, swiglu: bool = False):
         _cuda(w, BF16, "w")
         self.N, self.K, self.R, self.swiglu = int(w.shape[0]), int(w.shape[1]), int(R), bool(swiglu)
         n_tiles = -(-self.N // R)
         self.image = torch.empty(n_tiles * (self.K // 64) * R * 64, dtype=BF16, device=w.device)
-        check(lib().uvx_tile_weight(w.data_ptr(), self.N, self.K, w.stride(0), R, 8 if swiglu else 0, self.image.data_ptr(),
+        check(lib().uvx_tile_weight(w.data_ptr(), self.N, self.K, w.stride(0), R, (64 if R == 128 else 8) if swiglu else 0, self.image.data_ptr(),
                                     _stream()), "uvx_tile_weight")
 
     @property
