@@ -78,14 +78,15 @@ int uvx_mel_to_timemajor(const float* mel, int64_t N, int n_mels, int64_t T, voi
  * positional embedding added after GELU (ref :896-899, r_batch_stride = 0).
  * Requirements: K % 8 == 0, N % 64 == 0, strides % 8 == 0, 16-byte aligned bases.
  * Split-K partial sums are reduced in a fixed order by a second kernel: results are deterministic.
- * Calls with a_batch == 1, a_rows <= 256, a plain bf16 output and a workspace (the LLM prefill at B = 1, decode batches, the
- * projector) run the WEIGHT-STREAMING form (csrc/gemm_ws.cu): 128 weight rows on the UMMA M dimension, the tokens on the UMMA N
+ * Opt-in (UVX_GEMM_WS=1 or uvx_debug_gemm_ws): calls with a_batch == 1, a_rows <= 256, a plain bf16 output and a workspace (the LLM
+ * prefill at B = 1, decode batches, the projector) run the WEIGHT-STREAMING form (csrc/gemm_ws.cu): 128 weight rows on the UMMA M dimension, the tokens on the UMMA N
  * dimension (round16(rows) instead of 256 padded rows), stream-K over (feature tile, k-block) units with the partial accumulators
  * of split tiles summed in CTA order by the tile's owner (deterministic for a given device).  Workspace contract for that form:
  * at least 148*128*round16(rows)*4 + 1024 bytes, and the LAST 1024 bytes (slot flags) are the library's: it zeroes them the first
  * time it sees the pointer and leaves them zero after every launch - do not write there.                                       */
 enum { UVX_ACT_NONE = 0, UVX_ACT_GELU = 1, UVX_ACT_SWIGLU = 2 };
 enum { UVX_DT_BF16 = 0, UVX_DT_F32 = 1 };
+enum { UVX_TILE_PLAIN = 0, UVX_TILE_ROPE_PAIRS = 1, UVX_TILE_GATE_UP_8 = 8, UVX_TILE_GATE_UP_16 = 16 };   /* uvx_tile_weight interleave */
 
 typedef struct uvx_gemm_args {
   const void* A;            /* bf16 */
@@ -112,8 +113,8 @@ typedef struct uvx_gemm_args {
    *   N zero) instead of the row-major matrix, so every k-block of a tile is ONE contiguous R*128-byte run of DRAM (the weight
    *   stream of the LLM prefill is HBM-bound; see uvx_tile_weight).  The kernel then uses R-wide tiles.
    * act = UVX_ACT_SWIGLU (needs w_tiled = 208 and the image built with interleave = 8: 8 gate rows alternate with the 8 up rows of
-   *   the same features - or, for the weight-streaming form, w_tiled = 128 with interleave = 64: 64 gate rows | 64 up rows per
-   *   tile): the epilogue writes C[row, f] = silu(gate_f) * up_f for the N/2 features
+   *   the same features - or, for the weight-streaming form, w_tiled = 128 with interleave = 16: 16 gate rows | 16 up rows per
+   *   32-row quarter): the epilogue writes C[row, f] = silu(gate_f) * up_f for the N/2 features
    *   (LlamaMLP act_fn(gate_proj(x)) * up_proj(x), hf:modeling_llama.py:183) - the [rows, N] intermediate never reaches HBM.
    * rope_cos/rope_sin [max_pos, 64] fp32 (+ rope_positions / rope_rows_per_seq / rope_pos_offset as in uvx_rope): tiles whose
    *   first column is < rope_cols (= (Hq + Hkv) * 128) are rotated in the epilogue (hf:modeling_llama.py:124-168, head_dim 128).  */
@@ -125,7 +126,8 @@ typedef struct uvx_gemm_args {
   int64_t rope_rows_per_seq, rope_pos_offset;
   int32_t flags;            /* bit 0: run the round-1 kernel variant (no TMA-store epilogue / weight-stream producer) for this call;
                              * bit 1: never take the weight-streaming form for this call                                           */
-  int32_t reserved;
+  int32_t w_perm;           /* row order inside the tiles of a w_tiled = 128 image: 0 = plain, 1 = UVX_TILE_ROPE_PAIRS (needed by the fused
+                             * RoPE of the weight-streaming form)                                                                 */
 } uvx_gemm_args;
 
 int uvx_gemm_bf16(const uvx_gemm_args* args, uvx_stream_t stream);
@@ -140,7 +142,7 @@ int uvx_debug_gemm_times(void* dev_buf);
 int uvx_debug_gemm_stages(int n);
 /* tuning hook: L2 prefetch distance of the weight stream in k-blocks (0 = off; < 0 = default) */
 int uvx_debug_gemm_pf(int pf);
-/* tuning hook of the weight-streaming form: enable (1 / 0; -1 = UVX_GEMM_WS env, default on), isolation mode (0 = off, 1 = loads
+/* tuning hook of the weight-streaming form: enable (1 / 0; -1 = UVX_GEMM_WS env, default off), isolation mode (0 = off, 1 = loads
  * only, 2 = MMAs only, 3 = no epilogue; + 8 / 16 / 32 / 64 skip slot stores / slot reads / flag traffic / output stores), forced grid size (0 = one CTA per SM) */
 int uvx_debug_gemm_ws(int enable, int mode, int grid);
 /* tuning hook: device buffer [grid][16] int64 of per-CTA phase timestamps of the weight-streaming form (NULL = off) */
@@ -148,8 +150,9 @@ int uvx_debug_gemm_ws_times(void* dev_buf);
 /* W [N, K] bf16 row-major (row stride w_row_stride) -> the pre-tiled image uvx_gemm_args.w_tiled = R reads:
  * out[t][kb][r][0:64] = W[row(t, r), kb*64 : kb*64+64], zero where row >= N.  interleave = 0: row(t, r) = t*R + r.
  * interleave = 8 (fused gate|up, N = 2*F, R % 16 == 0): r = 16*g + j -> gate feature t*R/2 + 8g + j (j < 8) = W row of that
- * feature, or the up row F + t*R/2 + 8g + (j-8) (j >= 8).  interleave = 64 (R = 128, weight-streaming form): r < 64 -> gate
- * feature 64t + r, r >= 64 -> up row F + 64t + (r - 64).  out: ceil(N/R) * (K/64) * R * 64 bf16 elements.                 */
+ * feature, or the up row F + t*R/2 + 8g + (j-8) (j >= 8).  interleave = 16 (R = 128, weight-streaming form): r = 32q + j ->
+ * gate feature 64t + 16q + j (j < 16) or the up row of feature 64t + 16q + (j - 16).  interleave = 1 (UVX_TILE_ROPE_PAIRS, R = 128 =
+ * head_dim): r = 32q + j -> row 128t + 16q + j (j < 16) or its rotation partner 128t + 64 + 16q + (j - 16).  out: ceil(N/R) * (K/64) * R * 64 bf16 elements.                 */
 int uvx_tile_weight(const void* W, int64_t N, int64_t K, int64_t w_row_stride, int32_t R, int32_t interleave, void* out,
                     uvx_stream_t stream);
 /* tuning hook: force the thread-block cluster shape cm x cn (row tiles x column tiles sharing operand loads; 0 = heuristic) */

@@ -603,3 +603,25 @@ def test_llama_hidden_fused_paths_match_unfused():
     assert rel(fused, plain) < 6e-3, rel(fused, plain)
     assert torch.equal(cache.k[0, :, :201], cache2.k[0, :, :201]) and torch.equal(cache.v[0, :, :201], cache2.v[0, :, :201])  # layer 0: same inputs
     assert rel(cache.k[1, :, :201], cache2.k[1, :, :201]) < 6e-3
+    # opt-in weight-streaming GEMMs (UVX_GEMM_WS=1: tokens on the UMMA N dimension, stream-K, 128-row images incl. the pair-permuted
+    # q|k|v image and the 16 | 16 gate|up image) on the same model: prefill at S = 201 and a one-token step on the cache
+    from ultravox_b200 import _lib
+    saved_ws = mm.USE_WS
+    try:
+        mm.USE_WS = True
+        _lib.lib().uvx_debug_gemm_ws(1, 0, 0)
+        model._tiled = None
+        tw = model._tiled_weights()
+        assert tw is not None and tw[0]["qkv"].rope_pairs and tw[0]["gate_up"].R == 128
+        cache3 = model.new_cache(1, 210)
+        ws = model.llama_hidden(emb.clone(), cache3).clone()
+        step_in = emb[:, :1].clone()
+        ws_step = model.llama_hidden(step_in.clone(), cache3).clone()
+    finally:
+        mm.USE_WS = saved_ws
+        _lib.lib().uvx_debug_gemm_ws(-1, 0, 0)
+        model._tiled = None
+    plain_step = model.llama_hidden(step_in.clone(), cache2).clone()
+    assert rel(ws, plain) < 6e-3, rel(ws, plain)
+    assert rel(ws_step, plain_step) < 8e-3, rel(ws_step, plain_step)
+    assert rel(cache3.k[0, :, :201], cache2.k[0, :, :201]) < 4e-3         # layer 0 keys: same inputs, another fp32 summation order

@@ -496,13 +496,20 @@ def test_kv_write_and_token_finish(ops):
 def _tile_ref(w, R, interleave):
     N, K = w.shape
     n_tiles = -(-N // R)
-    if interleave == 64:
+    if interleave == 16:
         F = N // 2
         rows = []
         for t in range(n_tiles):
             for r in range(R):
-                f = t * (R // 2) + r % (R // 2)
-                rows.append((f if r < R // 2 else F + f) if f < F else -1)
+                qq, j = divmod(r, 32)
+                f = t * (R // 2) + qq * 16 + (j & 15)
+                rows.append((f if j < 16 else F + f) if f < F else -1)
+    elif interleave == 1:
+        rows = []
+        for t in range(n_tiles):
+            for r in range(R):
+                qq, j = divmod(r, 32)
+                rows.append(t * R + (qq * 16 + j if j < 16 else 64 + qq * 16 + j - 16))
     elif interleave:
         F = N // 2
         rows = []
@@ -519,10 +526,10 @@ def _tile_ref(w, R, interleave):
 
 
 @pytest.mark.parametrize("N,K,R,inter", [(512, 256, 128, 0), (1000, 128, 208, 0), (1024, 192, 208, 8), (28672, 256, 208, 8), (6144, 128, 128, 0),
-                                         (1024, 192, 128, 64), (28672, 128, 128, 64)])
+                                         (1024, 192, 128, 16), (28672, 128, 128, 16), (6144, 128, 128, 1)])
 def test_tile_weight_layout(ops, N, K, R, inter):
     w = rnd(N, K, seed=3)
-    t = ops.TiledWeight(w, R, swiglu=bool(inter))
+    t = ops.TiledWeight(w, R, swiglu=inter in (8, 16), rope_pairs=inter == 1)
     assert torch.equal(t.image, _tile_ref(w, R, inter))
 
 
@@ -577,6 +584,15 @@ def F_silu_mul(g, u):
 @pytest.mark.parametrize("tiled", [False, True])
 @pytest.mark.parametrize("M,S,past,with_pos", [(201, 201, 0, False), (402, 201, 3, False), (77, 77, 0, True)])
 def test_gemm_fused_rope_bit_exact(ops, tiled, M, S, past, with_pos):
+    _rope_case(ops, tiled, M, S, past, with_pos, ws=False)
+
+
+@pytest.mark.parametrize("M,S,past,with_pos", [(201, 201, 0, False), (77, 77, 0, True), (8, 1, 37, False)])
+def test_gemm_ws_fused_rope_bit_exact(ops, ws_on, M, S, past, with_pos):
+    _rope_case(ops, True, M, S, past, with_pos, ws=True)
+
+
+def _rope_case(ops, tiled, M, S, past, with_pos, ws):
     """RoPE in the q|k|v GEMM epilogue (head_dim 128) == GEMM then uvx_rope, bit for bit; v heads untouched."""
     Hq, Hkv, D, K = 8, 2, 128, 1024
     N = (Hq + 2 * Hkv) * D
@@ -586,7 +602,7 @@ def test_gemm_fused_rope_bit_exact(ops, tiled, M, S, past, with_pos):
     cos, sin = ops.rope_tables(inv, 512, "cuda")
     from ultravox_b200 import _lib
     positions = torch.randint(0, 500, (M,), dtype=torch.int32, device="cuda") if with_pos else None
-    if M <= 256:
+    if ws:
         want = ops.linear(x, w)                              # weight-streaming form on both sides: same units, same summation order
     else:
         _lib.lib().uvx_debug_gemm_override(1128, 1)          # the fused form runs one 128-wide head per tile: same tiling for the reference
@@ -596,7 +612,11 @@ def test_gemm_fused_rope_bit_exact(ops, tiled, M, S, past, with_pos):
             _lib.lib().uvx_debug_gemm_override(0, 0)
     ops.rope_(want, Hq, Hkv, D, cos, sin, rows_per_seq=S, pos_offset=past, positions=positions)
     rope = (cos, sin, positions, S, past, (Hq + Hkv) * D)
-    got = ops.linear_tiled(x, ops.TiledWeight(w, 128), rope=rope) if tiled else ops.linear(x, w, rope=rope)
+    if ws:
+        got = ops.linear_tiled(x, ops.TiledWeight(w, 128, rope_pairs=True), rope=rope)      # weight-streaming form: pair-permuted image
+        assert torch.equal(ops.linear_tiled(x, ops.TiledWeight(w, 128, rope_pairs=True)), ops.linear(x, w))   # the permutation alone moves no bits
+    else:
+        got = ops.linear_tiled(x, ops.TiledWeight(w, 128), rope=rope) if tiled else ops.linear(x, w, rope=rope)
     assert torch.equal(got, want)
 
 
@@ -634,9 +654,18 @@ def _old_kernel(ops, *a, **k):
     return ops.linear(*a, flags=2, **k)
 
 
+@pytest.fixture
+def ws_on():
+    """The weight-streaming form is opt-in (UVX_GEMM_WS=1): these tests switch it on through the tuning hook."""
+    from ultravox_b200 import _lib
+    _lib.lib().uvx_debug_gemm_ws(1, 0, 0)
+    yield
+    _lib.lib().uvx_debug_gemm_ws(-1, 0, 0)
+
+
 @pytest.mark.parametrize("M,N,K", [(201, 4096, 4096), (201, 6144, 4096), (201, 28672, 512), (201, 4096, 14336), (1, 4096, 4096), (16, 1024, 256),
                                    (37, 192, 200), (256, 128, 64), (129, 320, 72), (77, 2048, 8192), (5, 16064, 512)])
-def test_gemm_ws_plain_and_epilogues(ops, M, N, K):
+def test_gemm_ws_plain_and_epilogues(ops, ws_on, M, N, K):
     """Rows <= 256 run the weight-streaming form (tokens on the UMMA N dimension, stream-K with in-kernel fix-up): fp32 math on
     the same bf16 inputs rounded once (1e-3), agreement with gemm_tc_kernel on the same call, run-to-run identical bits
     (the owner adds the contributors' partial accumulators in CTA order), nothing written outside the output window;
@@ -681,7 +710,7 @@ def test_gemm_ws_stream_k_any_grid(ops, grid):
 
 
 @pytest.mark.parametrize("M,F,K", [(201, 14336, 4096), (201, 1024, 512), (64, 512, 256), (1, 256, 128), (256, 128, 4096)])
-def test_gemm_ws_fused_swiglu(ops, M, F, K):
+def test_gemm_ws_fused_swiglu(ops, ws_on, M, F, K):
     """act(gate) * up in the weight-streaming epilogue (64 gate | 64 up rows per tile, partner values swapped through shared
     memory) against GEMM -> bf16 [M, 2F] -> uvx_swiglu (a few bf16 ulps: ex2 / rcp sigmoid) and against fp32 math."""
     x, w = rnd(M, K, seed=1), rnd(2 * F, K, scale=0.03, seed=2)

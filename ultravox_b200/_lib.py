@@ -24,7 +24,7 @@ class GemmArgs(C.Structure):
                 ("act", c_i32), ("out_dtype", c_i32), ("workspace", c_vp), ("workspace_bytes", c_i64),
                 ("norm_w", c_vp), ("norm_out", c_vp), ("norm_eps", c_f32), ("w_tiled", c_i32), ("rope_cols", c_i32),
                 ("rope_cos", c_vp), ("rope_sin", c_vp), ("rope_positions", c_vp), ("rope_rows_per_seq", c_i64),
-                ("rope_pos_offset", c_i64), ("flags", c_i32), ("reserved", c_i32)]
+                ("rope_pos_offset", c_i64), ("flags", c_i32), ("w_perm", c_i32)]
 
 
 class AttnArgs(C.Structure):

@@ -187,12 +187,19 @@ __global__ void tile_weight_kernel(const bf16* __restrict__ W, int64_t N, int64_
       const int g = r / 16, j = r % 16;
       const int64_t f = t * (R / 2) + (int64_t)g * 8 + (j & 7);
       src_row = f < F ? (j < 8 ? f : F + f) : -1;
-    } else if (interleave == 64) {
-      // weight-streaming GEMM (gemm_ws.cu): rows [0, R/2) of a tile are gate rows, [R/2, R) the up rows of the same features
+    } else if (interleave == 16) {
+      // weight-streaming GEMM (gemm_ws.cu), fused gate|up: every 32-row quarter of a tile holds 16 gate rows then the 16 up rows of the
+      // same features, so the partner of a row sits in the same TMEM lane quarter (= the same epilogue warp)
       const int64_t F = N / 2;
-      const int h = R / 2;
-      const int64_t f = t * h + (r % h);
-      src_row = f < F ? (r < h ? f : F + f) : -1;
+      const int qq = r >> 5, j = r & 31;
+      const int64_t f = t * (R / 2) + qq * 16 + (j & 15);
+      src_row = f < F ? (j < 16 ? f : F + f) : -1;
+    } else if (interleave == 1) {
+      // weight-streaming GEMM, fused RoPE (head_dim 128 = one tile): quarter qq holds head columns 16 qq .. 16 qq + 15, then their
+      // rotation partners 64 + 16 qq ..
+      const int qq = r >> 5, j = r & 31;
+      src_row = t * R + (j < 16 ? qq * 16 + j : 64 + qq * 16 + (j - 16));
+      if (src_row >= N) src_row = -1;
     } else {
       src_row = t * R + r;
       if (src_row >= N) src_row = -1;
@@ -210,8 +217,9 @@ extern "C" int uvx_tile_weight(const void* W, int64_t N, int64_t K, int64_t w_ro
   using namespace uvx;
   UVX_REQUIRE(W && out && N >= 1 && K >= 64 && K % 64 == 0 && w_row_stride % 8 == 0, "uvx_tile_weight: K %% 64 == 0 required");
   UVX_REQUIRE(R == 64 || R == 128 || R == 208 || R == 256, "uvx_tile_weight: R must be 64 / 128 / 208 / 256");
-  UVX_REQUIRE(interleave == 0 || (interleave == 8 && R % 16 == 0 && N % 16 == 0) || (interleave == 64 && R == 128 && N % 2 == 0),
-              "uvx_tile_weight: interleave must be 0, 8 (8 gate | 8 up rows) or 64 (R = 128: 64 gate | 64 up rows)");
+  UVX_REQUIRE(interleave == 0 || (interleave == 8 && R % 16 == 0 && N % 16 == 0) || (interleave == 16 && R == 128 && N % 32 == 0) ||
+                  (interleave == 1 && R == 128 && N % 128 == 0),
+              "uvx_tile_weight: interleave must be 0, 8 (8 gate | 8 up rows), 16 (R = 128: 16 gate | 16 up rows per 32) or 1 (R = 128: RoPE pairs)");
   const int64_t n_tiles = (N + R - 1) / R;
   const int64_t total_vec = n_tiles * (K / 64) * R * 8;
   int64_t blocks = (total_vec + 255) / 256;

@@ -1850,6 +1850,7 @@ extern "C" int uvx_gemm_bf16(const uvx_gemm_args* a, uvx_stream_t stream_) {
   // (a forced tile configuration / split count / cluster shape / isolation mode addresses gemm_tc_kernel: those calls stay there)
   read_forced();
   if (forced <= 0 && forced_splits <= 0 && forced_cm == 0 && g_gemm_dbg == 0 && gemm_ws_eligible(a)) return launch_gemm_ws(a, stream);
+  UVX_REQUIRE(a->w_perm == 0, "uvx_gemm_bf16: a permuted weight image (w_perm) is read by the weight-streaming form only (UVX_GEMM_WS=1, rows <= 256)");
   int cfg, splits, cm = 1, cn = 1;
   pick_cfg(a->a_rows, a->a_batch, a->N, a->K, &cfg, &splits);
   if (forced_cm > 0 && forced_cn > 0) {

@@ -59,9 +59,11 @@ struct WsParams {
   int act;                 // UVX_ACT_NONE / GELU / SWIGLU
   int bnt;                 // UMMA N = round16(M)
   int num_kb, n_tiles;
-  int units;               // n_tiles * num_kb
+  int units;               // stream-K units: dp_r * num_kb
+  int dp_w, dp_r;          // whole tiles per CTA after the stream-K share; tiles [0, dp_r) are the stream-K tiles
   int stage_bytes, stages;
   int tiled;               // W is the pre-tiled image [n_tiles][K/64][128][64]
+  int pairs;               // the image is pair-permuted (UVX_TILE_ROPE_PAIRS): per 32 rows, 16 rows of columns d | the 16 rows of d + 64
   float* ws_partial;       // [gridDim.x][bnt][128] fp32 partial accumulators (token-major: a warp writes 128 contiguous bytes)
   int* flags;              // [gridDim.x], 0 between launches: slot c is complete
   const float* rope_cos;
@@ -87,6 +89,19 @@ __device__ __forceinline__ int ws_ld_relaxed(const int* p) {
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// 8 floats = 16-byte chunks ch0, ch0 + 1 (ch0 even) of a pad row, chunk index XOR-swizzled with the token parity
+__device__ __forceinline__ void pad_read8(const float* row, int tok, int ch0, float* o) {
+  const float4 a = *reinterpret_cast<const float4*>(row + ((ch0 ^ (tok & 1)) << 2));
+  const float4 b = *reinterpret_cast<const float4*>(row + (((ch0 + 1) ^ (tok & 1)) << 2));
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+  o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+// global -> shared bulk copy (TMA engine, no tensor map), completion on an mbarrier
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void ws_st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 __global__ void __launch_bounds__(kWsThreads, 1)
@@ -102,15 +117,38 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + kWsMaxStages;
   uint64_t* tmem_full = empty_bar + kWsMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  uint64_t* fix_bar = tmem_empty + 2;                  // bulk copies of the contributors' slots (owner fix-up)
+  uint32_t* tmem_slot = (uint32_t*)(fix_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = p.num_kb;
   const int stages = p.stages;
   const int G = (int)gridDim.x;
-  // equal contiguous unit ranges (stream-K)
+  // Work of this CTA, in this order: (1) its share [u0, u1) of the stream-K units - the (tile, k-block) pairs of the first dp_r
+  // tiles cut into gridDim.x equal contiguous ranges - then (2) dp_w whole tiles (tile dp_r + blockIdx.x + k * gridDim.x).  The split
+  // tiles come FIRST: their partial-accumulator traffic and the owners' fix-up run in the shadow of the whole tiles' main loops, and
+  // the only exposed epilogue is the plain one of the last whole tile.  (Fewer tiles than CTAs: dp_w = 0, stream-K only.)
   const int u0 = (int)((int64_t)p.units * blockIdx.x / G);
   const int u1 = (int)((int64_t)p.units * (blockIdx.x + 1) / G);
+  const int dp_w = p.dp_w, dp_r = p.dp_r;
+  // next segment of the sequence: (tile, first k-block, k-blocks); `u` and `k` are the cursor
+#define WS_NEXT_SEGMENT(u, k, tile, kb0, len, more)                                        \
+  {                                                                                       \
+    more = true;                                                                          \
+    if (u < u1) {                                                                         \
+      tile = u / KB;                                                                      \
+      kb0 = u - tile * KB;                                                                \
+      len = (KB - kb0) < (u1 - u) ? (KB - kb0) : (u1 - u);                                \
+      u += len;                                                                           \
+    } else if (k < dp_w) {                                                                \
+      tile = dp_r + (int)blockIdx.x + k * G;                                              \
+      kb0 = 0;                                                                            \
+      len = KB;                                                                           \
+      ++k;                                                                                \
+    } else {                                                                              \
+      more = false;                                                                       \
+    }                                                                                     \
+  }
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -122,6 +160,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 8);  // one arrival per epilogue warp
     }
+    mbar_init(fix_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -149,47 +188,50 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     __syncwarp();
     const int tiled = p.tiled;
     int pre = 0;
-    if (p.pdl && mode != 2) {
-      // weights do not depend on the previous kernel: the W boxes of the first ring round go out before griddepcontrol.wait
-      pre = (u1 - u0) < stages ? (u1 - u0) : stages;
+    int cu = u0, ck = 0, tile = 0, kb0 = 0, len = 0;
+    bool more;
+    WS_NEXT_SEGMENT(cu, ck, tile, kb0, len, more);
+    if (p.pdl && mode != 2 && more) {
+      // weights do not depend on the previous kernel: the first W boxes of the first segment go out before griddepcontrol.wait
+      pre = len < stages ? len : stages;
       for (int i = 0; i < pre; ++i) {
-        const int u = u0 + i;
-        const int tile = u / KB, kb = u - tile * KB;
         mbar_expect_tx_e(&full_bar[i], (uint32_t)p.stage_bytes);
-        tma_load_2d_e(smem + i * p.stage_bytes, &tmW, tiled ? 0 : kb * kBK, tiled ? u * kBM : tile * kBM, &full_bar[i]);
+        tma_load_2d_e(smem + i * p.stage_bytes, &tmW, tiled ? 0 : (kb0 + i) * kBK, tiled ? (tile * KB + kb0 + i) * kBM : tile * kBM, &full_bar[i]);
       }
     }
     pdl_wait();
     int s = 0;
     uint32_t ph = 0;
-    int tile = u0 / KB, kb = u0 - tile * KB;
-    for (int u = u0; u < u1; ++u) {
-      uint8_t* sa = smem + s * p.stage_bytes;
-      if (pre > 0) {
-        --pre;
-        tma_load_2d_e(sa + kWsWBytes, &tmX, kb * kBK, 0, &full_bar[s]);
-      } else {
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        if (mode == 2) {   // MMAs only: hand the (never loaded) slot over
-          if (lane == 0) mbar_arrive(&full_bar[s]);
-          __syncwarp();
-        } else {
-          mbar_expect_tx_e(&full_bar[s], (uint32_t)p.stage_bytes);
-          tma_load_2d_e(sa, &tmW, tiled ? 0 : kb * kBK, tiled ? u * kBM : tile * kBM, &full_bar[s]);
+    while (more) {
+      for (int kb = kb0; kb < kb0 + len; ++kb) {
+        uint8_t* sa = smem + s * p.stage_bytes;
+        if (pre > 0) {
+          --pre;
           tma_load_2d_e(sa + kWsWBytes, &tmX, kb * kBK, 0, &full_bar[s]);
+        } else {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          if (mode == 2) {   // MMAs only: hand the (never loaded) slot over
+            if (lane == 0) mbar_arrive(&full_bar[s]);
+            __syncwarp();
+          } else {
+            mbar_expect_tx_e(&full_bar[s], (uint32_t)p.stage_bytes);
+            tma_load_2d_e(sa, &tmW, tiled ? 0 : kb * kBK, tiled ? (tile * KB + kb) * kBM : tile * kBM, &full_bar[s]);
+            tma_load_2d_e(sa + kWsWBytes, &tmX, kb * kBK, 0, &full_bar[s]);
+          }
         }
+        if (++s == stages) { s = 0; ph ^= 1u; }
       }
-      if (++s == stages) { s = 0; ph ^= 1u; }
-      if (++kb == KB) { kb = 0; ++tile; }
+      WS_NEXT_SEGMENT(cu, ck, tile, kb0, len, more);
     }
   } else if (warp == 1) {
     // ---- MMA issuer (convergent warp, elect.sync issues)
     const uint32_t idesc = make_idesc(p.bnt);
     int s = 0;
     uint32_t ph = 0, seg = 0;
-    for (int u = u0; u < u1; ++seg) {
-      const int kb0 = u % KB;
-      const int len = (KB - kb0) < (u1 - u) ? (KB - kb0) : (u1 - u);
+    int cu = u0, ck = 0, tile = 0, kb0 = 0, len = 0;
+    bool more;
+    WS_NEXT_SEGMENT(cu, ck, tile, kb0, len, more);
+    for (; more; ++seg) {
       const uint32_t acc = seg & 1u, aph = (seg >> 1) & 1u;
       mbar_wait(&tmem_empty[acc], aph ^ 1u);
       tc_fence_after();
@@ -217,27 +259,31 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       } else {
         umma_commit_e(&tmem_full[acc]);
       }
-      u += len;
+      WS_NEXT_SEGMENT(cu, ck, tile, kb0, len, more);
     }
+    (void)tile;
     if (dbg && lane == 0) dbg[3] = clock64();
   } else {
     // ---- epilogue
     const int q = warp & 3;              // TMEM lane quarter of this warp
     const int cpar = (warp - 2) >> 2;    // this warp takes the 32-token chunks of this parity
-    const int fl = q * 32 + lane;        // feature (accumulator row) inside the tile = index of this thread in its 4-warp group
+    const int fl = q * 32 + lane;        // accumulator row (tile row) of this thread
     const int nchunks = (p.bnt + 31) >> 5;
-    // transpose buffer of the group: [16 tokens][128 features] fp32.  A thread owns one feature (TMEM lane) x 32 tokens; the output
-    // rows want one token x consecutive features, so half a chunk at a time goes through shared memory and comes back as
-    // 8-feature pieces: 16-byte loads of the residual, 16-byte stores of the output.
-    float* const stg = reinterpret_cast<float*>(smem + kWsXchOff + cpar * (kWsXchBytes / 2));
+    // Per-warp transpose pad, [16 tokens][32 tile rows] fp32 (2 KB): a thread owns one tile row (TMEM lane) x 32 tokens, the output
+    // wants one token x consecutive features.  Half a chunk goes through the pad and comes back as 8-feature pieces (16-byte
+    // residual loads and output stores).  No cross-warp traffic: the pre-tiled images put partner rows (gate / up, RoPE pairs)
+    // into the same 32-row quarter.  16-byte chunks of a pad row are XOR-swizzled with the token parity (conflict-free both ways).
+    float* const pad = reinterpret_cast<float*>(smem + kWsXchOff) + (warp - 2) * 512;
+    const int wofs0 = lane, wofs1 = lane ^ 4;
     const bool swiglu = p.act == UVX_ACT_SWIGLU;
     const bool gelu = p.act == UVX_ACT_GELU;
     const bool store_out = !(p.dbg_mode & 64);
-    uint32_t seg = 0;
-    for (int u = u0; u < u1; ++seg) {
-      const int tile = u / KB, kb0 = u - tile * KB;
-      const int len = (KB - kb0) < (u1 - u) ? (KB - kb0) : (u1 - u);
-      u += len;
+    uint32_t seg = 0, fix_ph = 0;
+    int cu = u0, ck = 0, tile = 0, kb0 = 0, len = 0, ntile = 0, nkb0 = 0, nlen = 0;
+    bool more, nmore;
+    WS_NEXT_SEGMENT(cu, ck, tile, kb0, len, more);
+    for (; more; ++seg, tile = ntile, kb0 = nkb0, len = nlen, more = nmore) {
+      WS_NEXT_SEGMENT(cu, ck, ntile, nkb0, nlen, nmore);    // (nmore == false: this is the CTA's last segment)
       const uint32_t acc = seg & 1u, aph = (seg >> 1) & 1u;
       mbar_wait(&tmem_full[acc], aph);
       tc_fence_after();
@@ -251,9 +297,9 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         continue;
       }
       if (kb0 != 0) {
-        // ---- contributor: park the fp32 partial accumulator in this CTA's slot ([token][128 features]: a warp writes 128
-        // contiguous bytes per token; the token rows past M hold exact zeros - their activation rows are TMA zero fill), then
-        // raise the flag: bar.sync orders every thread's stores before the one release at gpu scope
+        // ---- contributor: park the fp32 partial accumulator in this CTA's slot ([token][128 tile rows]: a warp writes 128
+        // contiguous bytes per token; token rows past M hold exact zeros - their activation rows are TMA zero fill), then raise
+        // the flag: bar.sync orders every thread's stores before the one release at gpu scope
         float* slot = p.ws_partial + (size_t)blockIdx.x * (size_t)(kBM * p.bnt) + fl;
         for (int c = cpar; c < nchunks; c += 2) {
           uint32_t raw[32];
@@ -286,119 +332,161 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         const int tile_end = (tile + 1) * KB;
         for (int c2 = (int)blockIdx.x + 1; c2 < G && (int)((int64_t)p.units * c2 / G) < tile_end; ++c2) ++nc;
         if (p.dbg_mode & 32) nc = 0;
-        if (lane == 0) {
-          for (int j = 1; j <= nc; ++j)
-            while (ws_ld_relaxed(p.flags + blockIdx.x + j) == 0) {}
-          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      }
+      const int nread = (p.dbg_mode & 16) ? 0 : nc;
+      // When the owner segment is the LAST thing this CTA computes its operand ring is idle (every stage was consumed before the
+      // accumulator completed): the contributors' slots come in by bulk copies - 16 KB per (chunk, slot), as many chunks per pass
+      // as the ring holds - instead of 4-byte loads whose L2 latency the eight epilogue warps cannot cover on the exposed tail.
+      // With whole tiles still to come the ring is busy and the fix-up is hidden under their main loops: plain loads then.
+      const bool bulk = nread > 0 && !nmore;
+      const int ring_chunks = (stages * p.stage_bytes) / 16384;
+      int per_pass = bulk ? (ring_chunks / nread < nchunks ? ring_chunks / nread : nchunks) : nchunks;
+      if (per_pass < 1) per_pass = 1;   // (the host keeps tiles to <= 9 members; 13 chunk buffers fit the ring at 208 tokens)
+      if (nc > 0) {
+        if (bulk) {
+          if (warp == 2 && lane == 0) {
+            for (int j = 1; j <= nc; ++j)
+              while (ws_ld_relaxed(p.flags + blockIdx.x + j) == 0) {}
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            asm volatile("fence.proxy.async;" ::: "memory");   // slots written through the generic proxy, bulk copies read through the async proxy
+          }
+        } else {
+          if (lane == 0) {
+            for (int j = 1; j <= nc; ++j)
+              while (ws_ld_relaxed(p.flags + blockIdx.x + j) == 0) {}
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
       if (stamp) dbg[4 + 3 * seg + 1] = clock64();
-      const int nread = (p.dbg_mode & 16) ? 0 : nc;
-      const int f = tile * kBM + fl;                 // W row of this thread
-      const bool rope = p.rope_cos != nullptr && tile * kBM < p.rope_cols;
-      const float bias = (p.bias && f < p.N) ? __bfloat162float(p.bias[f]) : 0.f;
-      for (int c = cpar; c < nchunks; c += 2) {
-        uint32_t raw[32];
-        tmem_ld32(tbase + (uint32_t)(c * 32), raw);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-        const bool full = c * 32 + 32 <= p.bnt;       // (else 16 tokens: bnt is a multiple of 16)
-        for (int j = 1; j <= nread; ++j) {
-          const float* src = p.ws_partial + (size_t)(blockIdx.x + j) * (size_t)(kBM * p.bnt) + (size_t)c * 32 * kBM + fl;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += src[i * kBM];
-          if (full) {
-#pragma unroll
-            for (int i = 16; i < 32; ++i) v[i] += src[i * kBM];
-          }
-        }
-        if (!(swiglu || rope)) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x = v[i] * p.alpha + bias;
-            if (gelu) x = gelu_fast(x);
-            v[i] = x;
-          }
-        }
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          if (half == 1 && !full) break;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) stg[i * kBM + fl] = v[half * 16 + i];
-          ws_bar_sync(2 + cpar, 128);
-          const int tbase_tok = c * 32 + half * 16;
-          if (swiglu) {
-            // tile rows 0..63 are gate rows, 64..127 the up rows of the same 64 features: 16 tokens x 64 outputs = one 8-feature piece
-            // per thread.  Rounding order of the unfused path: gate / up rounded to bf16, silu rounded to bf16, product rounded.
-            const int tok = fl >> 3, f8 = (fl & 7) * 8;
-            const int t = tbase_tok + tok;
-            const float4* g4 = reinterpret_cast<const float4*>(stg + tok * kBM + f8);
-            const float4* u4 = reinterpret_cast<const float4*>(stg + tok * kBM + 64 + f8);
-            const float4 ga = g4[0], gb = g4[1], ua = u4[0], ub = u4[1];
-            const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w}, uu[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
-            float o[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float gate = __bfloat162float(__float2bfloat16_rn(gg[e] * p.alpha));
-              const float up = __bfloat162float(__float2bfloat16_rn(uu[e] * p.alpha));
-              o[e] = __bfloat162float(__float2bfloat16_rn(silu_fast(gate))) * up;
+      // tile row -> output feature of this thread's 8-lane piece k: plain rows, or the pair-permuted image (16 rows d | 16 rows d + 64)
+      const int64_t tile_f0 = (int64_t)tile * kBM;
+      const bool rope = p.rope_cos != nullptr && tile_f0 < p.rope_cols;
+      for (int c_lo = 0; c_lo < nchunks; c_lo += per_pass) {
+        const int c_hi = c_lo + per_pass < nchunks ? c_lo + per_pass : nchunks;
+        if (bulk) {
+          if (c_lo > 0) ws_bar_sync(1, 256);   // every warp is done with the previous pass's buffers
+          if (warp == 2 && lane == 0) {
+            uint32_t bytes = 0;
+            for (int c = c_lo; c < c_hi; ++c) bytes += (uint32_t)((c * 32 + 32 <= p.bnt ? 32 : 16) * 512) * (uint32_t)nread;
+            mbar_expect_tx(fix_bar, bytes);
+            for (int c = c_lo; c < c_hi; ++c) {
+              const uint32_t cb = (uint32_t)((c * 32 + 32 <= p.bnt ? 32 : 16) * 512);
+              for (int j = 1; j <= nread; ++j) {
+                const float* src = p.ws_partial + (size_t)(blockIdx.x + j) * (size_t)(kBM * p.bnt) + (size_t)c * 32 * kBM;
+                bulk_load(smem + ((c - c_lo) * nread + (j - 1)) * 16384, src, cb, fix_bar);
+              }
             }
-            const int64_t fo = (int64_t)tile * 64 + f8;
-            if (t < p.M && fo < p.N / 2 && store_out) *reinterpret_cast<bf16x8*>(p.C + (int64_t)t * p.c_row_stride + fo) = pack8(o);
-          } else if (rope) {
-            // tile = one 128-wide head: features d and d + 64 rotate together (hf:modeling_llama.py:124-168).  The projection is
-            // rounded to bf16 first, the rotation runs in fp32 on those values (rope_pair: same bits as uvx_rope).
-            const int tok = fl >> 3, d8 = (fl & 7) * 8;
-            const int t = tbase_tok + tok;
-            if (t < p.M) {
-              const float4* a4 = reinterpret_cast<const float4*>(stg + tok * kBM + d8);
-              const float4* b4 = reinterpret_cast<const float4*>(stg + tok * kBM + 64 + d8);
-              const float4 xa = a4[0], xb = a4[1], ya = b4[0], yb = b4[1];
-              const float x1[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w}, x2[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
-              const int64_t pos = p.rope_pos ? (int64_t)p.rope_pos[t] : p.rope_pos_offset + (t % p.rope_rows_per_seq);
-              const float4* c4 = reinterpret_cast<const float4*>(p.rope_cos + pos * 64 + d8);
-              const float4* s4 = reinterpret_cast<const float4*>(p.rope_sin + pos * 64 + d8);
-              const float4 ca = c4[0], cb = c4[1], sa = s4[0], sb = s4[1];
-              const float cs[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w}, sn[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-              float o1[8], o2[8];
+          }
+          mbar_wait(fix_bar, fix_ph);
+          fix_ph ^= 1u;
+        }
+        for (int c = c_lo + ((cpar - c_lo) & 1); c < c_hi; c += 2) {
+          uint32_t raw[32];
+          tmem_ld32(tbase + (uint32_t)(c * 32), raw);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+          const bool full = c * 32 + 32 <= p.bnt;       // (else 16 tokens: bnt is a multiple of 16)
+          for (int j = 0; j < nread; ++j) {
+            const float* src = bulk ? reinterpret_cast<const float*>(smem + ((c - c_lo) * nread + j) * 16384) + fl
+                                    : p.ws_partial + (size_t)(blockIdx.x + 1 + j) * (size_t)(kBM * p.bnt) + (size_t)c * 32 * kBM + fl;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += src[i * kBM];
+            if (full) {
+#pragma unroll
+              for (int i = 16; i < 32; ++i) v[i] += src[i * kBM];
+            }
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            if (half == 1 && !full) break;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pad[i * 32 + ((i & 1) ? wofs1 : wofs0)] = v[half * 16 + i];
+            __syncwarp();
+            const int tok0 = c * 32 + half * 16;
+            if (swiglu) {
+              // quarter rows 0..15 = gate rows, 16..31 = the up rows of the same 16 features: 16 tokens x 16 outputs = one 8-feature
+              // piece per lane.  Rounding order of the unfused path: gate / up rounded to bf16, silu rounded to bf16, product rounded.
+              const int tok = lane >> 1, h = lane & 1;
+              const int t = tok0 + tok;
+              float gg[8], uu[8], o[8];
+              pad_read8(pad + tok * 32, tok, 2 * h, gg);
+              pad_read8(pad + tok * 32, tok, 4 + 2 * h, uu);
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                const float a = __bfloat162float(__float2bfloat16_rn(x1[e] * p.alpha));
-                const float b = __bfloat162float(__float2bfloat16_rn(x2[e] * p.alpha));
-                rope_pair(a, b, cs[e], sn[e], o1[e], o2[e]);
+                const float gate = __bfloat162float(__float2bfloat16_rn(gg[e] * p.alpha));
+                const float up = __bfloat162float(__float2bfloat16_rn(uu[e] * p.alpha));
+                o[e] = __bfloat162float(__float2bfloat16_rn(silu_fast(gate))) * up;
               }
-              if (store_out) {
-                bf16* crow = p.C + (int64_t)t * p.c_row_stride + (int64_t)tile * kBM;
-                *reinterpret_cast<bf16x8*>(crow + d8) = pack8(o1);
-                *reinterpret_cast<bf16x8*>(crow + 64 + d8) = pack8(o2);
-              }
-            }
-          } else {
-            // 16 tokens x 128 features = two 8-feature pieces per thread
+              const int64_t fo = (int64_t)tile * 64 + q * 16 + h * 8;
+              if (t < p.M && fo < p.N / 2 && store_out) *reinterpret_cast<bf16x8*>(p.C + (int64_t)t * p.c_row_stride + fo) = pack8(o);
+            } else if (rope) {
+              // pair-permuted image: quarter rows 0..15 = head columns d = 16 q + r, rows 16..31 = columns d + 64, which rotate together
+              // (hf:modeling_llama.py:124-168).  The projection is rounded to bf16 first, the rotation runs in fp32 on those values
+              // (rope_pair: same bits as uvx_rope).
+              const int tok = lane >> 1, h = lane & 1;
+              const int t = tok0 + tok;
+              if (t < p.M) {
+                float x1[8], x2[8], o1[8], o2[8];
+                pad_read8(pad + tok * 32, tok, 2 * h, x1);
+                pad_read8(pad + tok * 32, tok, 4 + 2 * h, x2);
+                const int d8 = q * 16 + h * 8;
+                const int64_t pos = p.rope_pos ? (int64_t)p.rope_pos[t] : p.rope_pos_offset + (t % p.rope_rows_per_seq);
+                const float4* c4 = reinterpret_cast<const float4*>(p.rope_cos + pos * 64 + d8);
+                const float4* s4 = reinterpret_cast<const float4*>(p.rope_sin + pos * 64 + d8);
+                const float4 ca = c4[0], cb = c4[1], sa = s4[0], sb = s4[1];
+                const float cs[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w}, sn[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const int pc = fl + 128 * k;
-              const int tok = pc >> 4, f8 = (pc & 15) * 8;
-              const int t = tbase_tok + tok;
-              const int64_t fg = (int64_t)tile * kBM + f8;
-              if (t < p.M && fg < p.N) {
-                const float4* s4 = reinterpret_cast<const float4*>(stg + tok * kBM + f8);
-                const float4 a = s4[0], b = s4[1];
-                float o[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                if (p.R) {
-                  float r[8];
-                  unpack8(*reinterpret_cast<const bf16x8*>(p.R + (int64_t)t * p.r_row_stride + fg), r);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) o[e] += r[e];
+                for (int e = 0; e < 8; ++e) {
+                  const float a = __bfloat162float(__float2bfloat16_rn(x1[e] * p.alpha));
+                  const float b = __bfloat162float(__float2bfloat16_rn(x2[e] * p.alpha));
+                  rope_pair(a, b, cs[e], sn[e], o1[e], o2[e]);
                 }
-                if (store_out) *reinterpret_cast<bf16x8*>(p.C + (int64_t)t * p.c_row_stride + fg) = pack8(o);
+                if (store_out) {
+                  bf16* crow = p.C + (int64_t)t * p.c_row_stride + tile_f0;
+                  *reinterpret_cast<bf16x8*>(crow + d8) = pack8(o1);
+                  *reinterpret_cast<bf16x8*>(crow + 64 + d8) = pack8(o2);
+                }
+              }
+            } else {
+              // 16 tokens x 32 tile rows = two 8-feature pieces per lane
+#pragma unroll
+              for (int k2 = 0; k2 < 2; ++k2) {
+                const int idx = lane + 32 * k2;
+                const int tok = idx >> 2, k = idx & 3;
+                const int t = tok0 + tok;
+                const int64_t fg = tile_f0 + (p.pairs ? (k < 2 ? q * 16 + k * 8 : 64 + q * 16 + (k - 2) * 8) : q * 32 + k * 8);
+                if (t < p.M && fg < p.N) {
+                  float o[8];
+                  pad_read8(pad + tok * 32, tok, 2 * k, o);
+                  if (p.bias) {
+                    float bb[8];
+                    unpack8(*reinterpret_cast<const bf16x8*>(p.bias + fg), bb);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = o[e] * p.alpha + bb[e];
+                  } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] *= p.alpha;
+                  }
+                  if (gelu) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = gelu_fast(o[e]);
+                  }
+                  if (p.R) {
+                    float r[8];
+                    unpack8(*reinterpret_cast<const bf16x8*>(p.R + (int64_t)t * p.r_row_stride + fg), r);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] += r[e];
+                  }
+                  if (store_out) *reinterpret_cast<bf16x8*>(p.C + (int64_t)t * p.c_row_stride + fg) = pack8(o);
+                }
               }
             }
+            __syncwarp();   // the pad is rewritten by the next half chunk
           }
-          ws_bar_sync(2 + cpar, 128);   // the buffer is rewritten by the next half chunk
         }
       }
       tc_fence_before();
@@ -461,7 +549,9 @@ static int ws_encode_2d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t
   return UVX_OK;
 }
 
-static int g_ws_enable = -1;   // -1: UVX_GEMM_WS env or 1
+static int g_ws_enable = -1;   // -1: UVX_GEMM_WS env or 0 (opt-in: measured at parity with gemm_tc_kernel on gate|up and behind it on
+                               // the 32-48-tile projections, profiles/r2_ws2_*.txt - both forms sit at the shared-memory bandwidth of
+                               // the SM, TMA writes + UMMA operand reads = 126 B/clk at the HBM rate)
 static int g_ws_dbg = 0;
 static int g_ws_grid = 0;      // tuning: force the grid (0 = #SMs)
 static long long* g_ws_times = nullptr;
@@ -469,7 +559,7 @@ static long long* g_ws_times = nullptr;
 int gemm_ws_enabled() {
   if (g_ws_enable < 0) {
     const char* e = getenv("UVX_GEMM_WS");
-    g_ws_enable = e ? atoi(e) : 1;
+    g_ws_enable = e ? atoi(e) : 0;
   }
   return g_ws_enable;
 }
@@ -500,7 +590,9 @@ bool gemm_ws_eligible(const uvx_gemm_args* a) {
   if (a->K % 8 != 0 || a->K < 64 || a->N < 128) return false;
   if (a->w_tiled && (a->w_tiled != 128 || a->K % kBK != 0)) return false;
   if (a->act == UVX_ACT_SWIGLU && (a->w_tiled != 128 || a->N % 256 != 0 || a->bias || a->R)) return false;
-  if (a->rope_cos && (a->rope_cols % 128 != 0 || a->bias || a->R || a->act != UVX_ACT_NONE || a->alpha != 1.0f)) return false;
+  if (a->w_perm != 0 && (a->w_perm != 1 || a->w_tiled != 128 || a->N % 128 != 0 || a->act == UVX_ACT_SWIGLU)) return false;
+  // fused RoPE rotates columns d and d + 64 of a head: they share a 32-row quarter only in the pair-permuted image
+  if (a->rope_cos && (a->w_perm != 1 || a->rope_cols % 128 != 0 || a->bias || a->R || a->act != UVX_ACT_NONE || a->alpha != 1.0f)) return false;
   const int bnt = (int)((a->a_rows + 15) / 16 * 16);
   const int64_t n_tiles = (a->N + kBM - 1) / kBM, num_kb = (a->K + kBK - 1) / kBK;
   if (n_tiles * num_kb >= (1ll << 30)) return false;
@@ -524,11 +616,11 @@ int launch_gemm_ws(const uvx_gemm_args* a, cudaStream_t stream) {
   p.bnt = (p.M + 15) / 16 * 16;
   p.num_kb = (p.K + kBK - 1) / kBK;
   p.n_tiles = (p.N + kBM - 1) / kBM;
-  p.units = p.n_tiles * p.num_kb;
   p.stage_bytes = kWsWBytes + p.bnt * kBK * 2;
   p.stages = kWsXchOff / p.stage_bytes;
   if (p.stages > kWsMaxStages) p.stages = kWsMaxStages;
   p.tiled = a->w_tiled ? 1 : 0;
+  p.pairs = a->w_perm == 1 ? 1 : 0;
   p.rope_cos = a->rope_cos;
   p.rope_sin = a->rope_sin;
   p.rope_pos = a->rope_positions;
@@ -543,8 +635,24 @@ int launch_gemm_ws(const uvx_gemm_args* a, cudaStream_t stream) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (sms <= 0 || sms > 148) sms = 148;
   int grid = g_ws_grid > 0 && g_ws_grid <= sms ? g_ws_grid : sms;
-  if (grid > p.units / 4) grid = p.units / 4;   // at least four k-blocks per CTA
-  if (grid < 1) grid = 1;
+  // at least four k-blocks per CTA, and at most ~9 CTAs per tile (the owner's fix-up stages every contributor's chunk in the ring)
+  const int min_units = (p.num_kb + 7) / 8 > 4 ? (p.num_kb + 7) / 8 : 4;
+  if (p.n_tiles >= grid) {
+    // more tiles than CTAs: whole tiles round-robin, the remainder (plus one round, if the remainder alone is too small to cut
+    // into `grid` useful shares) as stream-K units that every CTA works off FIRST
+    p.dp_w = p.n_tiles / grid;
+    p.dp_r = p.n_tiles - p.dp_w * grid;
+    if (p.dp_r > 0 && p.dp_r * p.num_kb < grid * min_units) {
+      p.dp_w -= 1;
+      p.dp_r += grid;
+    }
+  } else {
+    p.dp_w = 0;
+    p.dp_r = p.n_tiles;
+    if (grid > p.dp_r * p.num_kb / min_units) grid = p.dp_r * p.num_kb / min_units;
+    if (grid < 1) grid = 1;
+  }
+  p.units = p.dp_r * p.num_kb;
   p.ws_partial = (float*)a->workspace;
   p.flags = (int*)((char*)a->workspace + (size_t)a->workspace_bytes - kWsFlagBytes);
   int rc = ws_flags_ready(p.flags, stream);

@@ -33,7 +33,7 @@ USE_TILED = os.environ.get("UVX_TILED", "1") != "0"       # LLM prefill GEMMs st
 FUSE_ROPE = os.environ.get("UVX_FUSE_ROPE", "1") != "0"   # RoPE in the q|k|v GEMM epilogue (head_dim 128)
 QKV_MODE = os.environ.get("UVX_QKV_MODE", "fused")        # Llama q|k|v GEMM: "fused" RoPE epilogue | "r1" round-1 kernel + uvx_rope | "tma" + uvx_rope
 TILED_SET = os.environ.get("UVX_TILED_SET", "gate_up")        # which LLM projections get a pre-tiled image: "all" | "gate_up" | "mlp" (in situ only gate|up gains: r2_ab_bench_v3)
-USE_WS = os.environ.get("UVX_GEMM_WS", "1") != "0"         # rows <= 256: weight-streaming GEMM (tokens on the UMMA N dimension, stream-K), 128-row images of all four projections
+USE_WS = os.environ.get("UVX_GEMM_WS", "0") == "1"         # opt-in: rows <= 256 run the weight-streaming GEMM (tokens on the UMMA N dimension, stream-K) over 128-row images of all four projections
 FUSE_SWIGLU = os.environ.get("UVX_FUSE_SWIGLU", "1") != "0"   # act(gate)*up in the gate|up GEMM epilogue (needs the tiled image)
 BF16 = torch.bfloat16
 
@@ -475,7 +475,8 @@ class UltravoxModel(nn.Module):
                         attn_t = USE_WS or TILED_SET == "all"
                         down_t = USE_WS or TILED_SET in ("all", "mlp")
                         gu_rows = 128 if USE_WS else 208
-                        out.append(dict(qkv=ops.TiledWeight(sa.qkv_w, 128) if attn_t else None,
+                        lm_hd = self.language_model.head_dim
+                        out.append(dict(qkv=ops.TiledWeight(sa.qkv_w, 128, rope_pairs=USE_WS and lm_hd == 128) if attn_t else None,
                                         o=ops.TiledWeight(sa.o_proj.weight, 128) if attn_t else None,
                                         gate_up=ops.TiledWeight(mlp.gate_up_w, gu_rows, swiglu=True) if FUSE_SWIGLU
                                         else ops.TiledWeight(mlp.gate_up_w, gu_rows),

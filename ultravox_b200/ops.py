@@ -127,13 +127,16 @@ class TiledWeight:
     ``linear_tiled(..., act=ACT_SWIGLU)`` needs to finish act(gate)*up inside the GEMM epilogue: R = 128 -> 64 gate rows | 64 up
     rows per tile (the weight-streaming GEMM, rows <= 256), R = 208 -> 8 gate / 8 up rows alternating (gemm_tc.cu)."""
 
-    def __init__(self, w: torch.Tensor, R: int, swiglu: bool = False):
+    def __init__(self, w: torch.Tensor, R: int, swiglu: bool = False, rope_pairs: bool = False):
         _cuda(w, BF16, "w")
         self.N, self.K, self.R, self.swiglu = int(w.shape[0]), int(w.shape[1]), int(R), bool(swiglu)
+        self.rope_pairs = bool(rope_pairs)
+        if rope_pairs and (swiglu or R != 128 or self.N % 128 != 0):
+            raise ValueError("rope_pairs: a 128-row image of whole 128-wide heads")
         n_tiles = -(-self.N // R)
         self.image = torch.empty(n_tiles * (self.K // 64) * R * 64, dtype=BF16, device=w.device)
-        check(lib().uvx_tile_weight(w.data_ptr(), self.N, self.K, w.stride(0), R, (64 if R == 128 else 8) if swiglu else 0, self.image.data_ptr(),
-                                    _stream()), "uvx_tile_weight")
+        inter = ((16 if R == 128 else 8) if swiglu else (1 if rope_pairs else 0))
+        check(lib().uvx_tile_weight(w.data_ptr(), self.N, self.K, w.stride(0), R, inter, self.image.data_ptr(), _stream()), "uvx_tile_weight")
 
     @property
     def n_out(self) -> int:
@@ -174,6 +177,7 @@ def linear_tiled(x: torch.Tensor, wt: TiledWeight, out: Optional[torch.Tensor] =
     if norm is not None:
         a.norm_w, a.norm_eps, a.norm_out = norm[0].data_ptr(), float(norm[1]), norm[2].data_ptr()
     a.w_tiled = wt.R
+    a.w_perm = 1 if wt.rope_pairs else 0
     if rope is not None:
         cos, sin, positions, rows_per_seq, pos_offset, rope_cols = rope
         a.rope_cos, a.rope_sin, a.rope_positions = cos.data_ptr(), sin.data_ptr(), _p(positions)
