@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true", help="skip the stock-transformers bf16 GPU arm (N=1 only)")
     ap.add_argument("--no-train-record", action="store_true", help="skip the secondary cfg3 (adapter training) record")
+    ap.add_argument("--no-decode-record", action="store_true", help="skip the secondary cfg4-style (graphed decode) record")
+    ap.add_argument("--decode-tokens", type=int, default=33, help="tokens generated per stream in the decode record")
     ap.add_argument("--train-batch", type=int, default=4, help="clips per GPU of the secondary cfg3 record")
     ap.add_argument("--ttft-iters", type=int, default=200, help="end-to-end iterations behind TTFT p50 / p90 (>= --steps)")
     ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU arm (0 = sweep and keep the fastest)")
@@ -444,6 +446,54 @@ def train_record(model, cfg, args, rank, world, dev):
 
 
 # ----------------------------------------------------------------------------------------------- main
+def decode_record(model, cfg, eng, args, world):
+    """Secondary record (BASELINE config 4's serving loop on the cfg2 backbone): prefill of the bench clip's prompt, then
+    `--decode-tokens` greedy decode steps, each ONE CUDA-graph replay of `DecodeEngine` (embedding -> 32 layers of weight-streaming
+    GEMV / KV-cache attention -> lm head -> pick -> bookkeeping, nothing on the host), for 1 and 8 concurrent streams per GPU.
+    CUDA events around the decode loop; the HBM fraction counts the decoder weights once per step (what a step must read)."""
+    import torch
+    from ultravox_b200.engine import DecodeEngine
+    out = {"config": "cfg4 serving loop on the cfg2 (8B) backbone: 30 s clip prefill + greedy decode, CUDA-graphed step; the 70B replica "
+                     "is scripts/bench_configs.py decode", "new_tokens": args.decode_tokens, "streams": {}}
+    lm = model.language_model
+    wbytes = sum(p.numel() for n, p in lm.named_parameters() if "embed_tokens" not in n) * 2
+    peak = 0.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    from ultravox_b200 import ops
+    with torch.no_grad():                                      # the spliced prompt of the bench clip (same stages as the engine's step)
+        tm = ops.logmel(eng.wave, eng.n_mels, want_f32=False, want_tm=True)
+        aud = model.project_audio(model.encode_audio(tm, None, kv_len=eng.kv_len))
+        Bp, Sp = eng.input_ids.shape
+        src = ops.splice_plan(eng.start, eng.tok_len, eng.abs, Bp, Sp, aud.shape[1])
+        emb1 = ops.embed_splice(eng.input_ids, lm.model.embed_tokens.weight, aud, src)[:1].clone()
+    for B in (1, 8):
+        emb = emb1.expand(B, -1, -1).contiguous()
+        S = emb.shape[1]
+        de = DecodeEngine(model, B, S + args.decode_tokens + 2)
+        for rep in range(2):                                   # first pass captures the graph
+            torch.cuda.synchronize()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            de.prefill(emb.clone())
+            e1.record()
+            for _ in range(args.decode_tokens - 1):
+                de.step()
+            e2.record()
+            torch.cuda.synchronize()
+        ms_tok = e1.elapsed_time(e2) / max(1, args.decode_tokens - 1)
+        out["streams"][str(B)] = {"prefill_ms": e0.elapsed_time(e1), "decode_ms_per_token": ms_tok,
+                                  "tok_per_s_per_gpu": B / (ms_tok * 1e-3), "tok_per_s_all_gpus": world * B / (ms_tok * 1e-3),
+                                  "hbm_frac_weights_once": (wbytes / (ms_tok * 1e-3) / 1e9 / peak) if peak else None,
+                                  "launches_per_step": de.launches_per_step}
+        del de
+        torch.cuda.empty_cache()
+    out["weights_gb"] = wbytes / 1e9
+    return out
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -561,6 +611,13 @@ def main():
         except Exception as e:
             train = {"error": repr(e)[:300]}
 
+    decode = None
+    if not args.no_decode_record:
+        try:
+            decode = decode_record(model, cfg, eng, args, world)
+        except Exception as e:
+            decode = {"error": repr(e)[:300]}
+
     if rank == 0:
         peaks = {}
         try:
@@ -576,7 +633,7 @@ def main():
                 "ttft_ms_p50": statistics.median(per) * 1e3, "ttft_ms_p90": per_sorted[int(0.9 * (len(per) - 1))] * 1e3,
                 "ttft_ms_p50_cuda_events": per_ev[len(per_ev) // 2], "ttft_iters": n_tt,
                 "gpu_launches": eng.launches_per_step * K, "launches_per_step": eng.launches_per_step,
-                "clocks": clocks, "token_check": tokens_ok, "train": train}
+                "clocks": clocks, "token_check": tokens_ok, "train": train, "decode": decode}
         state = mel_used = lib_logits = None
         if not args.no_cpu_baseline:
             try:      # material for the CPU leg, fetched before anything else touches the allocator

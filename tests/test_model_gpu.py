@@ -622,6 +622,8 @@ def test_llama_hidden_fused_paths_match_unfused():
         _lib.lib().uvx_debug_gemm_ws(-1, 0, 0)
         model._tiled = None
     plain_step = model.llama_hidden(step_in.clone(), cache2).clone()
-    assert rel(ws, plain) < 6e-3, rel(ws, plain)
-    assert rel(ws_step, plain_step) < 8e-3, rel(ws_step, plain_step)
+    # every projection sums in another order and the RMSNorm reads the bf16-rounded residual stream (the reference's own order)
+    # instead of the fp32 split-K sums: two more roundings per layer than between the two gemm_tc paths above
+    assert rel(ws, plain) < 1.2e-2, rel(ws, plain)
+    assert rel(ws_step, plain_step) < 1.5e-2, rel(ws_step, plain_step)
     assert rel(cache3.k[0, :, :201], cache2.k[0, :, :201]) < 4e-3         # layer 0 keys: same inputs, another fp32 summation order
