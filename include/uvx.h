@@ -310,6 +310,13 @@ int uvx_transpose_bf16(const void* in, int64_t rows, int64_t cols, int64_t in_ro
 int uvx_rmsnorm_bwd(const void* dy, const void* x, const void* w, const void* dres, void* dx, float* dw,
                     int64_t rows, int64_t cols, int64_t x_row_stride, int64_t group_rows, int64_t group_stride,
                     int64_t valid_elems, float eps, uvx_stream_t stream);
+/* LayerNorm data gradient (+ optional residual-branch gradient dres): dx = LN'(x)^T dy + dres; the norm's weight / bias are frozen
+ * (encoder backward of LoRA training, hf:modeling_whisper.py:403-440).  cols %% 8 == 0, <= 2048.                                */
+int uvx_layernorm_bwd(const void* dy, const void* x, const void* w, const void* dres, void* dx, int64_t rows, int64_t cols,
+                      float eps, uvx_stream_t stream);
+/* erf-form GELU on bf16 (training keeps fc1's pre-activation) and its derivative: dx = dy * (Phi(x) + x phi(x)); n %% 8 == 0 */
+int uvx_gelu(const void* x, void* y, int64_t n, uvx_stream_t stream);
+int uvx_gelu_bwd(const void* x, const void* dy, void* dx, int64_t n, uvx_stream_t stream);
 int uvx_swiglu_bwd(const void* x, const void* dout, void* dx, int64_t rows, int64_t H, int64_t x_row_stride,
                    int gate_first, uvx_stream_t stream);
 /* dlogits (bf16 [B*S, V]) of uvx_ce_loss: (softmax - onehot) * grad_scale / count on valid rows, 0 elsewhere. */

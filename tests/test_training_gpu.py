@@ -46,6 +46,24 @@ def test_rmsnorm_bwd(rows, cols):
     assert rel(dw, wf.grad) < 1e-3
 
 
+@pytest.mark.parametrize("rows,cols", [(37, 128), (1500, 1280), (5, 384)])
+def test_layernorm_bwd_and_gelu(rows, cols):
+    """uvx_layernorm_bwd (data gradient + residual-branch gradient), uvx_gelu / uvx_gelu_bwd against torch autograd in fp32."""
+    from ultravox_b200 import ops
+    x, w, b, dy, dres = rnd(rows, cols, seed=1), rnd(cols, seed=2), rnd(cols, seed=3), rnd(rows, cols, seed=4), rnd(rows, cols, seed=5)
+    xf = x.float().requires_grad_(True)
+    F.layer_norm(xf, (cols,), w.float(), b.float(), 1e-5).backward(dy.float())
+    dx = ops.layernorm_bwd(dy, x, w, 1e-5, dres=dres)
+    assert rel(dx, (xf.grad + dres.float()).to(BF)) < 2e-3
+    assert rel(ops.layernorm_bwd(dy, x, w, 1e-5), xf.grad.to(BF)) < 2e-3
+    pre = rnd(rows, cols, scale=2.0, seed=6)
+    pf = pre.float().requires_grad_(True)
+    y = F.gelu(pf)
+    y.backward(dy.float())
+    assert rel(ops.gelu(pre), y.detach().to(BF)) < 1e-3
+    assert rel(ops.gelu_bwd(pre, dy), pf.grad.to(BF)) < 2e-3
+
+
 def test_stack_rmsnorm_bwd_weight_grad():
     from ultravox_b200 import ops
     T, C = 50, 128
@@ -171,6 +189,62 @@ def test_adapter_backward_matches_oracle_autograd():
         r = rel(got, sd[n].grad)
         cos = float(F.cosine_similarity(got.float().cpu().flatten(), sd[n].grad.flatten(), dim=0))
         assert r < 8e-2 and cos > 0.995, (n, r, cos)   # bf16 activations end to end vs fp32 autograd
+
+
+def test_encoder_lora_training_matches_oracle_autograd():
+    """LoRA r = 8 on the encoder's q / k projections (ref v0.5_config.yaml:5-6, ultravox_config.py:10-24) trained
+    together with the projector.  The adapter gradients of every layer (through the whole encoder backward: LayerNorm, fc2 / GELU /
+    fc1, out_proj, non-causal attention with key-length masks, q|k|v) against torch.autograd on the fp32 oracle with the same
+    adapters merged as W + s B A; then two optimizer steps must lower the loss and keep the PEFT-named export consistent."""
+    from oracle import model as om
+    from ultravox_b200 import ops
+    from ultravox_b200.autograd import EncoderLora
+    from ultravox_b200.training import AdapterTrainer
+    cfg, model, padded, batch = _setup([16000 * 2, 16000 + 77])
+    mel = ops.logmel(torch.from_numpy(padded).cuda(), cfg.audio_config.num_mel_bins)
+    lora = EncoderLora(model, r=8, alpha=8.0, seed=3)
+    r, d, L = lora.r, lora.d, lora.L
+    g = torch.Generator().manual_seed(9)
+    with torch.no_grad():                                  # B = 0 (PEFT init) gives dA = 0: test with trained-looking adapters
+        lora.Bq[:, :, :r] = (torch.randn(L, d, r, generator=g) * 0.05).to(BF).cuda()
+        lora.Bk[:, :, r:2 * r] = (torch.randn(L, d, r, generator=g) * 0.05).to(BF).cuda()
+    sd0 = om.state_dict_fp32(model)                        # base weights (before any merge)
+    tr = AdapterTrainer(model, lr=1e-3, encoder_lora=lora)
+    loss = tr.forward_backward(audio_values=mel, **batch)
+    # ---- oracle: same adapters as fp32 leaves, merged into q_proj / k_proj exactly as PEFT composes them
+    sh = om.shapes_from_config(cfg)
+    sd = dict(sd0)
+    leaves = []
+    for li in range(L):
+        Aq = lora.A[li, :r].float().cpu().requires_grad_(True)
+        Ak = lora.A[li, r:2 * r].float().cpu().requires_grad_(True)
+        Bq = lora.Bq[li, :, :r].float().cpu().requires_grad_(True)
+        Bk = lora.Bk[li, :, r:2 * r].float().cpu().requires_grad_(True)
+        p = f"audio_tower.layers.{li}.self_attn."
+        sd[p + "q_proj.weight"] = sd0[p + "q_proj.weight"] + lora.scaling * (Bq @ Aq)
+        sd[p + "k_proj.weight"] = sd0[p + "k_proj.weight"] + lora.scaling * (Bk @ Ak)
+        leaves.append((Aq, Ak, Bq, Bk))
+    _, ref_loss = om.forward(sd, sh, batch["input_ids"], mel.cpu().to(BF).float(), batch["audio_token_start_idx"],
+                             batch["audio_lens"], batch["audio_token_len"], batch["audio_batch_size"], labels=batch["labels"])
+    ref_loss.backward()
+    assert abs(float(loss) - float(ref_loss)) < 3e-2 * max(1.0, abs(float(ref_loss)))
+    for li, (Aq, Ak, Bq, Bk) in enumerate(leaves):
+        for name, got, want in (("Aq", lora.gA[li, :r], Aq.grad), ("Ak", lora.gA[li, r:2 * r], Ak.grad),
+                                ("Bq", lora.gBq[li, :, :r], Bq.grad), ("Bk", lora.gBk[li, :, r:2 * r], Bk.grad)):
+            cos = float(F.cosine_similarity(got.float().cpu().flatten(), want.flatten(), dim=0))
+            assert cos > 0.98 and rel(got, want) < 0.2, (li, name, cos, rel(got, want))     # bf16 activations through the whole stack
+        assert float(lora.gA[li, 2 * r:].abs().max()) == 0 and float(lora.gBq[li, :, r:].abs().max()) == 0
+    # ---- the projector gradients see the adapted encoder too
+    names = ["multi_modal_projector.linear_2.weight"]
+    # ---- two steps: loss goes down, adapters move, export carries PEFT's names and shapes
+    a0 = lora.A.detach().clone()
+    l0 = float(tr.train_step(audio_values=mel, **batch))
+    for _ in range(4):
+        l1 = float(tr.train_step(audio_values=mel, **batch))
+    assert l1 < l0 and not torch.equal(a0, lora.A)
+    exp = lora.peft_state_dict()
+    assert exp["audio_tower.base_model.model.layers.0.self_attn.q_proj.lora_A.default.weight"].shape == (r, d)
+    assert exp["audio_tower.base_model.model.layers.0.self_attn.k_proj.lora_B.default.weight"].shape == (d, r)
 
 
 def test_adamw_step_matches_torch():

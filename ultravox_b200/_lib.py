@@ -79,6 +79,9 @@ SIGNATURES = {
     "uvx_transpose_bf16": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "uvx_rmsnorm_bwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_vp]),
     "uvx_swiglu_bwd": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp]),
+    "uvx_layernorm_bwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, C.c_float, c_vp]),
+    "uvx_gelu": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "uvx_gelu_bwd": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "uvx_ce_bwd": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, C.c_int, c_vp, c_vp, c_f32, c_vp, c_vp]),
     "uvx_gather_rows": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "uvx_splice_inverse": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp]),

@@ -50,10 +50,11 @@ def projector_forward(model, enc: torch.Tensor) -> tuple[torch.Tensor, dict]:
     return aud, dict(enc=enc, xs=xs, y1=y1, z=z, zn=zn, aud_pre=aud_pre, N=N, T2=T2, dE=dE, rows_a=rows_a)
 
 
-def projector_backward(model, saved: dict, d_aud: torch.Tensor, grads: dict) -> None:
+def projector_backward(model, saved: dict, d_aud: torch.Tensor, grads: dict, want_d_enc: bool = False) -> Optional[torch.Tensor]:
     """d_aud [N*rows_a, D] bf16 -> fp32 weight gradients WRITTEN into ``grads[name]`` (name in ln_pre / linear_1 / ln_mid |
     ln_post / linear_2; tensors of the parameter's shape, overwritten for the linears, accumulated for the norms - zero them
-    first).  The encoder is frozen, so no gradient flows further back."""
+    first).  With a frozen encoder no gradient flows further back; ``want_d_enc`` (encoder LoRA training) also returns
+    d(loss)/d(encoder output) [N, T2, dE]."""
     pj, cfg = model.multi_modal_projector, model.config
     N, rows_a, T2, dE = saved["N"], saved["rows_a"], saved["T2"], saved["dE"]
     Ma = N * rows_a
@@ -69,7 +70,11 @@ def projector_backward(model, saved: dict, d_aud: torch.Tensor, grads: dict) -> 
     d_y1 = ops.swiglu_bwd(saved["y1"].reshape(Ma, -1), d_z, gate_first=False)
     ops.linear(ops.transpose(d_y1), ops.transpose(xs2), out=grads["linear_1"])        # dW1 = d_y1^T xs
     d_xs = ops.linear(d_y1, ops.transpose(pj.linear_1.weight))
-    ops.rmsnorm_bwd(d_xs, saved["enc"], pj.ln_pre.weight, 1e-6, want_dx=False, dw=grads["ln_pre"], stack=(rows_a, T2 * dE))
+    d_st = ops.rmsnorm_bwd(d_xs, saved["enc"], pj.ln_pre.weight, 1e-6, want_dx=want_d_enc, dw=grads["ln_pre"], stack=(rows_a, T2 * dE))
+    if not want_d_enc:
+        return None
+    # the stacked rows are the encoder frames in order (StackAudioFrames pads the tail of the last row with zeros)
+    return d_st.view(N, rows_a * cfg.stack_factor, dE)[:, :T2].contiguous()
 
 
 def projector_param_names(cfg) -> list[str]:
@@ -290,3 +295,160 @@ def adapter_loss(model, input_ids, enc: torch.Tensor, src_args: tuple, labels, a
     hidden = LlamaStackFn.apply(model, emb, kv_len)
     loss = HeadLossFn.apply(model, hidden, labels, alt_input_ids, alt_labels)
     return loss, hidden.detach()
+
+
+# ------------------------------------------------------------------------------------------------ encoder LoRA
+class EncoderLora(torch.nn.Module):
+    """LoRA adapters on ``q_proj`` / ``k_proj`` of every Whisper encoder layer - what ``audio_model_lora_config: {r: 8}`` of the
+    released recipes turns on (ref:ultravox/training/configs/v0.5_config.yaml:5-6; defaults ref:ultravox/model/ultravox_config.py:10-24:
+    lora_alpha 8, target modules k_proj / q_proj; ``peft.get_peft_model``, ref:ultravox/model/ultravox_model.py:690-709).
+
+    Per layer the adapters live in GEMM-shaped (zero-padded to 64) bf16 buffers so that every product runs on uvx_gemm_bf16:
+    ``A`` [64, d] (rows 0..r-1 = lora_A of q_proj, rows r..2r-1 = lora_A of k_proj), ``Bq`` / ``Bk`` [d, 64] (columns 0..r-1 /
+    r..2r-1 = lora_B).  PEFT initialisation: A ~ kaiming-uniform(a = sqrt 5) = U(-1/sqrt d, 1/sqrt d), B = 0.  Gradients are fp32.
+    ``merge_into(model)`` writes W + (alpha / r) B A into the fused q|k|v weight - the forward (training and inference) then
+    runs the unchanged encoder kernels on the adapted weights, exactly PEFT's ``x W^T + s (x A^T) B^T``."""
+
+    def __init__(self, model, r: int = 8, alpha: float = 8.0, seed: int = 0):
+        super().__init__()
+        at = model.audio_tower
+        d, L = at.d, len(at.layers)
+        if not (1 <= r <= 32):
+            raise ValueError("EncoderLora: 1 <= r <= 32")
+        self.r, self.scaling, self.d, self.L = int(r), float(alpha) / float(r), d, L
+        dev = model.device
+        g = torch.Generator().manual_seed(seed)
+        bound = d ** -0.5
+        A = torch.zeros(L, 64, d)
+        A[:, :2 * r] = (torch.rand(L, 2 * r, d, generator=g) * 2 - 1) * bound
+        self.A = torch.nn.Parameter(A.to(dev, BF16), requires_grad=False)
+        self.Bq = torch.nn.Parameter(torch.zeros(L, d, 64, dtype=BF16, device=dev), requires_grad=False)
+        self.Bk = torch.nn.Parameter(torch.zeros(L, d, 64, dtype=BF16, device=dev), requires_grad=False)
+        # frozen base q / k rows of the fused q|k|v weights (the model's own tensors hold the merged weights)
+        self.base_qk = [layer.self_attn.qkv_w[:2 * d].detach().clone() for layer in at.layers]
+        self.gA = torch.zeros(L, 64, d, dtype=torch.float32, device=dev)
+        self.gBq = torch.zeros(L, d, 64, dtype=torch.float32, device=dev)
+        self.gBk = torch.zeros(L, d, 64, dtype=torch.float32, device=dev)
+
+    def params_and_grads(self):
+        return [(self.A, self.gA), (self.Bq, self.gBq), (self.Bk, self.gBk)]
+
+    def zero_grad(self):
+        for _, g in self.params_and_grads():
+            g.zero_()
+
+    @torch.no_grad()
+    def merge_into(self, model) -> None:
+        """qkv_w[:2d] <- base + s * B A for every layer (two K = 64 GEMMs per layer with the base rows as the residual)."""
+        d = self.d
+        for li, layer in enumerate(model.audio_tower.layers):
+            At = ops.transpose(self.A[li])                                   # [d, 64]
+            w = layer.self_attn.qkv_w
+            ops.linear(self.Bq[li], At, residual=self.base_qk[li][:d], out=w[:d], alpha=self.scaling)
+            ops.linear(self.Bk[li], At, residual=self.base_qk[li][d:], out=w[d:2 * d], alpha=self.scaling)
+
+    def peft_state_dict(self, prefix: str = "audio_tower.base_model.model.") -> dict:
+        """The adapters under PEFT's names (what ``save_pretrained`` of the reference writes for a LoRA-wrapped tower)."""
+        out, r = {}, self.r
+        for li in range(self.L):
+            base = f"{prefix}layers.{li}.self_attn."
+            out[base + "q_proj.lora_A.default.weight"] = self.A[li, :r].detach().clone()
+            out[base + "k_proj.lora_A.default.weight"] = self.A[li, r:2 * r].detach().clone()
+            out[base + "q_proj.lora_B.default.weight"] = self.Bq[li, :, :r].detach().clone()
+            out[base + "k_proj.lora_B.default.weight"] = self.Bk[li, :, r:2 * r].detach().clone()
+        return out
+
+
+def transposed_encoder_weights(model) -> list:
+    """One-time [K, N] copies of the frozen encoder weights that the data-gradient GEMMs read (q|k|v is re-transposed every step:
+    its q / k rows carry the adapters)."""
+    cached = getattr(model, "_enc_wT", None)
+    if cached is None:
+        cached = [dict(o=ops.transpose(layer.self_attn.out_proj.weight), fc1=ops.transpose(layer.fc1.weight),
+                       fc2=ops.transpose(layer.fc2.weight)) for layer in model.audio_tower.layers]
+        model._enc_wT = cached
+    return cached
+
+
+def encoder_forward_train(model, x_tm: torch.Tensor, audio_lens: Optional[torch.Tensor],
+                          kv_len: Optional[torch.Tensor] = None) -> tuple[torch.Tensor, dict]:
+    """``UltravoxModel.encode_audio`` with the per-layer activations kept for ``encoder_backward`` (hf:modeling_whisper.py:403-440):
+    residual stream before each LayerNorm, LN1 output (the adapters' input), q|k|v, attention output + log-sum-exp, fc1
+    pre-activation.  The conv stem runs as in inference (no trainable parameter in front of layer 0)."""
+    at = model.audio_tower
+    N, Tp, _ = x_tm.shape
+    T = Tp - 2
+    if T > at.max_context_length:
+        raise ValueError(f"Whisper expects the mel input features to be of length {at.max_context_length} or less, but found {T}.")
+    d, H = at.d, at.heads
+    hd = d // H
+    T2 = (T + 1) // 2
+    dev = x_tm.device
+    h1 = torch.zeros(N, T + 2, d, dtype=BF16, device=dev)
+    ops.conv1d_k3(x_tm, model._derived["conv1_w"], at.conv1.bias, 1, h1, out_guard=True)
+    h = torch.empty(N, T2, d, dtype=BF16, device=dev)
+    ops.conv1d_k3(h1, model._derived["conv2_w"], at.conv2.bias, 2, h, out_guard=False, pos=at.embed_positions.weight[:T2])
+    if kv_len is None and audio_lens is not None:
+        kv_len = ((audio_lens.to(torch.int64) - 1) // 2 + 1).to(torch.int32).to(dev)
+    block = int(model.config.audio_latency_block_size or 0)
+    if block:
+        raise NotImplementedError("encoder LoRA training with the block-causal streaming mask")
+    rows = N * T2
+    h = h.view(rows, d)
+    layers = []
+    for layer in at.layers:
+        sa = layer.self_attn
+        h_in = h
+        ln1 = ops.layernorm(h_in, layer.self_attn_layer_norm.weight, layer.self_attn_layer_norm.bias, 1e-5)
+        qkv = ops.linear(ln1, sa.qkv_w, sa.qkv_b)
+        att = torch.empty(rows, d, dtype=BF16, device=dev)
+        lse = torch.empty(N, H, T2, dtype=torch.float32, device=dev)
+        ops.attention_fused_qkv_train(qkv, N, T2, H, H, hd, hd ** -0.5, False, att, lse, kv_len)
+        h_mid = ops.linear(att, sa.out_proj.weight, sa.out_proj.bias, residual=h_in)
+        ln2 = ops.layernorm(h_mid, layer.final_layer_norm.weight, layer.final_layer_norm.bias, 1e-5)
+        pre = ops.linear(ln2, layer.fc1.weight, layer.fc1.bias)
+        h = ops.linear(ops.gelu(pre), layer.fc2.weight, layer.fc2.bias, residual=h_mid)
+        layers.append(dict(h_in=h_in, ln1=ln1, qkv=qkv, att=att, lse=lse, h_mid=h_mid, pre=pre))
+    out = ops.layernorm(h, at.layer_norm.weight, at.layer_norm.bias, 1e-5)
+    return out.view(N, T2, d), dict(layers=layers, h_last=h, N=N, T2=T2, kv_len=kv_len)
+
+
+def encoder_backward(model, saved: dict, d_enc: torch.Tensor, lora: EncoderLora) -> None:
+    """d(loss)/d(encoder output) [N, T2, d] -> fp32 adapter gradients ACCUMULATED into ``lora.gA / gBq / gBk``.  Data gradients run
+    back through every layer (final LayerNorm, fc2 / GELU / fc1, LayerNorm, out_proj, attention, q|k|v, LayerNorm, residuals)
+    against pre-transposed weights; the base weights get no gradient (frozen, ref ``apply_lora``).  Per layer and projection:
+    dB = s dq^T (ln1 A^T), dA = s (dq B)^T ln1 - low-rank first, so no [d, d] weight gradient is ever formed."""
+    at = model.audio_tower
+    d, H = at.d, at.heads
+    hd = d // H
+    N, T2 = saved["N"], saved["T2"]
+    rows = N * T2
+    r, s = lora.r, lora.scaling
+    wT = transposed_encoder_weights(model)
+    dh = ops.layernorm_bwd(d_enc.reshape(rows, d).contiguous(), saved["h_last"], at.layer_norm.weight, 1e-5)
+    for li in range(len(at.layers) - 1, -1, -1):
+        layer, sv = at.layers[li], saved["layers"][li]
+        dg = ops.linear(dh, wT[li]["fc2"])                                                 # [rows, ffn]
+        dpre = ops.gelu_bwd(sv["pre"], dg)
+        dln2 = ops.linear(dpre, wT[li]["fc1"])
+        dh_mid = ops.layernorm_bwd(dln2, sv["h_mid"], layer.final_layer_norm.weight, 1e-5, dres=dh)
+        datt = ops.linear(dh_mid, wT[li]["o"])
+        dqkv = ops.attention_fused_qkv_bwd(sv["qkv"], sv["att"], datt, sv["lse"], N, T2, H, H, hd, hd ** -0.5, False, kv_len=saved["kv_len"])
+        # ---- adapter gradients (zero-padded rank dimension of 64: every product is a uvx_gemm_bf16 call)
+        dq, dk = dqkv[:, :d], dqkv[:, d:2 * d]
+        u = ops.linear(sv["ln1"], lora.A[li])                                              # [rows, 64]: (ln1 Aq^T | ln1 Ak^T | 0)
+        uT = ops.transpose(u)                                                              # [64, rows']
+        gq = torch.empty(d, 64, dtype=torch.float32, device=dh.device)
+        gk = torch.empty(d, 64, dtype=torch.float32, device=dh.device)
+        ops.linear(ops.transpose(dq), uT, out=gq)                                          # dq^T u
+        ops.linear(ops.transpose(dk), uT, out=gk)
+        lora.gBq[li, :, :r].add_(gq[:, :r], alpha=s)
+        lora.gBk[li, :, r:2 * r].add_(gk[:, r:2 * r], alpha=s)
+        t = ops.linear(dq, ops.transpose(lora.Bq[li]))                                     # [rows, 64]: dq Bq in columns 0..r-1
+        t = ops.linear(dk, ops.transpose(lora.Bk[li]), residual=t)                         # + dk Bk in columns r..2r-1
+        ga = torch.empty(64, d, dtype=torch.float32, device=dh.device)
+        ops.linear(ops.transpose(t), ops.transpose(sv["ln1"]), out=ga)                     # t^T ln1
+        lora.gA[li, :2 * r].add_(ga[:2 * r], alpha=s)
+        # ---- back through the (adapted) q|k|v projection and the first LayerNorm
+        dln1 = ops.linear(dqkv, ops.transpose(layer.self_attn.qkv_w))
+        dh = ops.layernorm_bwd(dln1, sv["h_in"], layer.self_attn_layer_norm.weight, 1e-5, dres=dh_mid)

@@ -153,6 +153,108 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ x, const bf16* __rest
   }
 }
 
+
+// ------------------------------------------------------------------------------------- LayerNorm backward (data gradient)
+// y = (x - mean) * rstd * w + b  ->  dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * w  (+ dres: the gradient that
+// bypasses the norm on the residual branch).  One warp per row, values in registers (cols <= 2048: the Whisper encoder's d_model).
+// Used by the encoder backward of LoRA training (ref:ultravox_model.py:690-709; hf:modeling_whisper.py:403-440); the norm's own
+// weight / bias are frozen there, so no dw / db.
+static constexpr int kLnbVec = 8;
+__global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                            const bf16* __restrict__ w, const bf16* __restrict__ dres,
+                                                            bf16* __restrict__ dx, int64_t rows, int64_t cols, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = (int)(cols / 8);
+  float xv[kLnbVec][8], gv[kLnbVec][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnbVec; ++i) {
+    const int j = lane + i * 32;
+    if (j < nvec) {
+      unpack8(*reinterpret_cast<const bf16x8*>(x + row * cols + (int64_t)j * 8), xv[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += xv[i][e];
+    }
+  }
+  const float mean = warp_sum(s) / (float)cols;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnbVec; ++i) {
+    const int j = lane + i * 32;
+    if (j < nvec) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        xv[i][e] -= mean;
+        sq += xv[i][e] * xv[i][e];
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)cols + eps);
+  float sg = 0.f, sgx = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnbVec; ++i) {
+    const int j = lane + i * 32;
+    if (j < nvec) {
+      float dyv[8], wv[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(dy + row * cols + (int64_t)j * 8), dyv);
+      unpack8(*reinterpret_cast<const bf16x8*>(w + (int64_t)j * 8), wv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        xv[i][e] *= rstd;                 // xhat
+        gv[i][e] = dyv[e] * wv[e];
+        sg += gv[i][e];
+        sgx += gv[i][e] * xv[i][e];
+      }
+    }
+  }
+  const float mg = warp_sum(sg) / (float)cols, mgx = warp_sum(sgx) / (float)cols;
+#pragma unroll
+  for (int i = 0; i < kLnbVec; ++i) {
+    const int j = lane + i * 32;
+    if (j < nvec) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = rstd * (gv[i][e] - mg - xv[i][e] * mgx);
+      if (dres) {
+        float rv[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(dres + row * cols + (int64_t)j * 8), rv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] += rv[e];
+      }
+      *reinterpret_cast<bf16x8*>(dx + row * cols + (int64_t)j * 8) = pack8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------- GELU (erf form) forward / backward
+// Training keeps the pre-activation of fc1 (the inference path fuses GELU into the GEMM epilogue and never stores it).
+__global__ void gelu_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int64_t nvec) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[8];
+    unpack8(reinterpret_cast<const bf16x8*>(x)[i], v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
+    reinterpret_cast<bf16x8*>(y)[i] = pack8(v);
+  }
+}
+// d/dx [x * Phi(x)] = Phi(x) + x * phi(x)
+__global__ void gelu_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, bf16* __restrict__ dx, int64_t nvec) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[8], d[8];
+    unpack8(reinterpret_cast<const bf16x8*>(x)[i], v);
+    unpack8(reinterpret_cast<const bf16x8*>(dy)[i], d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float cdf = 0.5f * (1.0f + erff(v[e] * 0.70710678118654752440f));
+      const float pdf = 0.3989422804014327f * expf(-0.5f * v[e] * v[e]);
+      d[e] *= cdf + v[e] * pdf;
+    }
+    reinterpret_cast<bf16x8*>(dx)[i] = pack8(d);
+  }
+}
+
 // ------------------------------------------------------------------------------------- CE backward
 // dlogits[r, v] = (softmax(logits[r])[v] - [v == label_r]) / count for rows with a valid (shifted) label, else 0.
 __global__ void __launch_bounds__(512) ce_bwd_kernel(const float* __restrict__ logits, int64_t row_stride,
@@ -270,6 +372,34 @@ extern "C" int uvx_swiglu_bwd(const void* x, const void* dout, void* dx, int64_t
   swiglu_bwd_kernel<<<grid_for(rows * (H / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)dout, (bf16*)dx,
                                                                                      rows, H, x_row_stride, gate_first);
   return check_launch("swiglu_bwd_kernel");
+}
+
+
+extern "C" int uvx_layernorm_bwd(const void* dy, const void* x, const void* w, const void* dres, void* dx, int64_t rows, int64_t cols,
+                                 float eps, uvx_stream_t stream) {
+  using namespace uvx;
+  UVX_REQUIRE(dy && x && w && dx, "uvx_layernorm_bwd: null pointer");
+  UVX_REQUIRE(cols % 8 == 0 && cols <= 32 * kLnbVec * 8, "uvx_layernorm_bwd: cols must be a multiple of 8 and <= %d", 32 * kLnbVec * 8);
+  if (rows == 0) return UVX_OK;
+  layernorm_bwd_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w,
+                                                                                     (const bf16*)dres, (bf16*)dx, rows, cols, eps);
+  return check_launch("layernorm_bwd_kernel");
+}
+
+extern "C" int uvx_gelu(const void* x, void* y, int64_t n, uvx_stream_t stream) {
+  using namespace uvx;
+  UVX_REQUIRE(x && y && n % 8 == 0, "uvx_gelu: n %% 8 == 0 required");
+  if (n == 0) return UVX_OK;
+  gelu_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, n / 8);
+  return check_launch("gelu_kernel");
+}
+
+extern "C" int uvx_gelu_bwd(const void* x, const void* dy, void* dx, int64_t n, uvx_stream_t stream) {
+  using namespace uvx;
+  UVX_REQUIRE(x && dy && dx && n % 8 == 0, "uvx_gelu_bwd: n %% 8 == 0 required");
+  if (n == 0) return UVX_OK;
+  gelu_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, n / 8);
+  return check_launch("gelu_bwd_kernel");
 }
 
 extern "C" int uvx_ce_bwd(const float* logits, int64_t row_stride, const int64_t* labels, int64_t B, int64_t S, int64_t V,

@@ -429,6 +429,39 @@ def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, eps: float, 
     return out if want_dx else None
 
 
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, eps: float = 1e-5, dres: Optional[torch.Tensor] = None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Data gradient of ``layernorm`` (+ ``dres``, the gradient arriving on the residual branch): rows x cols bf16."""
+    _cuda(dy, BF16, "dy"), _cuda(x, BF16, "x")
+    cols = x.shape[-1]
+    x2, dy2 = x.reshape(-1, cols), dy.reshape(-1, cols)
+    assert x2.is_contiguous() and dy2.is_contiguous() and (dres is None or dres.is_contiguous())
+    if out is None:
+        out = torch.empty_like(x2)
+    check(lib().uvx_layernorm_bwd(dy2.data_ptr(), x2.data_ptr(), w.data_ptr(), _p(dres), out.data_ptr(), x2.shape[0], cols, float(eps),
+                                  _stream()), "uvx_layernorm_bwd")
+    return out.view(x.shape)
+
+
+def gelu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(x, BF16, "x")
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib().uvx_gelu(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "uvx_gelu")
+    return out
+
+
+def gelu_bwd(x: torch.Tensor, dy: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx = dy * gelu'(x) for the pre-activation ``x`` (erf form)."""
+    _cuda(x, BF16, "x"), _cuda(dy, BF16, "dy")
+    assert x.is_contiguous() and dy.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib().uvx_gelu_bwd(x.data_ptr(), dy.data_ptr(), out.data_ptr(), x.numel(), _stream()), "uvx_gelu_bwd")
+    return out
+
+
 def swiglu_bwd(x: torch.Tensor, dout: torch.Tensor, gate_first: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     H = x.shape[-1] // 2
     x2 = x.reshape(-1, 2 * H)

@@ -25,8 +25,12 @@ from .model import BF16, UltravoxModel
 
 class AdapterTrainer:
     def __init__(self, model: UltravoxModel, lr: float = 2e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 0.0, process_group=None):
+                 weight_decay: float = 0.0, process_group=None, encoder_lora=None):
+        """``encoder_lora`` (``autograd.EncoderLora``): also train LoRA adapters on the encoder's q / k projections - the
+        ``audio_model_lora_config: {r: 8}`` of the released recipes (ref:ultravox/training/configs/v0.5_config.yaml:5-6); the
+        encoder then runs its training forward (activations kept) and a full data-gradient backward."""
         self.model = model
+        self.lora = encoder_lora
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.pg = process_group
         pj = model.multi_modal_projector
@@ -35,6 +39,11 @@ class AdapterTrainer:
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)     # flat fp32 gradient (all-reduced)
         self.m = torch.zeros(n, dtype=torch.float32, device=dev)
         self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.lora_state = []
+        if encoder_lora is not None:
+            for prm, _ in encoder_lora.params_and_grads():
+                self.lora_state.append((torch.zeros(prm.numel(), dtype=torch.float32, device=dev),
+                                        torch.zeros(prm.numel(), dtype=torch.float32, device=dev)))
         self.step_count = 0
         self.last = {}
         self._comm_stream: Optional[torch.cuda.Stream] = None
@@ -69,7 +78,12 @@ class AdapterTrainer:
                 audio_tm = m.mel_chunks_from_waveforms(audio_waveforms, audio_num_frames, audio_pad_frames=audio_pad_frames)
             if audio_tm is None:
                 audio_tm = ops.mel_to_timemajor(audio_values.to(dev, torch.float32))
-            enc = m.encode_audio(audio_tm, audio_lens).clone()                 # [N, T2, d]
+            sv_e = None
+            if self.lora is not None:
+                self.lora.merge_into(m)                                            # q|k|v weights <- base + s B A (this step's adapters)
+                enc, sv_e = ag.encoder_forward_train(m, audio_tm, audio_lens)
+            else:
+                enc = m.encode_audio(audio_tm, audio_lens).clone()                 # [N, T2, d]
             aud, sv_p = ag.projector_forward(m, enc)
             src = ops.splice_plan(audio_token_start_idx.to(dev, torch.int64).contiguous(),
                                   audio_token_len.to(dev, torch.int32).contiguous(),
@@ -83,7 +97,10 @@ class AdapterTrainer:
             dh = ag.llama_stack_backward(m, sv_l, ag.head_loss_backward(m, keep))
             d_aud = ops.gather_rows(dh, ops.splice_inverse(src, sv_p["N"] * sv_p["rows_a"]))
             names = ag.projector_param_names(cfg)
-            ag.projector_backward(m, sv_p, d_aud, {n: self.grad_view(n) for n in names})
+            d_enc = ag.projector_backward(m, sv_p, d_aud, {n: self.grad_view(n) for n in names}, want_d_enc=sv_e is not None)
+            if sv_e is not None:
+                self.lora.zero_grad()
+                ag.encoder_backward(m, sv_e, d_enc, self.lora)
         self.last = dict(loss=loss, rows=keep["n_rows"])
         return loss
 
@@ -93,12 +110,18 @@ class AdapterTrainer:
         NVSwitch when launched with one process per GPU).  Returns the scale (1 / world) the optimizer kernel applies - the
         mean is folded into ``uvx_adamw(grad_scale)`` instead of a separate pass over the 201 MB buffer."""
         from .dist_utils import allreduce_sum_
+        if self.lora is not None:
+            for _, g in self.lora.params_and_grads():
+                allreduce_sum_(g, self.pg)
         return allreduce_sum_(self.grad, self.pg)
 
     def optimizer_step(self, grad_scale: float = 1.0):
         self.step_count += 1
         ops.adamw_(self.model.multi_modal_projector.flat, self.grad, self.m, self.v, self.step_count, self.lr, self.betas,
                    self.eps, self.wd, grad_scale)
+        if self.lora is not None:
+            for (prm, g), (m1, v1) in zip(self.lora.params_and_grads(), self.lora_state):
+                ops.adamw_(prm.data.view(-1), g.view(-1), m1, v1, self.step_count, self.lr, self.betas, self.eps, self.wd, grad_scale)
 
     def train_step(self, **batch) -> torch.Tensor:
         loss = self.forward_backward(**batch)
