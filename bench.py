@@ -436,10 +436,39 @@ def train_record(model, cfg, args, rank, world, dev):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     loss1 = float(loss)
     model.multi_modal_projector.flat.copy_(flat0)          # leave the weights as the other passes expect them
+    # the released recipes' variant (audio_model_lora_config r = 8): the same step with LoRA adapters on the encoder's
+    # q / k projections trained too - encoder training forward (activations kept) + full encoder backward
+    lora_ms = None
+    if not getattr(args, "no_train_lora", False):
+        try:
+            from ultravox_b200.autograd import EncoderLora
+            lora = EncoderLora(model, r=8, alpha=8.0, seed=1)
+            tr2 = AdapterTrainer(model, lr=2e-3, encoder_lora=lora)
+            tr_saved, tr = tr, tr2
+            step()
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(2):
+                step()
+            f1.record()
+            torch.cuda.synchronize()
+            tl = torch.tensor([f0.elapsed_time(f1) / 2], device=dev)
+            if world > 1:
+                dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+            lora_ms = float(tl[0])
+            tr = tr_saved
+            lora.unmerge(model)
+            model.multi_modal_projector.flat.copy_(flat0)
+            del lora, tr2
+            torch.cuda.empty_cache()
+        except Exception as e:
+            lora_ms = "error: " + repr(e)[:200]
     ms, ar = float(t[0]), float(t[1])
     return {"config": "cfg3: adapter-only training (encoder + LLM frozen), bf16, data-parallel, one gradient all-reduce per step",
             "per_gpu_batch": B, "global_batch": B * world, "clip_seconds": secs, "steps": 3, "warmup": 1, "ms_per_step": ms,
             "clips_per_s": B * world / (ms * 1e-3), "audio_sec_per_s": B * world * secs / (ms * 1e-3),
+            "with_encoder_lora_r8_ms_per_step": lora_ms,
             "allreduce_ms": ar if world > 1 else 0.0, "allreduce_bytes": tr.grad.numel() * 4 if world > 1 else 0,
             "allreduce": "NCCL sum all-reduce of the flat fp32 projector gradient; 1/world folded into the AdamW kernel" if world > 1 else "none (1 GPU)",
             "loss_first": loss0, "loss_last": loss1, "timer": "CUDA events, max over ranks"}

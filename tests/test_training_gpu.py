@@ -247,6 +247,30 @@ def test_encoder_lora_training_matches_oracle_autograd():
     assert exp["audio_tower.base_model.model.layers.0.self_attn.k_proj.lora_B.default.weight"].shape == (d, r)
 
 
+def test_encoder_lora_through_autograd_door():
+    """``model.attach_encoder_lora()`` + ``model(**batch).loss.backward()`` (the HF Trainer door, ref train.py:250-330 with
+    ``audio_model_lora_config: {r: 8}``): the adapters' ``.grad`` equals what ``AdapterTrainer`` accumulates for the same batch."""
+    from ultravox_b200 import ops
+    from ultravox_b200.training import AdapterTrainer
+    cfg, model, padded, batch = _setup([16000 * 2, 16000 + 77])
+    mel = ops.logmel(torch.from_numpy(padded).cuda(), cfg.audio_config.num_mel_bins)
+    lora = model.attach_encoder_lora(r=8, alpha=8.0, seed=3)
+    with torch.no_grad():
+        lora.Bq[:, :, :8] = (torch.randn(lora.L, lora.d, 8, generator=torch.Generator().manual_seed(9)) * 0.05).to(BF).cuda()
+    for p in model.multi_modal_projector.parameters():
+        p.requires_grad_(True)
+    model.train()
+    out = model(audio_values=mel, **batch)
+    out.loss.backward()
+    assert lora.A.grad is not None and lora.Bq.grad is not None and float(lora.A.grad.float().abs().max()) > 0
+    gA, gBq = lora.A.grad.float().clone(), lora.Bq.grad.float().clone()
+    tr = AdapterTrainer(model, lr=1e-3, encoder_lora=lora)
+    loss = tr.forward_backward(audio_values=mel, **batch)
+    assert abs(float(loss) - float(out.loss)) < 1e-3 * max(1.0, abs(float(loss)))
+    assert rel(gA, lora.gA) < 1e-2 and rel(gBq, lora.gBq) < 1e-2          # same kernels; .grad is rounded to the bf16 parameter dtype
+    assert model.multi_modal_projector.linear_2.weight.grad is not None
+
+
 def test_adamw_step_matches_torch():
     from ultravox_b200 import ops
     n = 10007

@@ -215,10 +215,11 @@ class ProjectorFn(torch.autograd.Function):
         names = projector_param_names(model.config)
         pj = model.multi_modal_projector
         grads = {n: torch.zeros(getattr(pj, n).weight.shape, dtype=torch.float32, device=d_aud.device) for n in names}
-        projector_backward(model, saved, d_aud.reshape(saved["N"] * saved["rows_a"], -1).contiguous(), grads)
+        d_enc = projector_backward(model, saved, d_aud.reshape(saved["N"] * saved["rows_a"], -1).contiguous(), grads,
+                                   want_d_enc=ctx.needs_input_grad[1])      # (encoder LoRA training: the encoder output has a grad_fn)
         ctx.saved = None
         # parameters are bf16: autograd wants gradients in the parameter's dtype (the fp32 accumulation happened in the kernels)
-        return (None, None) + tuple(grads[n].to(getattr(pj, n).weight.dtype) for n in names)
+        return (None, d_enc) + tuple(grads[n].to(getattr(pj, n).weight.dtype) for n in names)
 
 
 class SpliceFn(torch.autograd.Function):
@@ -347,6 +348,12 @@ class EncoderLora(torch.nn.Module):
             ops.linear(self.Bq[li], At, residual=self.base_qk[li][:d], out=w[:d], alpha=self.scaling)
             ops.linear(self.Bk[li], At, residual=self.base_qk[li][d:], out=w[d:2 * d], alpha=self.scaling)
 
+    @torch.no_grad()
+    def unmerge(self, model) -> None:
+        """Puts the frozen base q / k rows back (drops the adapters from the model's weights)."""
+        for li, layer in enumerate(model.audio_tower.layers):
+            layer.self_attn.qkv_w[:2 * self.d].copy_(self.base_qk[li])
+
     def peft_state_dict(self, prefix: str = "audio_tower.base_model.model.") -> dict:
         """The adapters under PEFT's names (what ``save_pretrained`` of the reference writes for a LoRA-wrapped tower)."""
         out, r = {}, self.r
@@ -452,3 +459,25 @@ def encoder_backward(model, saved: dict, d_enc: torch.Tensor, lora: EncoderLora)
         # ---- back through the (adapted) q|k|v projection and the first LayerNorm
         dln1 = ops.linear(dqkv, ops.transpose(layer.self_attn.qkv_w))
         dh = ops.layernorm_bwd(dln1, sv["h_in"], layer.self_attn_layer_norm.weight, 1e-5, dres=dh_mid)
+
+
+class EncoderLoraFn(torch.autograd.Function):
+    """enc = WhisperEncoder(mel) with LoRA adapters on q / k: the adapters are autograd inputs, so ``loss.backward()`` fills their
+    ``.grad`` (zero-padded rank dimension: only the first r / 2r rows / columns are ever non-zero)."""
+
+    @staticmethod
+    def forward(ctx, model, x_tm, audio_lens, A, Bq, Bk):
+        lora = model.encoder_lora
+        lora.merge_into(model)
+        enc, saved = encoder_forward_train(model, x_tm, audio_lens)
+        ctx.model, ctx.saved = model, saved
+        return enc.clone()
+
+    @staticmethod
+    def backward(ctx, d_enc):
+        model, lora = ctx.model, ctx.model.encoder_lora
+        lora.zero_grad()
+        d = d_enc if d_enc.dtype == BF16 else d_enc.to(BF16)
+        encoder_backward(model, ctx.saved, d.contiguous(), lora)
+        ctx.saved = None
+        return None, None, None, lora.gA.to(lora.A.dtype), lora.gBq.to(lora.Bq.dtype), lora.gBk.to(lora.Bk.dtype)

@@ -737,6 +737,16 @@ class UltravoxModel(nn.Module):
         kv_len = end.to(torch.int32) if bool((end < S).any()) else None
         return kv_start, kv_len
 
+    def attach_encoder_lora(self, r: int = 8, alpha: float = 8.0, seed: int = 0):
+        """``apply_lora(audio_tower, audio_model_lora_config)`` (ref :496, :690-709) for the released recipes' ``r: 8`` on q_proj /
+        k_proj: registers ``autograd.EncoderLora`` as ``self.encoder_lora`` with trainable parameters; ``forward`` with gradients
+        enabled then routes the encoder through ``EncoderLoraFn`` so ``loss.backward()`` fills their ``.grad``."""
+        from .autograd import EncoderLora
+        self.encoder_lora = EncoderLora(self, r=r, alpha=alpha, seed=seed)
+        for p in self.encoder_lora.parameters():
+            p.requires_grad_(True)
+        return self.encoder_lora
+
     # -- forward / generate --------------------------------------------------------------------------
     def forward(self, input_ids: torch.Tensor, audio_values: Optional[torch.Tensor] = None,
                 inputs_embeds: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
@@ -762,7 +772,13 @@ class UltravoxModel(nn.Module):
                     tm = self.mel_chunks_from_waveforms(audio_waveforms, audio_num_frames, audio_pad_frames=audio_pad_frames)
                 else:
                     tm = ops.mel_to_timemajor(audio_values.to(dev, torch.float32))
-                inputs_embeds = self.encode_audio(tm, audio_lens).clone()       # encoder output; the towers are frozen
+                lora = getattr(self, "encoder_lora", None)
+                if lora is None or not lora.A.requires_grad:
+                    inputs_embeds = self.encode_audio(tm, audio_lens).clone()   # encoder output; the towers are frozen
+            if lora is not None and lora.A.requires_grad:
+                # encoder LoRA training through the autograd door: the adapters are autograd inputs of the encoder node
+                from .autograd import EncoderLoraFn
+                inputs_embeds = EncoderLoraFn.apply(self, tm, audio_lens, lora.A, lora.Bq, lora.Bk)
         elif inputs_embeds is None:
             if audio_waveforms is not None and len(audio_waveforms) > 0:
                 tm = self.mel_chunks_from_waveforms(audio_waveforms, audio_num_frames, audio_pad_frames=audio_pad_frames)
