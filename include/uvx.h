@@ -78,8 +78,8 @@ int uvx_mel_to_timemajor(const float* mel, int64_t N, int n_mels, int64_t T, voi
  * positional embedding added after GELU (ref :896-899, r_batch_stride = 0).
  * Requirements: K % 8 == 0, N % 64 == 0, strides % 8 == 0, 16-byte aligned bases.
  * Split-K partial sums are reduced in a fixed order by a second kernel: results are deterministic.
- * Opt-in (UVX_GEMM_WS=1 or uvx_debug_gemm_ws): calls with a_batch == 1, a_rows <= 256, a plain bf16 output and a workspace (the LLM
- * prefill at B = 1, decode batches, the projector) run the WEIGHT-STREAMING form (csrc/gemm_ws.cu): 128 weight rows on the UMMA M dimension, the tokens on the UMMA N
+ * Calls with a_batch == 1, a_rows <= 32 (decode batches; UVX_GEMM_WS=1 / uvx_debug_gemm_ws: every call with a_rows <= 256, e.g. the LLM
+ * prefill at B = 1; UVX_GEMM_WS=0: never), a plain bf16 output and a workspace run the WEIGHT-STREAMING form (csrc/gemm_ws.cu): 128 weight rows on the UMMA M dimension, the tokens on the UMMA N
  * dimension (round16(rows) instead of 256 padded rows), stream-K over (feature tile, k-block) units with the partial accumulators
  * of split tiles summed in CTA order by the tile's owner (deterministic for a given device).  Workspace contract for that form:
  * at least 148*128*round16(rows)*4 + 1024 bytes, and the LAST 1024 bytes (slot flags) are the library's: it zeroes them the first
@@ -142,7 +142,7 @@ int uvx_debug_gemm_times(void* dev_buf);
 int uvx_debug_gemm_stages(int n);
 /* tuning hook: L2 prefetch distance of the weight stream in k-blocks (0 = off; < 0 = default) */
 int uvx_debug_gemm_pf(int pf);
-/* tuning hook of the weight-streaming form: enable (1 / 0; -1 = UVX_GEMM_WS env, default off), isolation mode (0 = off, 1 = loads
+/* tuning hook of the weight-streaming form: enable (0 = never, 1 = rows <= 256, 2 = rows <= 32; -1 = UVX_GEMM_WS env, default 2), isolation mode (0 = off, 1 = loads
  * only, 2 = MMAs only, 3 = no epilogue; + 8 / 16 / 32 / 64 skip slot stores / slot reads / flag traffic / output stores), forced grid size (0 = one CTA per SM) */
 int uvx_debug_gemm_ws(int enable, int mode, int grid);
 /* tuning hook: device buffer [grid][16] int64 of per-CTA phase timestamps of the weight-streaming form (NULL = off) */

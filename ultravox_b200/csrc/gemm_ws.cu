@@ -549,9 +549,11 @@ static int ws_encode_2d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t
   return UVX_OK;
 }
 
-static int g_ws_enable = -1;   // -1: UVX_GEMM_WS env or 0 (opt-in: measured at parity with gemm_tc_kernel on gate|up and behind it on
-                               // the 32-48-tile projections, profiles/r2_ws2_*.txt - both forms sit at the shared-memory bandwidth of
-                               // the SM, TMA writes + UMMA operand reads = 126 B/clk at the HBM rate)
+static int g_ws_enable = -1;   // -1: UVX_GEMM_WS env or 2.  0 = never, 1 = every eligible call (rows <= 256), 2 = auto: rows <= 32 only.
+                               // Measured (profiles/r2_ws2_stream_k.md, r2_decode_sweep_v2.txt): at 2-8 decode streams (16-token UMMA N,
+                               // tiny accumulators) this form is 5-10 % faster per step than gemm_tc_kernel + split-K reduce and needs
+                               // 64 launches fewer; at the 201-token prefill it is at parity on gate|up and behind on the 32-48-tile
+                               // projections (exposed fix-up + epilogue passes), so those stay on gemm_tc_kernel unless UVX_GEMM_WS=1.
 static int g_ws_dbg = 0;
 static int g_ws_grid = 0;      // tuning: force the grid (0 = #SMs)
 static long long* g_ws_times = nullptr;
@@ -559,7 +561,7 @@ static long long* g_ws_times = nullptr;
 int gemm_ws_enabled() {
   if (g_ws_enable < 0) {
     const char* e = getenv("UVX_GEMM_WS");
-    g_ws_enable = e ? atoi(e) : 0;
+    g_ws_enable = e ? atoi(e) : 2;
   }
   return g_ws_enable;
 }
@@ -585,7 +587,9 @@ static int ws_flags_ready(void* flags, cudaStream_t stream) {
 
 // which calls take this form (everything else stays on gemm_tc_kernel)
 bool gemm_ws_eligible(const uvx_gemm_args* a) {
-  if (!gemm_ws_enabled() || (a->flags & 2)) return false;
+  const int mode = gemm_ws_enabled();
+  if (!mode || (a->flags & 2)) return false;
+  if (mode == 2 && a->a_rows > 32) return false;
   if (a->a_batch != 1 || a->a_rows > 256 || a->out_dtype != UVX_DT_BF16 || a->c_row_map || a->c_row_offset != 0) return false;
   if (a->K % 8 != 0 || a->K < 64 || a->N < 128) return false;
   if (a->w_tiled && (a->w_tiled != 128 || a->K % kBK != 0)) return false;

@@ -12,8 +12,12 @@ from typing import Optional
 
 import torch
 
+import os
+
 from . import _lib, ops
 from .model import UltravoxModel
+
+GEMV_MAX_B = int(os.environ.get("UVX_GEMV_MAX_B", "1"))     # decode streams up to which the linears run as matrix-vector kernels
 
 
 class PrefillEngine:
@@ -184,12 +188,15 @@ class DecodeEngine:
         lm, tc = m.language_model, m.config.text_config
         nq, nkv, hd, Dm = tc.num_attention_heads, tc.num_key_value_heads, lm.head_dim, tc.hidden_size
         B = self.B
+        # one or two streams: matrix-vector kernels (fp32 FMAs on the CUDA cores keep up with the weight stream); more streams: the
+        # tcgen05 GEMM (at B = 8 the FMA work per weight byte is 8x and the GEMV is instruction-bound: 19.6 vs ~5 ms per step on 8B)
+        gemv = ops.gemv if B <= GEMV_MAX_B else (lambda x, w, residual=None: ops.linear(x, w, residual=residual))
         h = ops.embed_splice(self.token, lm.model.embed_tokens.weight, None, None).view(B, Dm)
         smax = self.cache.k.shape[2]
         for li, layer in enumerate(lm.model.layers):
             sa, mlp = layer.self_attn, layer.mlp
             x = ops.rmsnorm(h, layer.input_layernorm.weight, tc.rms_norm_eps)
-            qkv = ops.gemv(x, sa.qkv_w)
+            qkv = gemv(x, sa.qkv_w)
             ops.rope_(qkv, nq, nkv, hd, self.cos, self.sin, rows_per_seq=1, positions=self.rope_pos)
             kc, vc = self.cache.k[li], self.cache.v[li]
             ops.kv_append(qkv, kc, vc, self.pos, nq, nkv, hd)
@@ -198,10 +205,10 @@ class DecodeEngine:
             ops.attention(qkv.data_ptr(), kc.data_ptr(), vc.data_ptr(), att, B, nq, nkv, 1, smax, hd,
                           (rs, rs, nkv * hd, smax * nkv * hd, nkv * hd, smax * nkv * hd, nq * hd, nq * hd), hd ** -0.5, False,
                           self.lens, 0, self.kv_start)
-            h = ops.gemv(att, sa.o_proj.weight, residual=h)
+            h = gemv(att, sa.o_proj.weight, residual=h)
             x = ops.rmsnorm(h, layer.post_attention_layernorm.weight, tc.rms_norm_eps)
-            act = ops.swiglu(ops.gemv(x, mlp.gate_up_w), gate_first=True)
-            h = ops.gemv(act, mlp.down_proj.weight, residual=h)
+            act = ops.swiglu(gemv(x, mlp.gate_up_w), gate_first=True)
+            h = gemv(act, mlp.down_proj.weight, residual=h)
         hn = ops.rmsnorm(h, lm.model.norm.weight, tc.rms_norm_eps)
         self._pick(ops.lm_head(hn, lm.lm_head.weight))
 
