@@ -246,6 +246,16 @@ int uvx_gemv_bf16(const void* x, int64_t B, int64_t x_row_stride, const void* W,
  * the decode step is capturable in a CUDA graph); cache layout [B, S_max, kv_width]                                    */
 int uvx_kv_append(const void* qkv, int64_t row_stride, int64_t k_col, int64_t v_col, int64_t kv_width, void* k_cache,
                   void* v_cache, int64_t cache_batch_stride, const int32_t* positions, int64_t B, uvx_stream_t stream);
+/* Decode-step fusions (one CUDA graph per step, ultravox_b200/engine.py): uvx_gemv_bf16 with a fused prologue on the B activation rows -
+ * norm_w != NULL: LlamaRMSNorm (bit-identical to uvx_rmsnorm followed by uvx_gemv_bf16), swiglu = 1: the row is [gate | up] of width
+ * 2K and the kernel consumes act_fn(gate) * up (bit-identical to uvx_swiglu(gate_first = 1) + uvx_gemv_bf16) - and RoPE on q / k +
+ * KV-cache append in one launch (same bits as uvx_rope + uvx_kv_append).                                                       */
+int uvx_gemv_fused_bf16(const void* x, int64_t B, int64_t x_row_stride, const void* W, int64_t w_row_stride, int64_t N, int64_t K,
+                        const void* R, int64_t r_row_stride, void* out, int64_t o_row_stride, int out_f32, const void* norm_w,
+                        float norm_eps, int swiglu, uvx_stream_t stream);
+int uvx_rope_kv_append(void* qkv, int64_t B, int64_t row_stride, int Hq, int Hkv, int D, const float* cos_tab, const float* sin_tab,
+                       const int32_t* rope_positions, void* k_cache, void* v_cache, int64_t cache_batch_stride,
+                       const int32_t* positions, uvx_stream_t stream);
 /* a[i] += delta (and b[i] += delta when b != NULL): advances the device-side positions / lengths after each step     */
 int uvx_add_i32(int32_t* a, int32_t* b, int64_t n, int32_t delta, uvx_stream_t stream);
 /* prefill counterpart of uvx_kv_append: rows b*S + s of the fused projection -> cache[b, past + s] (k and v sections),

@@ -493,6 +493,32 @@ def test_kv_write_and_token_finish(ops):
 
 
 # ------------------------------------------------------------------------------------------ round 2: weight-stream GEMM
+@pytest.mark.parametrize("B", [1, 2, 5])
+def test_decode_step_fusions_bit_identical(ops, B):
+    """uvx_gemv_fused_bf16 (RMSNorm / SwiGLU in the prologue) and uvx_rope_kv_append against the separate kernels they replace in the
+    decode step: same roundings, same fp32 summation order -> identical bits."""
+    K, N, Fh = 4096, 1024, 2048
+    x, w, nw, r = rnd(B, K, seed=1), rnd(N, K, scale=0.03, seed=2), rnd(K, seed=3), rnd(B, N, seed=4)
+    want = ops.gemv(ops.rmsnorm(x, nw, 1e-5), w, residual=r)
+    assert torch.equal(ops.gemv(x, w, residual=r, norm=(nw, 1e-5)), want)
+    gu, w2 = rnd(B, 2 * Fh, seed=5), rnd(N, Fh, scale=0.03, seed=6)
+    want = ops.gemv(ops.swiglu(gu, gate_first=True), w2, residual=r)
+    assert torch.equal(ops.gemv(gu, w2, residual=r, swiglu=True), want)
+    Hq, Hkv, D, smax = 8, 2, 128, 40
+    qkv = rnd(B, (Hq + 2 * Hkv) * D, seed=7)
+    inv = ops.llama3_inv_freq(D, 500000.0, None)
+    cos, sin = ops.rope_tables(inv, 64, "cuda")
+    rope_pos = torch.randint(0, 60, (B,), dtype=torch.int32, device="cuda")
+    slot = torch.randint(0, smax, (B,), dtype=torch.int32, device="cuda")
+    a, b = qkv.clone(), qkv.clone()
+    kc1, vc1 = torch.zeros(B, smax, Hkv, D, dtype=BF, device="cuda"), torch.zeros(B, smax, Hkv, D, dtype=BF, device="cuda")
+    kc2, vc2 = kc1.clone(), vc1.clone()
+    ops.rope_(a, Hq, Hkv, D, cos, sin, rows_per_seq=1, positions=rope_pos)
+    ops.kv_append(a, kc1, vc1, slot, Hq, Hkv, D)
+    ops.rope_kv_append_(b, Hq, Hkv, D, cos, sin, rope_pos, kc2, vc2, slot)
+    assert torch.equal(a, b) and torch.equal(kc1, kc2) and torch.equal(vc1, vc2)
+
+
 def _tile_ref(w, R, interleave):
     N, K = w.shape
     n_tiles = -(-N // R)

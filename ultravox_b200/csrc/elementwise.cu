@@ -161,6 +161,55 @@ __global__ void kv_append_kernel(const bf16* __restrict__ qkv, int64_t row_strid
   }
 }
 
+
+// One launch for the two row-local steps between the q|k|v projection and the attention of a decode step: RoPE on the q and k heads
+// (in place, same arithmetic as rope_kernel) and the append of the rotated k and of v to the static KV cache at positions[b].
+__global__ void rope_kv_append_kernel(bf16* __restrict__ qkv, int64_t row_stride, int Hq, int Hkv, int D,
+                                      const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
+                                      const int32_t* __restrict__ rope_pos, bf16* __restrict__ k_cache, bf16* __restrict__ v_cache,
+                                      int64_t cache_batch_stride, const int32_t* __restrict__ positions, int64_t B) {
+  pdl_trigger();
+  pdl_wait();
+  const int half = D / 2;
+  const int vec_per_head = half / 8;
+  const int heads = Hq + 2 * Hkv;
+  const int kv_width = Hkv * D;
+  const int64_t total = B * heads * vec_per_head;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int jv = (int)(idx % vec_per_head);
+    const int h = (int)((idx / vec_per_head) % heads);
+    const int64_t b = idx / ((int64_t)vec_per_head * heads);
+    bf16* base = qkv + b * row_stride + (int64_t)h * D + jv * 8;
+    const int64_t slot = (int64_t)positions[b];
+    if (h >= Hq + Hkv) {   // v head: copy both halves
+      bf16* dst = v_cache + b * cache_batch_stride + slot * kv_width + (int64_t)(h - Hq - Hkv) * D + jv * 8;
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(base);
+      *reinterpret_cast<uint4*>(dst + half) = *reinterpret_cast<const uint4*>(base + half);
+      continue;
+    }
+    const int64_t pos = (int64_t)rope_pos[b];
+    float x1[8], x2[8], c[8], sn[8], o1[8], o2[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(base), x1);
+    unpack8(*reinterpret_cast<const bf16x8*>(base + half), x2);
+    const float4* cp = reinterpret_cast<const float4*>(cos_tab + pos * half + jv * 8);
+    const float4* sp = reinterpret_cast<const float4*>(sin_tab + pos * half + jv * 8);
+    *reinterpret_cast<float4*>(c) = cp[0];
+    *reinterpret_cast<float4*>(c + 4) = cp[1];
+    *reinterpret_cast<float4*>(sn) = sp[0];
+    *reinterpret_cast<float4*>(sn + 4) = sp[1];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) rope_pair(x1[e], x2[e], c[e], sn[e], o1[e], o2[e]);
+    const bf16x8 p1 = pack8(o1), p2 = pack8(o2);
+    *reinterpret_cast<bf16x8*>(base) = p1;
+    *reinterpret_cast<bf16x8*>(base + half) = p2;
+    if (h >= Hq) {         // k head: the rotated row also goes to the cache
+      bf16* dst = k_cache + b * cache_batch_stride + slot * kv_width + (int64_t)(h - Hq) * D + jv * 8;
+      *reinterpret_cast<bf16x8*>(dst) = p1;
+      *reinterpret_cast<bf16x8*>(dst + half) = p2;
+    }
+  }
+}
+
 __global__ void add_i32_kernel(int32_t* __restrict__ a, int32_t* __restrict__ b2, int64_t n, int32_t delta) {
   pdl_trigger();
   pdl_wait();
@@ -308,6 +357,19 @@ extern "C" int uvx_kv_append(const void* qkv, int64_t row_stride, int64_t k_col,
   const int64_t total = B * (kv_width / 8) * 2;
   launch_k(kv_append_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)qkv, row_stride, (int)k_col, (int)v_col, (int)kv_width, (bf16*)k_cache, (bf16*)v_cache, cache_batch_stride, positions, B);
   return check_launch("kv_append_kernel");
+}
+
+
+extern "C" int uvx_rope_kv_append(void* qkv, int64_t B, int64_t row_stride, int Hq, int Hkv, int D, const float* cos_tab,
+                                  const float* sin_tab, const int32_t* rope_positions, void* k_cache, void* v_cache,
+                                  int64_t cache_batch_stride, const int32_t* positions, uvx_stream_t stream) {
+  using namespace uvx;
+  UVX_REQUIRE(qkv && cos_tab && sin_tab && rope_positions && k_cache && v_cache && positions, "uvx_rope_kv_append: null pointer");
+  UVX_REQUIRE(D % 16 == 0 && row_stride % 8 == 0 && cache_batch_stride % 8 == 0 && B >= 1, "uvx_rope_kv_append: alignment");
+  const int64_t total = B * (Hq + 2 * Hkv) * (D / 16);
+  launch_k(rope_kv_append_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, (bf16*)qkv, row_stride, Hq,
+           Hkv, D, cos_tab, sin_tab, rope_positions, (bf16*)k_cache, (bf16*)v_cache, cache_batch_stride, positions, B);
+  return check_launch("rope_kv_append_kernel");
 }
 
 extern "C" int uvx_add_i32(int32_t* a, int32_t* b, int64_t n, int32_t delta, uvx_stream_t stream) {

@@ -116,16 +116,53 @@ template <int B>
 __global__ void __launch_bounds__(kLmWarps * 32) gemv_kernel(const bf16* __restrict__ x, int64_t x_row_stride,
                                                              const bf16* __restrict__ W, int64_t w_row_stride, int64_t N,
                                                              int64_t K, const bf16* __restrict__ R, int64_t r_row_stride,
-                                                             void* __restrict__ out, int64_t o_row_stride, int out_f32) {
+                                                             void* __restrict__ out, int64_t o_row_stride, int out_f32,
+                                                             const bf16* __restrict__ norm_w, float norm_eps, int swiglu) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ uint8_t lm_smem[];
+  __shared__ float red[32];
   bf16* xs = reinterpret_cast<bf16*>(lm_smem);  // [B][K]
+  // Fused prologues of the decode step (every CTA stages the B activation rows anyway): act_fn(gate) * up of the row [gate | up]
+  // (LlamaMLP, same rounding as uvx_swiglu), or LlamaRMSNorm of the row (same rounding AND the same fp32 summation order as
+  // uvx_rmsnorm: 256 threads, element j = thread + 256 i, block_sum) - two launches per layer less, bit-identical results.
   for (int64_t i = threadIdx.x; i < (int64_t)B * K / 8; i += blockDim.x) {
     const int64_t b = i / (K / 8), j = i % (K / 8);
-    reinterpret_cast<uint4*>(xs)[i] = *reinterpret_cast<const uint4*>(x + b * x_row_stride + j * 8);
+    if (swiglu) {
+      float g[8], u[8], o[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(x + b * x_row_stride + j * 8), g);
+      unpack8(*reinterpret_cast<const bf16x8*>(x + b * x_row_stride + K + j * 8), u);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = __bfloat162float(__float2bfloat16_rn(silu(g[e]))) * u[e];
+      reinterpret_cast<bf16x8*>(xs)[i] = pack8(o);
+    } else {
+      reinterpret_cast<uint4*>(xs)[i] = *reinterpret_cast<const uint4*>(x + b * x_row_stride + j * 8);
+    }
   }
   __syncthreads();
+  if (norm_w) {
+    const int nv = (int)(K / 8);
+    for (int b = 0; b < B; ++b) {
+      bf16* xr = xs + (int64_t)b * K;
+      float sq = 0.f;
+      for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+        float v[8];
+        unpack8(reinterpret_cast<const bf16x8*>(xr)[j], v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sq += v[e] * v[e];
+      }
+      const float rstd = rsqrtf(block_sum(sq, red) / (float)K + norm_eps);
+      for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+        float v[8], wv[8], o[8];
+        unpack8(reinterpret_cast<const bf16x8*>(xr)[j], v);
+        unpack8(*reinterpret_cast<const bf16x8*>(norm_w + (int64_t)j * 8), wv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = wv[e] * __bfloat162float(__float2bfloat16_rn(v[e] * rstd));
+        reinterpret_cast<bf16x8*>(xr)[j] = pack8(o);
+      }
+    }
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * kLmWarps + (threadIdx.x >> 5);
   const int64_t total_warps = (int64_t)gridDim.x * kLmWarps;
@@ -162,7 +199,8 @@ __global__ void __launch_bounds__(kLmWarps * 32) gemv_kernel(const bf16* __restr
 
 template <int B>
 static int launch_gemv(const bf16* x, int64_t xs, const bf16* W, int64_t ws, int64_t N, int64_t K, const bf16* R, int64_t rs,
-                       void* out, int64_t os, int out_f32, cudaStream_t st) {
+                       void* out, int64_t os, int out_f32, cudaStream_t st, const bf16* norm_w = nullptr, float norm_eps = 0.f,
+                       int swiglu = 0) {
   const size_t smem = (size_t)B * K * 2;
   static bool attr = false;
   if (!attr && smem > 48 * 1024) {
@@ -171,7 +209,7 @@ static int launch_gemv(const bf16* x, int64_t xs, const bf16* W, int64_t ws, int
   }
   int64_t blocks = (N + kLmWarps - 1) / kLmWarps;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_k(gemv_kernel<B>, dim3((unsigned)blocks), dim3(kLmWarps * 32), smem, st, x, xs, W, ws, N, K, R, rs, out, os, out_f32);
+  launch_k(gemv_kernel<B>, dim3((unsigned)blocks), dim3(kLmWarps * 32), smem, st, x, xs, W, ws, N, K, R, rs, out, os, out_f32, norm_w, norm_eps, swiglu);
   return check_launch("gemv_kernel");
 }
 
@@ -241,6 +279,29 @@ extern "C" int uvx_gemv_bf16(const void* x, int64_t B, int64_t x_row_stride, con
     case 6: return launch_gemv<6>(xp, x_row_stride, wp, w_row_stride, N, K, rp, r_row_stride, out, o_row_stride, out_f32, st);
     case 7: return launch_gemv<7>(xp, x_row_stride, wp, w_row_stride, N, K, rp, r_row_stride, out, o_row_stride, out_f32, st);
     default: return launch_gemv<8>(xp, x_row_stride, wp, w_row_stride, N, K, rp, r_row_stride, out, o_row_stride, out_f32, st);
+  }
+}
+
+extern "C" int uvx_gemv_fused_bf16(const void* x, int64_t B, int64_t x_row_stride, const void* W, int64_t w_row_stride, int64_t N,
+                                   int64_t K, const void* R, int64_t r_row_stride, void* out, int64_t o_row_stride, int out_f32,
+                                   const void* norm_w, float norm_eps, int swiglu, uvx_stream_t stream) {
+  using namespace uvx;
+  UVX_REQUIRE(x && W && out, "uvx_gemv_fused_bf16: null pointer");
+  UVX_REQUIRE(B >= 1 && B <= kLmMaxB && K % 8 == 0 && x_row_stride % 8 == 0 && w_row_stride % 8 == 0,
+              "uvx_gemv_fused_bf16: 1 <= B <= %d and K %% 8 == 0 required", kLmMaxB);
+  UVX_REQUIRE((size_t)B * K * 2 <= 200 * 1024, "uvx_gemv_fused_bf16: B * K too large for shared memory (split the batch)");
+  cudaStream_t st = (cudaStream_t)stream;
+  UVX_REQUIRE(!(norm_w && swiglu), "uvx_gemv_fused_bf16: one prologue at a time");
+  const bf16 *xp = (const bf16*)x, *wp = (const bf16*)W, *rp = (const bf16*)R, *nw = (const bf16*)norm_w;
+  switch (B) {
+    case 1: return launch_gemv<1>(xp, x_row_stride, wp, w_row_stride, N, K, rp, r_row_stride, out, o_row_stride, out_f32, st, nw, norm_eps, swiglu);
+    case 2: return launch_gemv<2>(xp, x_row_stride, wp, w_row_stride, N, K, rp, r_row_stride, out, o_row_stride, out_f32, st, nw, norm_eps, swiglu);
+    case 3: return launch_gemv<3>(xp, x_row_stride, wp, w_row_stride, N, K, rp, r_row_stride, out, o_row_stride, out_f32, st, nw, norm_eps, swiglu);
+    case 4: return launch_gemv<4>(xp, x_row_stride, wp, w_row_stride, N, K, rp, r_row_stride, out, o_row_stride, out_f32, st, nw, norm_eps, swiglu);
+    case 5: return launch_gemv<5>(xp, x_row_stride, wp, w_row_stride, N, K, rp, r_row_stride, out, o_row_stride, out_f32, st, nw, norm_eps, swiglu);
+    case 6: return launch_gemv<6>(xp, x_row_stride, wp, w_row_stride, N, K, rp, r_row_stride, out, o_row_stride, out_f32, st, nw, norm_eps, swiglu);
+    case 7: return launch_gemv<7>(xp, x_row_stride, wp, w_row_stride, N, K, rp, r_row_stride, out, o_row_stride, out_f32, st, nw, norm_eps, swiglu);
+    default: return launch_gemv<8>(xp, x_row_stride, wp, w_row_stride, N, K, rp, r_row_stride, out, o_row_stride, out_f32, st, nw, norm_eps, swiglu);
   }
 }
 

@@ -188,28 +188,36 @@ class DecodeEngine:
         lm, tc = m.language_model, m.config.text_config
         nq, nkv, hd, Dm = tc.num_attention_heads, tc.num_key_value_heads, lm.head_dim, tc.hidden_size
         B = self.B
-        # one or two streams: matrix-vector kernels (fp32 FMAs on the CUDA cores keep up with the weight stream); more streams: the
-        # tcgen05 GEMM (at B = 8 the FMA work per weight byte is 8x and the GEMV is instruction-bound: 19.6 vs ~5 ms per step on 8B)
-        gemv = ops.gemv if B <= GEMV_MAX_B else (lambda x, w, residual=None: ops.linear(x, w, residual=residual))
+        # one stream: matrix-vector kernels (fp32 FMAs on the CUDA cores keep up with the weight stream) with RMSNorm / SwiGLU fused
+        # into their prologues; more streams: the tcgen05 GEMM (at B = 8 the FMA work per weight byte is 8x and the GEMV is
+        # instruction-bound: 19.6 vs 5.0 ms per step on the 8B backbone, profiles/r2_decode_sweep_v2.txt)
+        one = B <= GEMV_MAX_B
+        eps = tc.rms_norm_eps
         h = ops.embed_splice(self.token, lm.model.embed_tokens.weight, None, None).view(B, Dm)
         smax = self.cache.k.shape[2]
         for li, layer in enumerate(lm.model.layers):
             sa, mlp = layer.self_attn, layer.mlp
-            x = ops.rmsnorm(h, layer.input_layernorm.weight, tc.rms_norm_eps)
-            qkv = gemv(x, sa.qkv_w)
-            ops.rope_(qkv, nq, nkv, hd, self.cos, self.sin, rows_per_seq=1, positions=self.rope_pos)
             kc, vc = self.cache.k[li], self.cache.v[li]
-            ops.kv_append(qkv, kc, vc, self.pos, nq, nkv, hd)
+            if one:     # RMSNorm rides in the matrix-vector kernel's prologue
+                qkv = ops.gemv(h, sa.qkv_w, norm=(layer.input_layernorm.weight, eps))
+            else:
+                qkv = ops.linear(ops.rmsnorm(h, layer.input_layernorm.weight, eps), sa.qkv_w)
+            ops.rope_kv_append_(qkv, nq, nkv, hd, self.cos, self.sin, self.rope_pos, kc, vc, self.pos)
             att = torch.empty(B, nq * hd, dtype=torch.bfloat16, device=h.device)
             rs = qkv.stride(0)
             ops.attention(qkv.data_ptr(), kc.data_ptr(), vc.data_ptr(), att, B, nq, nkv, 1, smax, hd,
                           (rs, rs, nkv * hd, smax * nkv * hd, nkv * hd, smax * nkv * hd, nq * hd, nq * hd), hd ** -0.5, False,
                           self.lens, 0, self.kv_start)
-            h = gemv(att, sa.o_proj.weight, residual=h)
-            x = ops.rmsnorm(h, layer.post_attention_layernorm.weight, tc.rms_norm_eps)
-            act = ops.swiglu(gemv(x, mlp.gate_up_w), gate_first=True)
-            h = gemv(act, mlp.down_proj.weight, residual=h)
-        hn = ops.rmsnorm(h, lm.model.norm.weight, tc.rms_norm_eps)
+            if one:
+                h = ops.gemv(att, sa.o_proj.weight, residual=h)
+                gu = ops.gemv(h, mlp.gate_up_w, norm=(layer.post_attention_layernorm.weight, eps))
+                h = ops.gemv(gu, mlp.down_proj.weight, residual=h, swiglu=True)         # act_fn(gate) * up in the prologue
+            else:
+                h = ops.linear(att, sa.o_proj.weight, residual=h)
+                x = ops.rmsnorm(h, layer.post_attention_layernorm.weight, eps)
+                act = ops.swiglu(ops.linear(x, mlp.gate_up_w), gate_first=True)
+                h = ops.linear(act, mlp.down_proj.weight, residual=h)
+        hn = ops.rmsnorm(h, lm.model.norm.weight, eps)
         self._pick(ops.lm_head(hn, lm.lm_head.weight))
 
     def step(self) -> torch.Tensor:

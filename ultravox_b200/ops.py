@@ -538,11 +538,25 @@ def adamw_(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, s
 
 # ------------------------------------------------------------------------------------------ decode step (a13)
 def gemv(x: torch.Tensor, w: torch.Tensor, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-         out_dtype=BF16) -> torch.Tensor:
-    """y = x @ w.T (+ residual) for x [B <= 8, K]: weight-streaming matrix-vector kernel (no tensor cores)."""
+         out_dtype=BF16, norm: Optional[tuple] = None, swiglu: bool = False) -> torch.Tensor:
+    """y = x @ w.T (+ residual) for x [B <= 8, K]: weight-streaming matrix-vector kernel (no tensor cores).  Fused prologues of the
+    decode step: ``norm=(weight, eps)`` -> y = RMSNorm(x) @ w.T; ``swiglu=True`` -> x is [B, 2K] = gate | up and
+    y = (act_fn(gate) * up) @ w.T - both bit-identical to the separate kernels."""
     _cuda(x, BF16, "x"), _cuda(w, BF16, "w")
-    B, K = x.shape
+    B = x.shape[0]
+    K = x.shape[1] // 2 if swiglu else x.shape[1]
     N = w.shape[0]
+    if norm is not None or swiglu:
+        if (200 * 1024) // (2 * K) < B or B > 8:            # (the fused form has no slab loop)
+            x = rmsnorm(x, norm[0], norm[1]) if norm is not None else globals()["swiglu"](x, gate_first=True)
+            return gemv(x, w, residual=residual, out=out, out_dtype=out_dtype)
+        if out is None:
+            out = torch.empty(B, N, dtype=out_dtype, device=x.device)
+        check(lib().uvx_gemv_fused_bf16(x.data_ptr(), B, x.stride(0), w.data_ptr(), w.stride(0), N, K, _p(residual),
+                                        residual.stride(0) if residual is not None else 0, out.data_ptr(), out.stride(0),
+                                        int(out.dtype == torch.float32), norm[0].data_ptr() if norm is not None else None,
+                                        float(norm[1]) if norm is not None else 0.0, int(swiglu), _stream()), "uvx_gemv_fused_bf16")
+        return out
     if out is None:
         out = torch.empty(B, N, dtype=out_dtype, device=x.device)
     slab = max(1, min(8, (200 * 1024) // (2 * K)))      # rows whose activations fit the kernel's shared memory
@@ -562,6 +576,15 @@ def kv_append(qkv: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, p
     B = qkv.shape[0]
     check(lib().uvx_kv_append(qkv.data_ptr(), qkv.stride(0), Hq * D, (Hq + Hkv) * D, Hkv * D, k_cache.data_ptr(),
                               v_cache.data_ptr(), k_cache.stride(0), positions.data_ptr(), B, _stream()), "uvx_kv_append")
+
+
+def rope_kv_append_(qkv: torch.Tensor, Hq: int, Hkv: int, D: int, cos: torch.Tensor, sin: torch.Tensor, rope_positions: torch.Tensor,
+                    k_cache: torch.Tensor, v_cache: torch.Tensor, positions: torch.Tensor) -> None:
+    """``rope_`` (per-row positions) + ``kv_append`` in one launch: the decode step's q / k rotation and cache append."""
+    B = qkv.shape[0]
+    check(lib().uvx_rope_kv_append(qkv.data_ptr(), B, qkv.stride(0), Hq, Hkv, D, cos.data_ptr(), sin.data_ptr(), rope_positions.data_ptr(),
+                                   k_cache.data_ptr(), v_cache.data_ptr(), k_cache.stride(0), positions.data_ptr(), _stream()),
+          "uvx_rope_kv_append")
 
 
 def add_i32_(a: torch.Tensor, b: Optional[torch.Tensor], delta: int) -> None:
