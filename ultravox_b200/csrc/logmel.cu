@@ -210,8 +210,7 @@ __global__ void __launch_bounds__(kThreads) logmel_power_kernel(const float* __r
       idx += 16 * k2;
       while (idx >= kNfft) idx -= kNfft;
     }
-    __syncwarp();
-    // (all stage-C reads of s_z are done per thread; s_pow aliases s_x, which nobody reads any more)
+    // (s_pow aliases s_x, which nobody has read since the barrier after stage A / B)
 #pragma unroll
     for (int f = 0; f < kFT; ++f) s_pow[f][k] = re[f] * re[f] + im[f] * im[f];
   }
