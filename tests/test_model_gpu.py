@@ -392,6 +392,24 @@ def test_processor_to_model_long_clip_two_chunks_device_mel_both_ways():
     assert rel(out_a.logits, ref_logits) < 3e-2
 
 
+def test_prefill_engine_long_clip_two_chunks():
+    """35 s clip -> two encoder chunks inside the CUDA-graph prefill engine: same token and logits as the eager
+    ``model.forward`` on the processor's output for the same waveform."""
+    from ultravox_b200.engine import PrefillEngine
+    from ultravox_b200.processing import MelSpec, UltravoxProcessor
+    cfg, model, sd, sh = build()
+    w = wave(3, 16000 * 35)
+    pb = UltravoxProcessor(MelSpec(feature_size=80), _Tok(), defer_mel=True)
+    bb = pb("a b c <|audio|> d e", audio=w, sampling_rate=16000)
+    assert bb["audio_token_len"].tolist() == [188, 32]
+    eng = PrefillEngine(model, 16000 * 35, bb["input_ids"], bb["audio_token_start_idx"], bb["audio_token_len"], bb["audio_batch_size"])
+    assert eng.chunked and eng.graph is not None
+    tok = eng.run_e2e(torch.from_numpy(w[None]).pin_memory()).clone()
+    out = model(logits_to_keep=1, **{k: v for k, v in bb.items()})
+    assert int(tok[0]) == int(out.logits.view(1, -1).argmax(-1))
+    assert torch.allclose(eng.logits, out.logits.view(1, -1), rtol=1e-5, atol=1e-5)
+
+
 def ref_t(a):
     return torch.from_numpy(np.asarray(a))
 

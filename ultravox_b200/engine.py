@@ -24,23 +24,32 @@ class PrefillEngine:
     def __init__(self, model: UltravoxModel, clip_samples: int, input_ids: torch.Tensor,
                  audio_token_start_idx: torch.Tensor, audio_token_len: torch.Tensor, audio_batch_size: torch.Tensor,
                  n_clips: Optional[int] = None, use_graph: bool = True):
-        """All index tensors follow the processor's output contract; one <=30 s chunk per clip."""
+        """All index tensors follow the processor's output contract (one entry per encoder CHUNK: a clip longer than the encoder
+        context of 3000 frames = 30 s is cut into chunks exactly like ``UltravoxProcessor._chunk_and_pad_audio``, ref
+        ultravox_processing.py:153-215; ``n_clips`` waveforms of ``clip_samples`` samples each)."""
+        from .processing import frame_chunks
         self.model = model
         dev = model.device
         hop = 160
         L = -(-clip_samples // hop) * hop
         T = L // hop
-        if T > model.audio_tower.max_context_length:
-            raise ValueError("PrefillEngine handles clips of at most 30 s (one encoder chunk per clip)")
-        N = int(n_clips if n_clips is not None else audio_token_start_idx.numel())
+        ctx = model.audio_tower.max_context_length
+        frames_clip = -(-clip_samples // hop)
+        chunks_per_clip = -(-frames_clip // ctx)
+        N = int(n_clips if n_clips is not None else audio_token_start_idx.numel() // chunks_per_clip)
+        self.chunked = chunks_per_clip > 1
         self.N, self.L, self.T = N, L, T
+        plan, _ = frame_chunks([frames_clip] * N, ctx)
+        if len(plan) != audio_token_start_idx.numel():
+            raise ValueError(f"{audio_token_start_idx.numel()} audio index entries for {len(plan)} encoder chunks")
+        self.frames_host = torch.full((N,), frames_clip, dtype=torch.int64)
         self.n_mels = model.audio_tower.n_mels
         self.wave = torch.zeros(N, L, dtype=torch.float32, device=dev)          # static input buffer
         self.input_ids = input_ids.to(dev).contiguous()
         self.start = audio_token_start_idx.to(dev, torch.int64).contiguous()
         self.tok_len = audio_token_len.to(dev, torch.int32).contiguous()
         self.abs = audio_batch_size.to(dev, torch.int64).reshape(-1).contiguous()
-        frames = torch.full((N,), -(-clip_samples // hop), dtype=torch.int64)
+        frames = torch.tensor([p[2] for p in plan], dtype=torch.int64)          # valid frames of every chunk
         self.kv_len = ((frames - 1) // 2 + 1).to(torch.int32).to(dev)             # encoder key lengths
         self.audio_lens_host = frames
         self.token = torch.zeros(self.input_ids.shape[0], dtype=torch.int64, device=dev)
@@ -68,7 +77,10 @@ class PrefillEngine:
     # the hot path, in order (each call is one libuvx kernel or a short sequence of them)
     def _step(self):
         m = self.model
-        tm = ops.logmel(self.wave, self.n_mels, want_f32=False, want_tm=True)
+        if self.chunked:     # log-mel once per clip (its max is per CLIP), then cut into 3000-frame chunks, continuation chunks zero-padded
+            tm = m.mel_chunks_from_waveforms(self.wave, self.frames_host)
+        else:
+            tm = ops.logmel(self.wave, self.n_mels, want_f32=False, want_tm=True)
         enc = m.encode_audio(tm, None, kv_len=self.kv_len)
         aud = m.project_audio(enc)
         B, S = self.input_ids.shape
