@@ -690,7 +690,8 @@ def ws_on():
 
 
 @pytest.mark.parametrize("M,N,K", [(201, 4096, 4096), (201, 6144, 4096), (201, 28672, 512), (201, 4096, 14336), (1, 4096, 4096), (16, 1024, 256),
-                                   (37, 192, 200), (256, 128, 64), (129, 320, 72), (77, 2048, 8192), (5, 16064, 512)])
+                                   (37, 192, 200), (256, 128, 64), (129, 320, 72), (77, 2048, 8192), (5, 16064, 512),
+                                   (8, 28672, 512), (2, 19200, 256), (8, 4096, 14336), (32, 28672, 4096)])
 def test_gemm_ws_plain_and_epilogues(ops, ws_on, M, N, K):
     """Rows <= 256 run the weight-streaming form (tokens on the UMMA N dimension, stream-K with in-kernel fix-up): fp32 math on
     the same bf16 inputs rounded once (1e-3), agreement with gemm_tc_kernel on the same call, run-to-run identical bits
