@@ -92,7 +92,7 @@ def test_gemm_forced_configs_and_split_k(ops, cfg, splits):
     assert torch.equal(y1, y2)  # split-K reduction order is fixed -> bitwise reproducible
 
 
-@pytest.mark.parametrize("cfg", [4128, 4256, 5416, 5512])
+@pytest.mark.parametrize("cfg", [4128, 4256, 5416, 5512, 9128])
 @pytest.mark.parametrize("M,N,K", [(256, 256, 64), (1500, 1280, 1280), (201, 512, 4096), (700, 768, 200)])
 def test_gemm_two_sm_pairs(ops, cfg, M, N, K):
     """cta_group::2 kernel (cluster of 2 CTAs, 256-row pair tiles; 5xxx = two accumulators per pair tile, ragged N),
@@ -108,6 +108,27 @@ def test_gemm_two_sm_pairs(ops, cfg, M, N, K):
         _lib.lib().uvx_debug_gemm_override(0, 0)
     assert rel(y, ref) < 1e-3
     assert rel(y32, x.float() @ w.float().T) < 1e-5
+
+
+def test_gemm_deep_k_one_wave_takes_the_pair_kernel(ops):
+    """The encoder fc2 shape (1500 x 1280 x 5120, bias + in-place residual) is routed to the 2-SM pair kernel with 8 epilogue warps:
+    fp32 math on the same inputs, and the same call on the 1-SM kernel (forced) within bf16 rounding."""
+    from ultravox_b200 import _lib
+    M, N, K = 1500, 1280, 5120
+    x, w, b, r = rnd(M, K, seed=1), rnd(N, K, scale=0.03, seed=2), rnd(N, seed=3), rnd(M, N, seed=4)
+    ref = x.float() @ w.float().T + b.float() + r.float()
+    h = r.clone()
+    ops.linear(x, w, bias=b, residual=h, out=h)
+    assert rel(h, ref) < 1e-3
+    _lib.lib().uvx_debug_gemm_override(1128, 1)
+    try:
+        h1 = r.clone()
+        ops.linear(x, w, bias=b, residual=h1, out=h1)
+    finally:
+        _lib.lib().uvx_debug_gemm_override(0, 0)
+    assert rel(h, h1.float()) < 2e-3
+    y = ops.linear(x, w, bias=b, act=ops.ACT_GELU)
+    assert rel(y, F.gelu(x.float() @ w.float().T + b.float())) < 1.5e-3
 
 
 def test_gemm_epilogues(ops):

@@ -1857,6 +1857,19 @@ extern "C" int uvx_gemm_bf16(const uvx_gemm_args* a, uvx_stream_t stream_) {
     cm = forced_cm;
     cn = forced_cn;
   }
+  // Deep-K, at most one wave of 128 x 128 tiles (the Whisper fc2: 1500 x 1280 x 5120 = 120 tiles): the 2-SM pair kernel (256 x 128
+  // pair tiles, each CTA stages its 128 rows of A and HALF of the weight tile, 8 epilogue warps) moves 25 % fewer bytes into shared
+  // memory per k-block and the main loop dominates - 22.8 vs 26.5 us (profiles/r2_enc_cfg_sweep2.txt).  Shallow-K shapes stay on the
+  // 1-SM kernel (their exposed epilogue is shorter there).
+  static int pair_fc2 = -1;
+  if (pair_fc2 < 0) {
+    const char* e = getenv("UVX_PAIR_DEEPK");
+    pair_fc2 = e ? atoi(e) : 1;
+  }
+  if (pair_fc2 && forced <= 0 && forced_splits <= 0 && forced_cm == 0 && g_gemm_dbg == 0 && a->a_batch == 1 && a->a_rows > 256 &&
+      a->N % 128 == 0 && a->K >= 4096 && ((a->a_rows + 127) / 128) * (a->N / 128) <= 148 && !a->w_tiled && !a->rope_cos &&
+      a->act != UVX_ACT_SWIGLU && !a->norm_w && !a->c_row_map && a->c_row_offset == 0 && a->out_dtype == UVX_DT_BF16)
+    cfg = 9128;
   UVX_REQUIRE(a->act != UVX_ACT_SWIGLU || (a->w_tiled == 208 && !a->bias && !a->R && !a->norm_w && a->out_dtype == UVX_DT_BF16 && a->N % 16 == 0),
               "uvx_gemm_bf16: UVX_ACT_SWIGLU needs the 208-row interleaved gate|up image, bf16 output, no bias / residual / norm");
   UVX_REQUIRE(!a->rope_cos || (a->rope_sin && a->a_batch == 1 && a->alpha == 1.0f && !a->bias && !a->R && a->act == UVX_ACT_NONE &&
@@ -1904,6 +1917,8 @@ extern "C" int uvx_gemm_bf16(const uvx_gemm_args* a, uvx_stream_t stream_) {
     case 1208: return launch_gemm<1, 208>(a, splits, cm, cn, stream);
     case 2208: return launch_gemm<2, 208>(a, splits, cm, cn, stream);
     case 4128: return launch_gemm_2sm<128, 1, 4>(a, stream);
+    case 9128: return launch_gemm_2sm<128, 1, 8>(a, stream);   // (tuning: 8 epilogue warps per CTA)
+    case 9256: return launch_gemm_2sm<256, 1, 8>(a, stream);
     case 4256: return launch_gemm_2sm<256, 1, 4>(a, stream);
     case 5416: return launch_gemm_2sm<208, 2, 4>(a, stream);   // 256 x 416 pair tiles (weight-streaming regime)
     case 5512: return launch_gemm_2sm<256, 2, 8>(a, stream);   // 256 x 512 pair tiles (tensor-bound regime)
